@@ -1,0 +1,63 @@
+// Error plumbing + small utility kernels shared by the C-ABI (include/spb200.h).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_last_error[512] = "";
+
+void spb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* spb_last_error() { return g_last_error; }
+
+extern "C" int spb_abi_version() { return 1; }
+
+namespace {
+
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n,
+                                        const uint8_t* __restrict__ rowmask, int row_len) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += stride) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        if (rowmask != nullptr && !rowmask[i / row_len]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    }
+    if (i < n && i + 3 >= n) {
+        for (int64_t j = i; j < n; ++j) {
+            float v = src[j];
+            if (rowmask != nullptr && !rowmask[j / row_len]) v = 0.f;
+            dst[j] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+}  // namespace
+
+// dst[i] = bf16(src[i]) (optionally zeroing whole rows of length row_len where rowmask is false;
+// row_len must be a multiple of 4 in that case).
+extern "C" int spb_cast_f32_bf16(const float* src, void* dst, int64_t n, const uint8_t* rowmask, int row_len,
+                                 cudaStream_t stream) {
+    if (n <= 0) return SPB_OK;
+    SPB_CHECK_ARG(src && dst, "spb_cast_f32_bf16: null pointer");
+    SPB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                  "spb_cast_f32_bf16: unaligned pointers");
+    SPB_CHECK_ARG(rowmask == nullptr || (row_len > 0 && row_len % 4 == 0), "spb_cast_f32_bf16: row_len must be a multiple of 4");
+    const int threads = 256;
+    int64_t blocks = (n / 4 + threads - 1) / threads;
+    int max_blocks = spb_num_sms() * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    cast_f32_to_bf16_kernel<<<(int)blocks, threads, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n, rowmask,
+                                                                 row_len > 0 ? row_len : 1);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}

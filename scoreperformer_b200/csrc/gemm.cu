@@ -1,0 +1,286 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = op(A)[M,K] * op(B)[N,K]^T  (+bias) (*rowmask) (+residual)
+//
+// This is the dense-contraction workhorse behind every Linear of the ScorePerformer step
+// (reference call sites: modules/transformer/attention.py:135-137,214; feedforward.py:19-21,56-61;
+//  models/scoreperformer/embeddings.py:134-143,253-255,345-353; modules/layers.py:41-47).
+//
+// Layout per CTA (192 threads, 2 CTAs/SM):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles, 128B swizzle, 3-stage mbarrier ring
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16; accumulator in TMEM
+//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> (bias) -> smem transpose -> (rowmask, residual) ->
+//                                coalesced bf16/fp32 stores, or fp32 atomics for split-K
+// Both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the MN-major
+// form feeds dgrad (B = W[out,in]) and wgrad (A = dY^T, B = X^T) without materialising transposes.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;       // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+    int M, N, K;
+    int kb_per_split;      // k-blocks handled by one blockIdx.z
+    void* C;
+    int ldc;
+    int c_fp32;            // 1: fp32 output, 0: bf16
+    int atomic;            // 1: red.add fp32 (split-K / accumulate)
+    const float* bias;     // [N] or null
+    const float* residual; // fp32 [M, ldr] or null
+    int ldr;
+    const uint8_t* rowmask;  // [M] (bool) or null
+};
+
+template <int BN>
+constexpr int gemm_smem_bytes() {
+    return STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 /*align slack*/ + 128 /*barriers*/;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    constexpr int B_STAGE_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM;
+    const int total_kb = (p.K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+    const int num_kb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[s], phase ^ 1);
+                uint8_t* sA = smem + s * STAGE_BYTES;
+                uint8_t* sB = sA + A_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                if (A_MN) {
+#pragma unroll
+                    for (int h = 0; h < BM / 64; ++h) tma_load_2d(sA + h * (BK * 128), &tmA, &full_bar[s], m0 + h * 64, kb * BK);
+                } else {
+                    tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(sB + h * (BK * 128), &tmB, &full_bar[s], n0 + h * 64, kb * BK);
+                } else {
+                    tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                }
+                if (++s == STAGES) { s = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+            // K-major: 8-row groups are 1024 B apart (SBO); LBO unused.  MN-major: 64-element MN atoms
+            // are BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+            constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
+            constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;   // bytes per UMMA_K step
+            constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+            int s = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < num_kb; ++i) {
+                mbar_wait(&full_bar[s], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t da = umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+                    const uint64_t db = umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (++s == STAGES) { s = 0; phase ^= 1; }
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+        const int q = warp & 3;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+        const int row_base = m0 + q * 32;
+        float* Cf = reinterpret_cast<float*>(p.C);
+        __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col = n0 + c * 32 + lane;
+            if (n0 + c * 32 >= p.N) break;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const bool col_ok = col < p.N;
+            const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + col) : 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const int row = row_base + r;
+                if (row >= p.M) break;
+                float val = stage[r * 33 + lane] + bias;
+                if (col_ok) {
+                    if (p.rowmask != nullptr) val = p.rowmask[row] ? val : 0.f;
+                    if (p.residual != nullptr) val += p.residual[(size_t)row * p.ldr + col];
+                    const size_t off = (size_t)row * p.ldc + col;
+                    if (p.atomic) atomicAdd(Cf + off, val);
+                    else if (p.c_fp32) Cf[off] = val;
+                    else Cb[off] = __float2bfloat16_rn(val);
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits, cudaStream_t stream) {
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN>()));
+        configured = true;
+    }
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), splits);
+    kern<<<grid, GEMM_THREADS, gemm_smem_bytes<BN>(), stream>>>(tmA, tmB, p);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+}  // namespace
+
+int spb_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                          uint32_t box_inner, uint32_t box_outer) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) {
+        spb_set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+        return SPB_ERR_DRIVER;
+    }
+    SPB_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer %p is not 16-byte aligned", base);
+    SPB_CHECK_ARG((row_stride_bytes & 15) == 0, "TMA row stride %llu B is not a multiple of 16",
+                  (unsigned long long)row_stride_bytes);
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        spb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)", (int)r,
+                      (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+                      box_outer);
+        return SPB_ERR_DRIVER;
+    }
+    return SPB_OK;
+}
+
+// C-ABI entry point; see include/spb200.h for the contract.
+extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
+                             int ldb, int ldc, const float* bias, const float* residual, int ldr, const uint8_t* rowmask,
+                             int c_fp32, int split_k, int accumulate, cudaStream_t stream) {
+    SPB_CHECK_ARG(A && B && C, "spb_gemm_bf16: null operand");
+    SPB_CHECK_ARG(M > 0 && N > 0 && K > 0, "spb_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    SPB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "spb_gemm_bf16: lda=%d / ldb=%d must be multiples of 8 (TMA 16 B rule)", lda,
+                  ldb);
+    SPB_CHECK_ARG(!(accumulate || split_k > 1) || c_fp32, "spb_gemm_bf16: split-K / accumulate need an fp32 C");
+
+    const int BN = (N <= 64) ? 64 : 128;
+    const int total_kb = ceil_div(K, BK);
+    int splits = 1;
+    if (split_k > 1) splits = split_k;
+    else if (split_k == 0 && c_fp32 && bias == nullptr && residual == nullptr && rowmask == nullptr) {
+        // auto split-K for tall-K / small-output problems (wgrad): aim at ~2 CTAs per SM
+        const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+        const int target = 2 * spb_num_sms();
+        if (tiles < spb_num_sms() && total_kb >= 8) splits = max(1, min(total_kb / 4, target / tiles));
+    }
+    int kb_per_split = ceil_div(total_kb, splits);
+    splits = ceil_div(total_kb, kb_per_split);
+
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (trans_a) rc = spb_make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK);
+    else rc = spb_make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
+    if (rc != SPB_OK) return rc;
+    if (trans_b) rc = spb_make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
+    else rc = spb_make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)BN);
+    if (rc != SPB_OK) return rc;
+
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.kb_per_split = kb_per_split;
+    p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
+    p.atomic = (splits > 1 || accumulate) ? 1 : 0;
+    p.bias = bias; p.residual = residual; p.ldr = ldr; p.rowmask = rowmask;
+
+    if (splits > 1 && !accumulate) {
+        if (ldc == N) SPB_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), stream));
+        else SPB_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, stream));
+    }
+
+#define SPB_DISPATCH(BN_)                                                                          \
+    if (trans_a && trans_b) return launch_gemm<BN_, true, true>(tmA, tmB, p, splits, stream);     \
+    if (trans_a) return launch_gemm<BN_, true, false>(tmA, tmB, p, splits, stream);               \
+    if (trans_b) return launch_gemm<BN_, false, true>(tmA, tmB, p, splits, stream);               \
+    return launch_gemm<BN_, false, false>(tmA, tmB, p, splits, stream);
+    if (BN == 64) { SPB_DISPATCH(64) }
+    SPB_DISPATCH(128)
+#undef SPB_DISPATCH
+}
