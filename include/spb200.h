@@ -1,0 +1,112 @@
+/* spb200.h -- C ABI of libspb200.so, the sm_100a kernel library behind scoreperformer_b200.
+ *
+ * The reference (ilya16/ScorePerformer) has no FFI: its hot path is PyTorch eager code behind the nn.Module API of
+ * `scoreperformer.models`.  This header is therefore the *new* bottom layer: each entry point
+ * replaces the PyTorch library calls made by the reference lines cited next to it.  A maintainer binds it with
+ * ctypes; scoreperformer_b200/lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative code (-1 bad argument, -2 CUDA runtime error, -3 driver API
+ *     error) and never throws; `spb_last_error()` returns the message for the calling thread;
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch tensors); the library allocates nothing;
+ *   - `stream` is the caller's current CUDA stream (cudaStream_t passed as void*); no call synchronises;
+ *   - bf16 buffers are `void*`, fp32 are `float*`, masks are `uint8_t*` (torch.bool), tokens/labels `int64_t*`;
+ *   - "ACCUMULATED" outputs are added to (the caller zero-initialises), everything else is overwritten;
+ *   - functions are re-entrant; the only global state is the cached driver entry point for TMA descriptor encoding.
+ */
+#ifndef SPB200_H
+#define SPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spb_stream_t; /* cudaStream_t */
+
+int spb_abi_version(void);
+const char* spb_last_error(void);
+
+/* fp32 -> bf16 cast (autocast's weight/activation casts); optionally zeroes rows where rowmask is false. */
+int spb_cast_f32_bf16(const float* src, void* dst, int64_t n, const uint8_t* rowmask, int row_len, spb_stream_t stream);
+
+/* out fp32 [n_cols] += column sums of x [n_rows, ld] (bias gradients of every Linear). */
+int spb_colsum(const void* x, int x_fp32, int ld, float* out, int n_rows, int n_cols, spb_stream_t stream);
+
+/* C[M,N] = alpha * op(A) op(B)^T (+bias[n]) (*rowmask[m]) (+residual[m,n]);  tcgen05/TMEM/TMA GEMM, bf16 in, fp32 accumulate.
+ *   trans_a = 0: A is row-major [M,K] (lda);  1: A is stored [K,M] (lda)        -- wgrad's dY^T
+ *   trans_b = 0: B is row-major [N,K] (ldb), i.e. an nn.Linear weight;  1: stored [K,N] (ldb)   -- dgrad / wgrad
+ *   c_fp32: output dtype; split_k: 0 auto, 1 off, >1 forced (fp32 C only); accumulate: add into C (fp32 only);
+ *   alpha: optional device scalar.
+ * Replaces: nn.Linear / F.linear / `@` in modules/transformer/attention.py:135-137,214, feedforward.py:19-21,56-61,
+ * modules/layers.py:41-47, models/scoreperformer/embeddings.py:134-143,253-255,345-353 and their autograd backward. */
+int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda, int ldb, int ldc,
+                  const float* bias, const float* residual, int ldr, const uint8_t* rowmask, int c_fp32, int split_k, int accumulate,
+                  const float* alpha, spb_stream_t stream);
+
+/* LayerNorm / AdaptiveLayerNorm over the last dim (256, 512, 1280 or 1536); pass (w,b) or gb = [gamma | beta] bf16 [n, 2*dim].
+ * Replaces nn.LayerNorm and modules/layers.py:31-47. */
+int spb_layer_norm_fwd(const void* x, int x_fp32, int ldx, const float* w, const float* b, const void* gb, int ldgb, void* y, int y_fp32,
+                       int ldy, float* mean, float* rstd, int n_rows, int dim, float eps, spb_stream_t stream);
+/* dx (= LN backward, + dres if given); dw/db ACCUMULATED (affine) or dgb written (adaptive). */
+int spb_layer_norm_bwd(const void* dy, int lddy, const void* x, int x_fp32, int ldx, const float* mean, const float* rstd, const float* w,
+                       const void* gb, int ldgb, const float* dres, int lddres, void* dx, int dx_fp32, int lddx, float* dw, float* db,
+                       void* dgb, int lddgb, int n_rows, int dim, spb_stream_t stream);
+
+/* GLU(SiLU) + dropout: u bf16 [n, 2*hidden] -> h bf16 [n, hidden] (modules/transformer/feedforward.py:13-22,56-61). */
+int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, spb_stream_t stream);
+/* du bf16 [n, 2*hidden]; dbias fp32 [2*hidden] ACCUMULATED (may be NULL). */
+int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p, uint64_t seed,
+                spb_stream_t stream);
+
+/* Fused SPMuple tuple-token embedding: out[n, F*128] = LayerNorm(cat_f table[off_f + tokens[n,f]]) in bf16.
+ * table fp32 [sum V_f, 128] is the concatenation of the computed per-field tables (modules/transformer/embeddings.py:91-143).
+ * Replaces models/scoreperformer/embeddings.py:121-143 (12 gathers + cat + LayerNorm). */
+int spb_embed_ln_fwd(const int64_t* tokens, int ld_tok, const float* table, const int* field_sizes, int n_fields, const float* w,
+                     const float* b, void* out, int ld_out, float* mean, float* rstd, int n_rows, float eps, spb_stream_t stream);
+/* dtable / dw / db ACCUMULATED; c1, c2 fp32 [n] scratch.  PAD rows (token 0) receive no gradient (padding_idx=0). */
+int spb_embed_ln_bwd(const void* dy, int ld_dy, const int64_t* tokens, int ld_tok, const float* table, const int* field_sizes,
+                     int n_fields, const float* w, const float* mean, const float* rstd, float* c1, float* c2, float* dtable, float* dw,
+                     float* db, int n_rows, spb_stream_t stream);
+
+/* Fused MQA attention with learned-slope ALiBi, key padding, causal mask and dropout; qkv bf16 [B*T, ld] = q(H*64) | k(64) | v(64).
+ * lse fp32 [B,H,T] is saved for the backward.  Replaces modules/transformer/attend.py:58-126 + attention.py:139-197. */
+int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, void* out, int ld_out, float* lse, int B,
+                      int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed, spb_stream_t stream);
+/* dqkv bf16 [B*T, ld_dqkv] in the qkv column layout; delta fp32 [B,H,T] scratch; dlogslopes fp32 [H] ACCUMULATED. */
+int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out, const void* dout,
+                      int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv, float* dlogslopes, int B, int T, int H,
+                      int dim_head, int causal, float dropout_p, uint64_t seed, spb_stream_t stream);
+
+/* One level of the hierarchical MMD-VAE style encoder (models/scoreperformer/mmd_transformer.py:304-368):
+ * segmented mean over cat(hidden*mask, style[:, :w_style]) -> Linear -> latents_mask -> broadcast back into style[:, col0:col0+z].
+ * pooled fp32 [B*S,320] and counts int32 [B*S] must be zeroed; segments == NULL selects mode 'mean' (S == 2, slot 1). */
+int spb_latent_level_fwd(const float* hidden, const float* style_in, int ld_style, const uint8_t* mask, const int64_t* segments,
+                         const float* W, const float* bias, float* pooled, int* counts, float* latents, uint8_t* lmask, float* style_out,
+                         int col0, int B, int T, int S, int d_hidden, int w_style, int z, spb_stream_t stream);
+int spb_latent_level_bwd(float* d_style, int ld_style, int col0, const float* dlat_direct, const uint8_t* mask, const int64_t* segments,
+                         const float* W, const float* pooled, const int* counts, const uint8_t* lmask, float* dlat, float* dpooled,
+                         float* d_hidden, float* dW, float* dbias, int B, int T, int S, int d_hidden_dim, int w_style, int z,
+                         spb_stream_t stream);
+
+/* Fused pairwise-RBF MMD (mmd_transformer.py:505-534): loss and d loss / d y in one pass, no [n,n,d] tensor. */
+int spb_mmd_fwd_bwd(const float* z_prior, const float* y, const uint8_t* w, int n_z, int n_y, int d, float* coef, float* loss,
+                    float* grad_y, spb_stream_t stream);
+
+/* Masked cross-entropy over one field's logits (models/scoreperformer/wrappers.py:49-59): loss_sum/count ACCUMULATED,
+ * optional unscaled dlogits = softmax - onehot (bf16) and argmax. */
+int spb_ce_rows(const float* logits, int ld, const int64_t* labels, int ld_lab, int V, long long ignore_index, float* loss_sum,
+                float* count, void* dlogits, int ld_d, int* argmax_out, int n_rows, spb_stream_t stream);
+
+/* Direction-classifier heads (models/classifiers/model.py:74-82,202-216): Dropout -> Linear(in_dim, C_g) -> weighted CE. */
+int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, const int64_t* labels, int ld_lab, const float* W, const float* bias,
+                  const float* class_w, const int* n_classes, int n_heads, float* num, float* den, const float* dlogit_scale, float* dW,
+                  float* db, float* dl_scratch, int n_rows, int in_dim, float dropout_p, uint64_t seed, int backward, spb_stream_t stream);
+int spb_clf_logits(const float* x, int ldx, const float* W, const float* bias, float* out, int n_rows, int in_dim, int total,
+                   spb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPB200_H */

@@ -61,3 +61,50 @@ extern "C" int spb_cast_f32_bf16(const float* src, void* dst, int64_t n, const u
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
+
+namespace {
+
+// out[c] += sum_r x[r, c];  thread owns 2 adjacent columns, 8 row-lanes per block, rows split over blockIdx.y
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, int n_rows, int n_cols, int rows_per_block) {
+    __shared__ float red[8][64];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 2;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+    float s0 = 0.f, s1 = 0.f;
+    if (c < n_cols) {
+        const bool pair = (c + 1 < n_cols);
+        for (int r = r0 + ty; r < r1; r += 8) {
+            s0 += (float)x[(size_t)r * ld + c];
+            if (pair) s1 += (float)x[(size_t)r * ld + c + 1];
+        }
+    }
+    red[ty][tx * 2] = s0;
+    red[ty][tx * 2 + 1] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        const int cc = blockIdx.x * 64 + threadIdx.x;
+        if (cc < n_cols && s != 0.f) atomicAdd(out + cc, s);
+    }
+}
+
+}  // namespace
+
+// out fp32 [n_cols] += column sums of x [n_rows, ld] (bias gradients).  x_fp32 selects the input dtype.
+extern "C" int spb_colsum(const void* x, int x_fp32, int ld, float* out, int n_rows, int n_cols, cudaStream_t stream) {
+    if (n_rows <= 0 || n_cols <= 0) return SPB_OK;
+    SPB_CHECK_ARG(x && out, "spb_colsum: null pointer");
+    int chunks = ceil_div(2 * spb_num_sms(), ceil_div(n_cols, 64));
+    int rows_per_block = ceil_div(n_rows, chunks);
+    if (rows_per_block < 64) rows_per_block = 64;
+    chunks = ceil_div(n_rows, rows_per_block);
+    dim3 grid(ceil_div(n_cols, 64), chunks);
+    if (x_fp32) colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ld, out, n_rows, n_cols, rows_per_block);
+    else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, n_rows, n_cols, rows_per_block);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}

@@ -1,0 +1,576 @@
+// Fused multi-query attention (1 KV head shared by H query heads) with in-kernel learned-slope ALiBi,
+// key-padding + causal masking and dropout: forward and backward, flash style (no [T,T] tensor in HBM).
+//
+// Reference semantics: modules/transformer/attention.py:107-222 (MQA projections, masks, ALiBi) and
+// modules/transformer/attend.py:58-126 (additive bias with masked fill, softmax, dropout, P@V).
+//   S_ij = scale * q_i.k_j - slope_h * |i - j|     (modules/transformer/embeddings.py:294-325, symmetric)
+//   masked (padded key, or j > i when causal) entries are excluded from the softmax
+// Round-1 implementation: bf16 mma.sync.m16n8k16 with ldmatrix from XOR-swizzled shared memory tiles and
+// cp.async double buffering; the tcgen05/TMEM version is the next step.
+//
+// Layout: qkv bf16 [B*T, ld] with q at columns [0, H*64), k at [H*64, H*64+64), v at [H*64+64, H*64+128).
+#include "common.cuh"
+
+namespace {
+
+constexpr int DH = 64;
+constexpr int TQ = 64;   // queries per CTA
+constexpr int TK = 64;   // keys per tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnParams {
+    const __nv_bfloat16* qkv;
+    int ld;                      // row stride of qkv (elements)
+    const uint8_t* key_mask;     // [B, T] or null
+    const float* logslopes;      // [H]
+    int B, T, H;
+    float scale;
+    int causal;
+    float dropout_p;
+    uint64_t seed;
+    uint32_t drop_thresh24;
+    float keep_scale;
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A 64x64 bf16 tile: row r at r*128 B, 16-byte chunk c stored at chunk (c ^ (r & 7)).
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
+    return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
+// Load a [64 rows x 64 cols] bf16 tile from global (row stride ld) starting at (row0, col0); rows >= n_valid zero-filled.
+__device__ __forceinline__ void load_tile_async(void* smem, const __nv_bfloat16* g, int ld, int row0, int col0, int row_limit) {
+    const uint32_t base = smem_u32(smem);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = threadIdx.x + i * 128;
+        const int r = idx >> 3, c = idx & 7;
+        const bool ok = (row0 + r) < row_limit;
+        const __nv_bfloat16* src = g + (size_t)(ok ? row0 + r : 0) * ld + col0 + c * 8;
+        const uint32_t dst = tile_addr(base, r, c);
+        const int bytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+}
+
+// A fragments (16 rows x 64 k) of a row-major tile: frag[ks][0..3] for the 4 k-steps.
+__device__ __forceinline__ void load_a_frags(uint32_t base, int row0, int lane, uint32_t frag[4][4]) {
+    const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(tile_addr(base, r, ks * 2 + (lane >> 4)), frag[ks][0], frag[ks][1], frag[ks][2], frag[ks][3]);
+}
+
+// acc[nt][4] (16 x 64) = A(16 x 64k) * Tile^T where Tile is [n=64][k=64] row-major ("K-like": rows are n).
+__device__ __forceinline__ void mma_a_tile_nt(float acc[8][4], const uint32_t a[4][4], uint32_t tile, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {   // two k-steps per ldmatrix.x4
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(tile_addr(tile, nt * 8 + (lane & 7), kp * 4 + (lane >> 3)), b0, b1, b2, b3);
+            mma16816(acc[nt], a[kp * 2], b0, b1);
+            mma16816(acc[nt], a[kp * 2 + 1], b2, b3);
+        }
+    }
+}
+// acc[nt][4] (16 x 64n) += P(16 x 64k, as A fragments pf[ks]) * Tile where Tile is [k=64][n=64] row-major ("V-like").
+__device__ __forceinline__ void mma_p_tile_nn(float acc[8][4], const uint32_t pf[4][4], uint32_t tile, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {   // two n-blocks per ldmatrix.x4.trans
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(tile_addr(tile, ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)), b0, b1, b2, b3);
+            mma16816(acc[np * 2], pf[ks], b0, b1);
+            mma16816(acc[np * 2 + 1], pf[ks], b2, b3);
+        }
+    }
+}
+// pack a 16x64 fp32 accumulator into A fragments for the next MMA
+__device__ __forceinline__ void acc_to_frags(const float acc[8][4], uint32_t pf[4][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        pf[ks][0] = pack_bf16x2(acc[2 * ks][0], acc[2 * ks][1]);
+        pf[ks][1] = pack_bf16x2(acc[2 * ks][2], acc[2 * ks][3]);
+        pf[ks][2] = pack_bf16x2(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+        pf[ks][3] = pack_bf16x2(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- forward
+// grid (ceil(T/64), H, B), 128 threads; warp w owns query rows [16w, 16w+16) of the tile.
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float* __restrict__ lse_out) {
+    __shared__ __align__(128) uint8_t sQ[TQ * 128];
+    __shared__ __align__(128) uint8_t sK[2][TK * 128];
+    __shared__ __align__(128) uint8_t sV[2][TK * 128];
+    __shared__ uint8_t sMask[2][TK];
+
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T;
+    const int q0 = qt * TQ;
+    const int kcol = p.H * DH, vcol = kcol + DH;
+    const __nv_bfloat16* base = p.qkv + (size_t)b * T * p.ld;
+    const float slope = __expf(p.logslopes[h]) * LOG2E;
+    const float scale2 = p.scale * LOG2E;
+
+    const int n_kt = p.causal ? min(qt + 1, ceil_div(T, TK)) : ceil_div(T, TK);
+
+    auto load_kv = [&](int kt, int buf) {
+        load_tile_async(sK[buf], base, p.ld, kt * TK, kcol, T);
+        load_tile_async(sV[buf], base, p.ld, kt * TK, vcol, T);
+        if (threadIdx.x < TK) {
+            const int j = kt * TK + threadIdx.x;
+            sMask[buf][threadIdx.x] = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+        }
+    };
+
+    load_tile_async(sQ, base, p.ld, q0, h * DH, T);
+    load_kv(0, 0);
+    cp_async_commit();
+
+    float o_acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    uint32_t qf[4][4];
+    const int r_lo = q0 + warp * 16 + (lane >> 2);   // this thread's rows: r_lo and r_lo + 8
+
+    for (int kt = 0; kt < n_kt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_kt) load_kv(kt + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (kt == 0) load_a_frags(smem_u32(sQ), warp * 16, lane, qf);
+
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+        mma_a_tile_nt(s, qf, smem_u32(sK[buf]), lane);
+
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int jl = nt * 8 + (lane & 3) * 2 + (e & 1);
+                const int j = kt * TK + jl;
+                const int i = r_lo + (e >> 1) * 8;
+                const bool ok = sMask[buf][jl] && (!p.causal || j <= i);
+                const float v = ok ? s[nt][e] * scale2 - slope * fabsf((float)(i - j)) : -INFINITY;
+                s[nt][e] = v;
+                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+        }
+        float corr[2], m_use[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+            corr[r] = exp2f(m_run[r] - m_use[r]);      // m_run = -inf -> 0
+            m_run[r] = m_new;
+        }
+        float rs[2] = {0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float pv = exp2f(s[nt][e] - m_use[e >> 1]);
+                rs[e >> 1] += pv;
+                if (p.drop_thresh24 != 0) {
+                    const int j = kt * TK + nt * 8 + (lane & 3) * 2 + (e & 1);
+                    const int i = r_lo + (e >> 1) * 8;
+                    const uint64_t idx = (((uint64_t)(b * p.H + h) * T + i) * T) + j;
+                    pv = spb_keep(p.seed, idx, p.drop_thresh24) ? pv * p.keep_scale : 0.f;
+                }
+                s[nt][e] = pv;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            o_acc[nt][0] *= corr[0]; o_acc[nt][1] *= corr[0];
+            o_acc[nt][2] *= corr[1]; o_acc[nt][3] *= corr[1];
+        }
+        uint32_t pf[4][4];
+        acc_to_frags(s, pf);
+        mma_p_tile_nn(o_acc, pf, smem_u32(sV[buf]), lane);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = r_lo + r * 8;
+        if (i < T) {
+            const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+            __nv_bfloat16* dst = out + ((size_t)b * T + i) * ld_out + h * DH + (lane & 3) * 2;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16x2(o_acc[nt][r * 2] * inv, o_acc[nt][r * 2 + 1] * inv);
+            if ((lane & 3) == 0 && lse_out != nullptr)
+                lse_out[((size_t)b * p.H + h) * T + i] = l_run[r] > 0.f ? (m_run[r] + log2f(l_run[r])) : INFINITY;  // base-2 units; +inf => P = 0 in backward
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- backward
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int ld,
+                                  float* __restrict__ delta, int B, int T, int H) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= B * T * H) return;
+    const int h = gw % H;
+    const int bt = gw / H;
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + (size_t)bt * ld + h * DH + lane * 2));
+    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + (size_t)bt * ld + h * DH + lane * 2));
+    const float s = warp_sum(a.x * d.x + a.y * d.y);
+    if (lane == 0) delta[((size_t)(bt / T) * H + h) * T + (bt % T)] = s;
+}
+
+// dK, dV: grid (ceil(T/64) key tiles, B); warp w owns keys [16w, 16w+16); loops over heads and query tiles.
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_do, const float* __restrict__ lse,
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int ld_dqkv) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    uint8_t* sK = dyn_smem;
+    uint8_t* sV = sK + TK * 128;
+    uint8_t (*sQ)[TQ * 128] = reinterpret_cast<uint8_t (*)[TQ * 128]>(sV + TK * 128);
+    uint8_t (*sDO)[TQ * 128] = reinterpret_cast<uint8_t (*)[TQ * 128]>(sV + TK * 128 + 2 * TQ * 128);
+    __shared__ float sLse[2][TQ], sDelta[2][TQ];
+
+    const int kt = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, H = p.H;
+    const int k0 = kt * TK;
+    const int kcol = H * DH, vcol = kcol + DH;
+    const __nv_bfloat16* base = p.qkv + (size_t)b * T * p.ld;
+    const __nv_bfloat16* dbase = dout + (size_t)b * T * ld_do;
+    const float scale2 = p.scale * LOG2E;
+
+    const int n_qt = ceil_div(T, TQ);
+    const int qt_begin = p.causal ? kt : 0;
+    const int iters = H * (n_qt - qt_begin);
+
+    auto load_q = [&](int it, int buf) {
+        const int h = it / (n_qt - qt_begin), qt = qt_begin + it % (n_qt - qt_begin);
+        load_tile_async(sQ[buf], base, p.ld, qt * TQ, h * DH, T);
+        load_tile_async(sDO[buf], dbase, ld_do, qt * TQ, h * DH, T);
+        if (threadIdx.x < TQ) {
+            const int i = qt * TQ + threadIdx.x;
+            sLse[buf][threadIdx.x] = i < T ? lse[((size_t)b * H + h) * T + i] : INFINITY;   // +inf -> P = 0
+            sDelta[buf][threadIdx.x] = i < T ? delta[((size_t)b * H + h) * T + i] : 0.f;
+        }
+    };
+
+    load_tile_async(sK, base, p.ld, k0, kcol, T);
+    load_tile_async(sV, base, p.ld, k0, vcol, T);
+    if (iters > 0) load_q(0, 0);
+    cp_async_commit();
+
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
+    uint32_t kf[4][4], vf[4][4];
+    const int j_lo = k0 + warp * 16 + (lane >> 2);   // this thread's keys: j_lo, j_lo + 8
+    bool key_ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int j = j_lo + r * 8;
+        key_ok[r] = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+    }
+
+    for (int it = 0; it < iters; ++it) {
+        const int buf = it & 1;
+        const int h = it / (n_qt - qt_begin), qt = qt_begin + it % (n_qt - qt_begin);
+        if (it + 1 < iters) load_q(it + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (it == 0) {
+            load_a_frags(smem_u32(sK), warp * 16, lane, kf);
+            load_a_frags(smem_u32(sV), warp * 16, lane, vf);
+        }
+        const float slope = __expf(p.logslopes[h]) * LOG2E;
+
+        // S^T[keys x queries] = K Q^T
+        float st[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st[i][j] = 0.f;
+        mma_a_tile_nt(st, kf, smem_u32(sQ[buf]), lane);
+        // dP^T[keys x queries] = V dO^T
+        float dpt[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dpt[i][j] = 0.f;
+        mma_a_tile_nt(dpt, vf, smem_u32(sDO[buf]), lane);
+
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float pd[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int il = nt * 8 + (lane & 3) * 2 + (e & 1);
+                const int i = qt * TQ + il;
+                const int j = j_lo + (e >> 1) * 8;
+                const bool ok = key_ok[e >> 1] && (!p.causal || j <= i);
+                float pv = ok ? exp2f(st[nt][e] * scale2 - slope * fabsf((float)(i - j)) - sLse[buf][il]) : 0.f;
+                float keep = 1.f;
+                if (p.drop_thresh24 != 0) {
+                    const uint64_t idx = (((uint64_t)(b * H + h) * T + i) * T) + j;
+                    keep = spb_keep(p.seed, idx, p.drop_thresh24) ? p.keep_scale : 0.f;
+                }
+                pd[e] = pv * keep;                                               // dropped P^T (for dV)
+                st[nt][e] = pv * (dpt[nt][e] * keep - sDelta[buf][il]);          // dS^T
+            }
+            // pack P^T_drop into A fragments as we go (two n-tiles form one k-step)
+            const int ks = nt >> 1;
+            if ((nt & 1) == 0) { pf[ks][0] = pack_bf16x2(pd[0], pd[1]); pf[ks][1] = pack_bf16x2(pd[2], pd[3]); }
+            else { pf[ks][2] = pack_bf16x2(pd[0], pd[1]); pf[ks][3] = pack_bf16x2(pd[2], pd[3]); }
+        }
+        mma_p_tile_nn(dv, pf, smem_u32(sDO[buf]), lane);   // dV += P^T_drop dO
+        acc_to_frags(st, pf);
+        mma_p_tile_nn(dk, pf, smem_u32(sQ[buf]), lane);    // dK += dS^T Q
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int j = j_lo + r * 8;
+        if (j < T) {
+            __nv_bfloat16* dst = dqkv + ((size_t)b * T + j) * ld_dqkv + (lane & 3) * 2;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                *reinterpret_cast<uint32_t*>(dst + kcol + nt * 8) = pack_bf16x2(dk[nt][r * 2] * p.scale, dk[nt][r * 2 + 1] * p.scale);
+                *reinterpret_cast<uint32_t*>(dst + vcol + nt * 8) = pack_bf16x2(dv[nt][r * 2], dv[nt][r * 2 + 1]);
+            }
+        }
+    }
+}
+
+// dQ and d(logslope): grid (ceil(T/64), H, B); same tiling as the forward.
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_do, const float* __restrict__ lse,
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int ld_dqkv,
+                   float* __restrict__ dlogslopes) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    uint8_t* sQ = dyn_smem;
+    uint8_t* sDO = sQ + TQ * 128;
+    uint8_t (*sK)[TK * 128] = reinterpret_cast<uint8_t (*)[TK * 128]>(sDO + TQ * 128);
+    uint8_t (*sV)[TK * 128] = reinterpret_cast<uint8_t (*)[TK * 128]>(sDO + TQ * 128 + 2 * TK * 128);
+    __shared__ uint8_t sMask[2][TK];
+
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, H = p.H;
+    const int q0 = qt * TQ;
+    const int kcol = H * DH, vcol = kcol + DH;
+    const __nv_bfloat16* base = p.qkv + (size_t)b * T * p.ld;
+    const __nv_bfloat16* dbase = dout + (size_t)b * T * ld_do;
+    const float slope_nat = __expf(p.logslopes[h]);
+    const float slope = slope_nat * LOG2E;
+    const float scale2 = p.scale * LOG2E;
+    const int n_kt = p.causal ? min(qt + 1, ceil_div(T, TK)) : ceil_div(T, TK);
+
+    auto load_kv = [&](int kt, int buf) {
+        load_tile_async(sK[buf], base, p.ld, kt * TK, kcol, T);
+        load_tile_async(sV[buf], base, p.ld, kt * TK, vcol, T);
+        if (threadIdx.x < TK) {
+            const int j = kt * TK + threadIdx.x;
+            sMask[buf][threadIdx.x] = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+        }
+    };
+    load_tile_async(sQ, base, p.ld, q0, h * DH, T);
+    load_tile_async(sDO, dbase, ld_do, q0, h * DH, T);
+    load_kv(0, 0);
+    cp_async_commit();
+
+    const int r_lo = q0 + warp * 16 + (lane >> 2);
+    float lse_r[2], delta_r[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = r_lo + r * 8;
+        lse_r[r] = i < T ? lse[((size_t)b * H + h) * T + i] : INFINITY;
+        delta_r[r] = i < T ? delta[((size_t)b * H + h) * T + i] : 0.f;
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+    uint32_t qf[4][4], dof[4][4];
+    // d slope needs sum_j dS_ij * |i-j|.  In exact arithmetic sum_j dS_ij = 0; the bf16 rounding of O makes delta_i
+    // slightly off, which would leak eps_i * E_i[|i-j|] into the sum.  Track the row residual and remove that term.
+    float ds_dist[2] = {0.f, 0.f}, ds_sum[2] = {0.f, 0.f}, p_dist[2] = {0.f, 0.f};
+
+    for (int kt = 0; kt < n_kt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_kt) load_kv(kt + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (kt == 0) {
+            load_a_frags(smem_u32(sQ), warp * 16, lane, qf);
+            load_a_frags(smem_u32(sDO), warp * 16, lane, dof);
+        }
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
+        mma_a_tile_nt(s, qf, smem_u32(sK[buf]), lane);     // S = Q K^T
+        mma_a_tile_nt(dp, dof, smem_u32(sV[buf]), lane);   // dP = dO V^T
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int jl = nt * 8 + (lane & 3) * 2 + (e & 1);
+                const int j = kt * TK + jl;
+                const int i = r_lo + (e >> 1) * 8;
+                const bool ok = sMask[buf][jl] && (!p.causal || j <= i);
+                const float dist = fabsf((float)(i - j));
+                const float pv = ok ? exp2f(s[nt][e] * scale2 - slope * dist - lse_r[e >> 1]) : 0.f;
+                float keep = 1.f;
+                if (p.drop_thresh24 != 0) {
+                    const uint64_t idx = (((uint64_t)(b * H + h) * T + i) * T) + j;
+                    keep = spb_keep(p.seed, idx, p.drop_thresh24) ? p.keep_scale : 0.f;
+                }
+                const float ds = pv * (dp[nt][e] * keep - delta_r[e >> 1]);
+                ds_dist[e >> 1] += ds * dist;
+                ds_sum[e >> 1] += ds;
+                p_dist[e >> 1] += pv * dist;
+                s[nt][e] = ds;
+            }
+        }
+        uint32_t pf[4][4];
+        acc_to_frags(s, pf);
+        mma_p_tile_nn(dq, pf, smem_u32(sK[buf]), lane);    // dQ += dS K
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = r_lo + r * 8;
+        if (i < T) {
+            __nv_bfloat16* dst = dqkv + ((size_t)b * T + i) * ld_dqkv + h * DH + (lane & 3) * 2;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16x2(dq[nt][r * 2] * p.scale, dq[nt][r * 2 + 1] * p.scale);
+        }
+    }
+    // d logslope_h = slope_h * sum_ij dS_ij * (-|i-j|)
+    float dslope = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            ds_dist[r] += __shfl_xor_sync(0xffffffffu, ds_dist[r], o);
+            ds_sum[r] += __shfl_xor_sync(0xffffffffu, ds_sum[r], o);
+            p_dist[r] += __shfl_xor_sync(0xffffffffu, p_dist[r], o);
+        }
+        if ((lane & 3) == 0) dslope -= ds_dist[r] - ds_sum[r] * p_dist[r];
+    }
+    dslope = warp_sum(dslope);
+    if (lane == 0 && dlogslopes != nullptr) atomicAdd(dlogslopes + h, dslope * slope_nat);
+}
+
+int fill_params(AttnParams& p, const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, int B, int T, int H,
+                int dim_head, int causal, float dropout_p, uint64_t seed) {
+    SPB_CHECK_ARG(qkv && logslopes, "attention: null pointer");
+    SPB_CHECK_ARG(dim_head == DH, "attention: dim_head must be %d, got %d", DH, dim_head);
+    SPB_CHECK_ARG(ld % 8 == 0 && ld >= H * DH + 2 * DH, "attention: qkv row stride %d too small / unaligned", ld);
+    SPB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p must be in [0,1)");
+    p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    p.ld = ld; p.key_mask = key_mask; p.logslopes = logslopes;
+    p.B = B; p.T = T; p.H = H;
+    p.scale = 1.f / sqrtf((float)dim_head);
+    p.causal = causal;
+    p.dropout_p = dropout_p;
+    p.seed = seed;
+    double t = (double)dropout_p * 16777216.0;
+    p.drop_thresh24 = dropout_p > 0.f ? (uint32_t)(t < 1 ? 1 : t) : 0;
+    p.keep_scale = 1.f / (1.f - dropout_p);
+    return SPB_OK;
+}
+
+}  // namespace
+
+// out bf16 [B*T, ld_out] (H*64 columns written); lse fp32 [B, H, T] in base-2 units (consumed only by the backward).
+extern "C" int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, void* out, int ld_out,
+                                 float* lse, int B, int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed,
+                                 cudaStream_t stream) {
+    if (B <= 0 || T <= 0) return SPB_OK;
+    AttnParams p;
+    int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed);
+    if (rc != SPB_OK) return rc;
+    SPB_CHECK_ARG(out != nullptr && ld_out % 2 == 0, "spb_attention_fwd: bad output");
+    attn_fwd_kernel<<<dim3(ceil_div(T, TQ), H, B), 128, 0, stream>>>(p, reinterpret_cast<__nv_bfloat16*>(out), ld_out, lse);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// dqkv bf16 [B*T, ld_dqkv]: dq | dk | dv in the qkv column layout; delta fp32 [B,H,T] scratch;
+// dlogslopes fp32 [H] is ACCUMULATED into.
+extern "C" int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out,
+                                 const void* dout, int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv,
+                                 float* dlogslopes, int B, int T, int H, int dim_head, int causal, float dropout_p,
+                                 uint64_t seed, cudaStream_t stream) {
+    if (B <= 0 || T <= 0) return SPB_OK;
+    AttnParams p;
+    int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed);
+    if (rc != SPB_OK) return rc;
+    SPB_CHECK_ARG(out && dout && lse && delta && dqkv, "spb_attention_bwd: null pointer");
+    const int n_warps = B * T * H;
+    attn_delta_kernel<<<ceil_div((int64_t)n_warps * 32, 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
+    SPB_CHECK_LAUNCH();
+    constexpr int BWD_SMEM = 6 * 64 * 128;
+    static bool configured = false;
+    if (!configured) {
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        configured = true;
+    }
+    attn_bwd_dkv_kernel<<<dim3(ceil_div(T, TK), B), 128, BWD_SMEM, stream>>>(p, reinterpret_cast<const __nv_bfloat16*>(dout), ld_out, lse,
+                                                                     delta, reinterpret_cast<__nv_bfloat16*>(dqkv), ld_dqkv);
+    SPB_CHECK_LAUNCH();
+    attn_bwd_dq_kernel<<<dim3(ceil_div(T, TQ), H, B), 128, BWD_SMEM, stream>>>(p, reinterpret_cast<const __nv_bfloat16*>(dout), ld_out, lse,
+                                                                       delta, reinterpret_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
+                                                                       dlogslopes);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}

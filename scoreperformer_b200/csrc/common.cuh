@@ -50,7 +50,7 @@ static inline int spb_num_sms() {
     return n;
 }
 
-static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------- small device utils
 #ifdef __CUDACC__

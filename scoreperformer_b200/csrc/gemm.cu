@@ -35,6 +35,7 @@ struct GemmParams {
     const float* residual; // fp32 [M, ldr] or null
     int ldr;
     const uint8_t* rowmask;  // [M] (bool) or null
+    const float* alpha;      // device scalar multiplying the accumulator, or null
 };
 
 template <int BN>
@@ -150,11 +151,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             const bool col_ok = col < p.N;
             const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + col) : 0.f;
+            const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 1.f;
 #pragma unroll 4
             for (int r = 0; r < 32; ++r) {
                 const int row = row_base + r;
                 if (row >= p.M) break;
-                float val = stage[r * 33 + lane] + bias;
+                float val = stage[r * 33 + lane] * alpha + bias;
                 if (col_ok) {
                     if (p.rowmask != nullptr) val = p.rowmask[row] ? val : 0.f;
                     if (p.residual != nullptr) val += p.residual[(size_t)row * p.ldr + col];
@@ -234,7 +236,7 @@ int spb_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, ui
 // C-ABI entry point; see include/spb200.h for the contract.
 extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
                              int ldb, int ldc, const float* bias, const float* residual, int ldr, const uint8_t* rowmask,
-                             int c_fp32, int split_k, int accumulate, cudaStream_t stream) {
+                             int c_fp32, int split_k, int accumulate, const float* alpha, cudaStream_t stream) {
     SPB_CHECK_ARG(A && B && C, "spb_gemm_bf16: null operand");
     SPB_CHECK_ARG(M > 0 && N > 0 && K > 0, "spb_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
     SPB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "spb_gemm_bf16: lda=%d / ldb=%d must be multiples of 8 (TMA 16 B rule)", lda,
@@ -268,7 +270,7 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
     p.kb_per_split = kb_per_split;
     p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
     p.atomic = (splits > 1 || accumulate) ? 1 : 0;
-    p.bias = bias; p.residual = residual; p.ldr = ldr; p.rowmask = rowmask;
+    p.bias = bias; p.residual = residual; p.ldr = ldr; p.rowmask = rowmask; p.alpha = alpha;
 
     if (splits > 1 && !accumulate) {
         if (ldc == N) SPB_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), stream));

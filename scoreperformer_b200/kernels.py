@@ -1,0 +1,289 @@
+"""Thin tensor-level wrappers over the C ABI (include/spb200.h).  No math happens in Python here.
+
+Every wrapper launches on torch's current CUDA stream and bumps `LAUNCHES` by the number of kernels the
+entry point launches, so bench.py can report `gpu_launches`.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import ctypes
+import torch
+from torch import Tensor
+
+from . import lib as _lib
+
+BF16, F32 = torch.bfloat16, torch.float32
+LAUNCHES = 0
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("scoreperformer_b200 kernels need CUDA tensors: there is no CPU fallback")
+
+
+def _call(name: str, *args) -> None:
+    fn = getattr(_lib.lib(), name)
+    _lib.check(fn(*args), name)
+
+
+def seed_from_torch() -> int:
+    """Draw a 63-bit dropout seed from torch's CPU generator (so torch.manual_seed governs the masks)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# ----------------------------------------------------------------------------- elementwise helpers
+def cast_bf16(x: Tensor, rowmask: Optional[Tensor] = None) -> Tensor:
+    """fp32 -> bf16 copy; rows (last dim) where rowmask is False are zeroed."""
+    _require_cuda(x)
+    if x.dtype == BF16 and rowmask is None:
+        return x
+    assert x.dtype == F32 and x.is_contiguous(), (x.dtype, x.is_contiguous())
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    row_len = x.shape[-1] if rowmask is not None else 0
+    _call("spb_cast_f32_bf16", _p(x), _p(out), x.numel(), _p(rowmask), row_len, _stream())
+    _count()
+    return out
+
+
+def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """out[c] += sum_r x[r, c] (fp32 accumulate)."""
+    _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.zeros(x.shape[1], dtype=F32, device=x.device)
+    _call("spb_colsum", _p(x), int(x.dtype == F32), x.stride(0), _p(out), x.shape[0], x.shape[1], _stream())
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------- GEMM
+def gemm(a: Tensor, b: Tensor, *, trans_a: bool = False, trans_b: bool = False, bias: Optional[Tensor] = None,
+         residual: Optional[Tensor] = None, rowmask: Optional[Tensor] = None, out: Optional[Tensor] = None,
+         out_dtype: torch.dtype = BF16, split_k: int = 1, accumulate: bool = False, alpha: Optional[Tensor] = None) -> Tensor:
+    """C = op(A) op(B)^T with the fused epilogue of spb_gemm_bf16.
+
+    a: [M,K] (or [K,M] when trans_a), b: [N,K] (or [K,N] when trans_b); both bf16 with unit inner stride.
+    """
+    _require_cuda(a, b)
+    assert a.dtype == BF16 and b.dtype == BF16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if trans_a:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if trans_b:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, f"gemm: inner dims differ ({K} vs {Kb})"
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        if accumulate:
+            out.zero_()
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (BF16, F32)
+    if residual is not None:
+        assert residual.dtype == F32 and residual.shape == (M, N) and residual.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() == N
+    _call("spb_gemm_bf16", _p(a), _p(b), _p(out), M, N, K, int(trans_a), int(trans_b), a.stride(0), b.stride(0), out.stride(0),
+          _p(bias), _p(residual), residual.stride(0) if residual is not None else 0, _p(rowmask), int(out.dtype == F32),
+          split_k, int(accumulate), _p(alpha), _stream())
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+def layer_norm_fwd(x: Tensor, w: Optional[Tensor], b: Optional[Tensor], gb: Optional[Tensor] = None,
+                   out: Optional[Tensor] = None, out_dtype: torch.dtype = BF16, eps: float = 1e-5, need_stats: bool = True):
+    """x [n, dim] (fp32 or bf16, unit inner stride) -> (y, mean, rstd)."""
+    _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    n, dim = x.shape
+    if out is None:
+        out = torch.empty((n, dim), dtype=out_dtype, device=x.device)
+    mean = torch.empty(n, dtype=F32, device=x.device) if need_stats else None
+    rstd = torch.empty(n, dtype=F32, device=x.device) if need_stats else None
+    _call("spb_layer_norm_fwd", _p(x), int(x.dtype == F32), x.stride(0), _p(w), _p(b), _p(gb), gb.stride(0) if gb is not None else 0,
+          _p(out), int(out.dtype == F32), out.stride(0), _p(mean), _p(rstd), n, dim, float(eps), _stream())
+    _count()
+    return out, mean, rstd
+
+
+def layer_norm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, w: Optional[Tensor], gb: Optional[Tensor] = None,
+                   dres: Optional[Tensor] = None, dx_dtype: torch.dtype = F32, dw: Optional[Tensor] = None,
+                   db: Optional[Tensor] = None, dgb: Optional[Tensor] = None) -> Tensor:
+    """Returns dx; dw/db (fp32 [dim]) are accumulated into, dgb (bf16 view [n, 2*dim]) is written."""
+    _require_cuda(dy, x)
+    assert dy.dtype == BF16 and dy.stride(1) == 1 and x.stride(1) == 1
+    n, dim = x.shape
+    dx = torch.empty((n, dim), dtype=dx_dtype, device=x.device)
+    _call("spb_layer_norm_bwd", _p(dy), dy.stride(0), _p(x), int(x.dtype == F32), x.stride(0), _p(mean), _p(rstd), _p(w), _p(gb),
+          gb.stride(0) if gb is not None else 0, _p(dres), dres.stride(0) if dres is not None else 0, _p(dx), int(dx.dtype == F32),
+          dx.stride(0), _p(dw), _p(db), _p(dgb), dgb.stride(0) if dgb is not None else 0, n, dim, _stream())
+    _count()
+    return dx
+
+
+# ----------------------------------------------------------------------------- GLU
+def glu_fwd(u: Tensor, dropout_p: float, seed: int) -> Tensor:
+    _require_cuda(u)
+    assert u.dtype == BF16 and u.is_contiguous()
+    n, two_h = u.shape
+    h = torch.empty((n, two_h // 2), dtype=BF16, device=u.device)
+    _call("spb_glu_fwd", _p(u), _p(h), n, two_h // 2, float(dropout_p), seed, _stream())
+    _count()
+    return h
+
+
+def glu_bwd(dh: Tensor, u: Tensor, dbias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:
+    assert dh.dtype == BF16 and dh.is_contiguous() and u.is_contiguous()
+    n, two_h = u.shape
+    du = torch.empty_like(u)
+    _call("spb_glu_bwd", _p(dh), _p(u), _p(du), _p(dbias), n, two_h // 2, float(dropout_p), seed, _stream())
+    _count()
+    return du
+
+
+# ----------------------------------------------------------------------------- tuple embedding
+def _sizes_array(sizes: Sequence[int]):
+    return (ctypes.c_int * len(sizes))(*[int(s) for s in sizes])
+
+
+def embed_ln_fwd(tokens: Tensor, table: Tensor, sizes: Sequence[int], w: Tensor, b: Tensor, out: Optional[Tensor] = None,
+                 eps: float = 1e-5):
+    """tokens int64 [n, F] (any row stride), table fp32 [sum V, 128] -> (bf16 [n, F*128], mean, rstd)."""
+    _require_cuda(tokens, table)
+    assert tokens.dtype == torch.int64 and tokens.dim() == 2 and tokens.stride(1) == 1
+    assert table.dtype == F32 and table.is_contiguous() and table.shape[1] == 128
+    n, F = tokens.shape[0], len(sizes)
+    if out is None:
+        out = torch.empty((n, F * 128), dtype=BF16, device=tokens.device)
+    mean = torch.empty(n, dtype=F32, device=tokens.device)
+    rstd = torch.empty(n, dtype=F32, device=tokens.device)
+    _call("spb_embed_ln_fwd", _p(tokens), tokens.stride(0), _p(table), _sizes_array(sizes), F, _p(w), _p(b), _p(out), out.stride(0),
+          _p(mean), _p(rstd), n, float(eps), _stream())
+    _count()
+    return out, mean, rstd
+
+
+def embed_ln_bwd(dy: Tensor, tokens: Tensor, table: Tensor, sizes: Sequence[int], w: Tensor, mean: Tensor, rstd: Tensor,
+                 dtable: Tensor, dw: Tensor, db: Tensor) -> None:
+    assert dy.dtype == BF16 and dy.stride(1) == 1
+    n = tokens.shape[0]
+    scratch = torch.empty((2, n), dtype=F32, device=dy.device)
+    _call("spb_embed_ln_bwd", _p(dy), dy.stride(0), _p(tokens), tokens.stride(0), _p(table), _sizes_array(sizes), len(sizes), _p(w),
+          _p(mean), _p(rstd), _p(scratch[0]), _p(scratch[1]), _p(dtable), _p(dw), _p(db), n, _stream())
+    _count(2)
+
+
+# ----------------------------------------------------------------------------- attention
+def attention_fwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, B: int, T: int, H: int, causal: bool,
+                  dropout_p: float, seed: int):
+    """qkv bf16 [B*T, H*64+128] -> (out bf16 [B*T, H*64], lse fp32 [B,H,T])."""
+    _require_cuda(qkv)
+    assert qkv.dtype == BF16 and qkv.stride(1) == 1 and logslopes.dtype == F32
+    out = torch.empty((B * T, H * 64), dtype=BF16, device=qkv.device)
+    lse = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+    _call("spb_attention_fwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), out.stride(0), _p(lse), B, T, H, 64,
+          int(causal), float(dropout_p), seed, _stream())
+    _count()
+    return out, lse
+
+
+def attention_bwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, out: Tensor, dout: Tensor, lse: Tensor,
+                  dlogslopes: Tensor, B: int, T: int, H: int, causal: bool, dropout_p: float, seed: int) -> Tensor:
+    assert dout.dtype == BF16 and dout.stride(1) == 1 and dout.stride(0) == out.stride(0)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+    _call("spb_attention_bwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), _p(dout), out.stride(0), _p(lse), _p(delta),
+          _p(dqkv), dqkv.stride(0), _p(dlogslopes), B, T, H, 64, int(causal), float(dropout_p), seed, _stream())
+    _count(3)
+    return dqkv
+
+
+# ----------------------------------------------------------------------------- latent levels / MMD
+def latent_level_fwd(hidden: Tensor, style: Tensor, mask: Tensor, segments: Optional[Tensor], W: Tensor, bias: Tensor, col0: int,
+                     S: int, z: int):
+    """One VAE level.  Returns (latents [B,S,z], lmask [B,S] bool, pooled [B*S,320], counts [B*S])."""
+    _require_cuda(hidden, style)
+    B, T, D = hidden.shape
+    assert hidden.dtype == F32 and hidden.is_contiguous() and style.dtype == F32 and style.is_contiguous()
+    pooled = torch.zeros((B * S, 320), dtype=F32, device=hidden.device)
+    counts = torch.zeros((B * S,), dtype=torch.int32, device=hidden.device)
+    latents = torch.empty((B, S, z), dtype=F32, device=hidden.device)
+    lmask = torch.empty((B, S), dtype=torch.bool, device=hidden.device)
+    _call("spb_latent_level_fwd", _p(hidden), _p(style), style.shape[-1], _p(mask), _p(segments), _p(W), _p(bias), _p(pooled), _p(counts),
+          _p(latents), _p(lmask), _p(style), col0, B, T, S, D, col0, z, _stream())
+    _count(3)
+    return latents, lmask, pooled, counts
+
+
+def latent_level_bwd(d_style: Tensor, col0: int, dlat_direct: Optional[Tensor], mask: Tensor, segments: Optional[Tensor], W: Tensor,
+                     pooled: Tensor, counts: Tensor, lmask: Tensor, d_hidden: Tensor, dW: Tensor, dbias: Tensor, S: int, z: int) -> None:
+    B, T, D = d_hidden.shape
+    dlat = torch.zeros((B * S, z), dtype=F32, device=d_hidden.device)
+    dpooled = torch.empty((B * S, 320), dtype=F32, device=d_hidden.device)
+    _call("spb_latent_level_bwd", _p(d_style), d_style.shape[-1], col0, _p(dlat_direct), _p(mask), _p(segments), _p(W), _p(pooled),
+          _p(counts), _p(lmask), _p(dlat), _p(dpooled), _p(d_hidden), _p(dW), _p(dbias), B, T, S, D, col0, z, _stream())
+    _count(5)
+
+
+def mmd_fwd_bwd(z_prior: Tensor, y: Tensor, w: Tensor):
+    """Returns (loss [1] fp32, grad_y [n_y, d] fp32)."""
+    _require_cuda(z_prior, y)
+    assert z_prior.dtype == F32 and y.dtype == F32 and z_prior.is_contiguous() and y.is_contiguous() and w.dtype == torch.bool
+    n_z, d = z_prior.shape
+    n_y = y.shape[0]
+    coef = torch.empty(n_z + n_y, dtype=F32, device=y.device)
+    loss = torch.zeros(1, dtype=F32, device=y.device)
+    grad = torch.zeros_like(y)
+    _call("spb_mmd_fwd_bwd", _p(z_prior), _p(y), _p(w), n_z, n_y, d, _p(coef), _p(loss), _p(grad), _stream())
+    _count(2)
+    return loss, grad
+
+
+# ----------------------------------------------------------------------------- heads
+def ce_rows(logits: Tensor, labels: Tensor, V: int, loss_sum: Tensor, count: Tensor, dlogits: Optional[Tensor] = None,
+            argmax: Optional[Tensor] = None, ignore_index: int = -100) -> None:
+    """logits fp32 [n, >=V]; labels int64 [n] (strided view allowed)."""
+    assert logits.dtype == F32 and logits.stride(1) == 1 and labels.dtype == torch.int64 and labels.dim() == 1
+    _call("spb_ce_rows", _p(logits), logits.stride(0), _p(labels), labels.stride(0), V, ignore_index, _p(loss_sum), _p(count),
+          _p(dlogits), dlogits.stride(0) if dlogits is not None else 0, _p(argmax), logits.shape[0], _stream())
+    _count()
+
+
+def clf_heads(x: Tensor, rowmask: Tensor, labels: Tensor, W: Tensor, bias: Tensor, class_w: Tensor, n_classes: Sequence[int],
+              dropout_p: float, seed: int, num: Optional[Tensor] = None, den: Optional[Tensor] = None,
+              dlogit_scale: Optional[Tensor] = None, dW: Optional[Tensor] = None, db: Optional[Tensor] = None) -> None:
+    """x fp32 [n, in_dim]; labels int64 [n, n_heads]; forward when dlogit_scale is None, else backward."""
+    assert x.dtype == F32 and x.stride(1) == 1 and labels.dtype == torch.int64 and labels.stride(1) == 1
+    n, in_dim = x.shape
+    backward = dlogit_scale is not None
+    scratch = torch.empty((n, int(sum(n_classes))), dtype=F32, device=x.device) if backward else None
+    _call("spb_clf_heads", _p(x), x.stride(0), _p(rowmask), _p(labels), labels.stride(0), _p(W), _p(bias), _p(class_w),
+          _sizes_array(n_classes), len(n_classes), _p(num), _p(den), _p(dlogit_scale), _p(dW), _p(db), _p(scratch), n, in_dim,
+          float(dropout_p), seed, int(backward), _stream())
+    _count(2 if backward else 1)
+
+
+def clf_logits(x: Tensor, W: Tensor, bias: Tensor) -> Tensor:
+    n, in_dim = x.shape
+    out = torch.empty((n, W.shape[0]), dtype=F32, device=x.device)
+    _call("spb_clf_logits", _p(x), x.stride(0), _p(W), _p(bias), _p(out), n, in_dim, W.shape[0], _stream())
+    _count()
+    return out

@@ -1,0 +1,89 @@
+"""ctypes binding of libspb200.so (the C ABI declared in include/spb200.h).
+
+There is no CPU fallback: importing works anywhere, but touching `lib()` without the built
+library, or calling a kernel without a CUDA device, raises.  Build with
+`python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_uint64, c_void_p
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libspb200.so")
+SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "attention.cu", "latents.cu", "heads.cu"]
+
+_P, _I, _F, _L, _U64 = c_void_p, c_int, c_float, c_int64, c_uint64
+
+# name -> argument ctypes (all functions return int); mirrors include/spb200.h line by line
+SIGNATURES = {
+    "spb_cast_f32_bf16": [_P, _P, _L, _P, _I, _P],
+    "spb_colsum": [_P, _I, _I, _P, _I, _I, _P],
+    "spb_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P],
+    "spb_layer_norm_fwd": [_P, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P, _I, _I, _F, _P],
+    "spb_layer_norm_bwd": [_P, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P],
+    "spb_glu_fwd": [_P, _P, _I, _I, _F, _U64, _P],
+    "spb_glu_bwd": [_P, _P, _P, _P, _I, _I, _F, _U64, _P],
+    "spb_embed_ln_fwd": [_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _F, _P],
+    "spb_embed_ln_bwd": [_P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "spb_attention_fwd": [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P],
+    "spb_attention_bwd": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P],
+    "spb_latent_level_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "spb_latent_level_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "spb_mmd_fwd_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "spb_ce_rows": [_P, _I, _P, _I, _I, c_longlong, _P, _P, _P, _I, _P, _I, _P],
+    "spb_clf_heads": [_P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U64, _I, _P],
+    "spb_clf_logits": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def nvcc_command(out: str = LIB_PATH):
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every kernel for sm_100a into scoreperformer_b200/csrc/libspb200.so (in-tree, git-ignored)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = nvcc_command()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(" ".join(cmd))
+        print(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libspb200.so:\n" + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: scoreperformer_b200 has no CPU / PyTorch fallback. "
+                "Run `python -c \"import __graft_entry__ as g; g.build()\"` (needs nvcc).")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        handle.spb_last_error.restype = c_char_p
+        handle.spb_last_error.argtypes = []
+        handle.spb_abi_version.restype = c_int
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, name: str) -> None:
+    if rc != 0:
+        msg = lib().spb_last_error().decode(errors="replace")
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")

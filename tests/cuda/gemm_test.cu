@@ -10,7 +10,7 @@
 
 extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
                              int ldb, int ldc, const float* bias, const float* residual, int ldr, const uint8_t* rowmask,
-                             int c_fp32, int split_k, int accumulate, cudaStream_t stream);
+                             int c_fp32, int split_k, int accumulate, const float* alpha, cudaStream_t stream);
 extern "C" const char* spb_last_error();
 
 static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
@@ -44,7 +44,7 @@ static int run_case(int M, int N, int K, int ta, int tb, int epi, int c_fp32, in
     cudaMemcpy(dmask, mask.data(), M, cudaMemcpyHostToDevice);
     cudaMemset(dC, 0xFF, csz);
     int rc = spb_gemm_bf16(dA, dB, dC, M, N, K, ta, tb, lda, ldb, N, (epi & 1) ? dbias : nullptr, (epi & 2) ? dres : nullptr, N,
-                           (epi & 4) ? dmask : nullptr, c_fp32, split, 0, 0);
+                           (epi & 4) ? dmask : nullptr, c_fp32, split, 0, nullptr, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc != 0 || e != cudaSuccess) {
         printf("FAIL launch M=%d N=%d K=%d ta=%d tb=%d: rc=%d %s / %s\n", M, N, K, ta, tb, rc, spb_last_error(), cudaGetErrorString(e));
@@ -84,10 +84,10 @@ static void bench(int M, int N, int K, int ta, int tb, int c_fp32, int split, co
     int lda = ta ? M : K, ldb = tb ? N : K;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) spb_gemm_bf16(dA, dB, dC, M, N, K, ta, tb, lda, ldb, N, 0, 0, 0, 0, c_fp32, split, 0, 0);
+    for (int i = 0; i < 3; ++i) spb_gemm_bf16(dA, dB, dC, M, N, K, ta, tb, lda, ldb, N, 0, 0, 0, 0, c_fp32, split, 0, nullptr, 0);
     cudaEventRecord(e0);
     const int iters = 20;
-    for (int i = 0; i < iters; ++i) spb_gemm_bf16(dA, dB, dC, M, N, K, ta, tb, lda, ldb, N, 0, 0, 0, 0, c_fp32, split, 0, 0);
+    for (int i = 0; i < iters; ++i) spb_gemm_bf16(dA, dB, dC, M, N, K, ta, tb, lda, ldb, N, 0, 0, 0, 0, c_fp32, split, 0, nullptr, 0);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;

@@ -1,0 +1,364 @@
+"""Per-kernel parity: every C-ABI entry point against a plain PyTorch fp32 statement of the same op (on the GPU)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def k():
+    from scoreperformer_b200 import kernels
+    return kernels
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-6))
+
+
+def cos_dist(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return float(1 - torch.dot(a, b) / (a.norm() * b.norm()).clamp(min=1e-12))
+
+
+def randn(*shape, dtype=F32, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(dtype)
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(257, 384, 256), (1022, 132, 128), (64, 1536, 512)])
+def test_gemm_variants(k, ta, tb, M, N, K):
+    torch.manual_seed(0)
+    A, B = randn(M, K, dtype=BF16), randn(N, K, dtype=BF16)
+    a = A.t().contiguous() if ta else A
+    b = B.t().contiguous() if tb else B
+    if (ta and M % 8) or (tb and N % 8):
+        pytest.skip("MN-major operands need a 16-byte aligned row stride")
+    ref = A.float() @ B.float().t()
+    out = k.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), out_dtype=F32)
+    assert rel_err(out, ref) < 2e-5
+    bias, res = randn(N), randn(M, N)
+    mask = torch.rand(M, device="cuda") > 0.3
+    alpha = torch.tensor([0.37], device="cuda")
+    out = k.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), bias=bias, residual=res, rowmask=mask, out_dtype=BF16, alpha=alpha)
+    ref2 = (0.37 * ref + bias) * mask[:, None] + res
+    assert rel_err(out, ref2) < 1e-2
+
+
+def test_gemm_splitk_wgrad(k):
+    torch.manual_seed(1)
+    dy, x = randn(4090 * 2, 384, dtype=BF16), randn(4090 * 2, 256, dtype=BF16)
+    ref = dy.float().t() @ x.float()
+    out = k.gemm(dy, x, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+    assert rel_err(out, ref) < 1e-4
+    out2 = k.gemm(dy, x, trans_a=True, trans_b=True, out=out.clone(), split_k=0, accumulate=True)
+    assert rel_err(out2, 2 * ref) < 1e-4
+
+
+def test_gemm_strided_views(k):
+    torch.manual_seed(2)
+    big = randn(300, 1536, dtype=BF16)
+    w = randn(165, 128, dtype=BF16)
+    a = big[:, 256:384]
+    out = k.gemm(a, w, out_dtype=F32)
+    assert rel_err(out, a.float() @ w.float().t()) < 2e-5
+    buf = torch.zeros(300, 512, dtype=BF16, device="cuda")
+    k.gemm(a, randn(256, 128, dtype=BF16), out=buf[:, 256:])
+    assert float(buf[:, :256].abs().max()) == 0 and float(buf[:, 256:].abs().max()) > 0
+
+
+def test_cast_and_colsum(k):
+    x = randn(777, 256)
+    mask = torch.rand(777, device="cuda") > 0.5
+    assert torch.equal(k.cast_bf16(x), x.to(BF16))
+    assert torch.equal(k.cast_bf16(x, mask), (x * mask[:, None]).to(BF16))
+    y = randn(3001, 507)
+    assert rel_err(k.colsum(y), y.sum(0)) < 1e-5
+    assert rel_err(k.colsum(y.to(BF16)), y.to(BF16).float().sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("dim,x_dtype,y_dtype,ada", [(256, F32, BF16, False), (256, F32, BF16, True), (256, F32, F32, False),
+                                                     (1536, BF16, BF16, False), (256, BF16, BF16, False)])
+def test_layer_norm(k, dim, x_dtype, y_dtype, ada):
+    torch.manual_seed(3)
+    n = 517
+    x = randn(n, dim, dtype=x_dtype, scale=2.0) + 0.5
+    w, b = randn(dim) * 0.2 + 1, randn(dim) * 0.1
+    gb = (randn(n, 2 * dim) * 0.3 + 0.8).to(BF16) if ada else None
+    xr = x.float().requires_grad_(True)
+    if ada:
+        gbr = gb.float().requires_grad_(True)
+        ref = gbr[:, :dim] * F.layer_norm(xr, (dim,)) + gbr[:, dim:]
+    else:
+        wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ref = F.layer_norm(xr, (dim,), wr, br)
+    y, mean, rstd = k.layer_norm_fwd(x, None if ada else w, None if ada else b, gb, out_dtype=y_dtype)
+    assert rel_err(y, ref) < (1e-5 if y_dtype == F32 else 1e-2)
+    dy = randn(n, dim, dtype=BF16)
+    dres = randn(n, dim)
+    ref.backward(dy.float())
+    if not ((x_dtype == F32 and not ada) or (x_dtype == F32 and ada) or x_dtype == BF16):
+        return
+    dx_dtype = F32 if (x_dtype == F32 and y_dtype == BF16) else (BF16 if x_dtype == BF16 else BF16)
+    if ada:
+        dgb = torch.empty(n, 2 * dim, dtype=BF16, device="cuda")
+        dx = k.layer_norm_bwd(dy, x, mean, rstd, None, gb, dres=dres, dx_dtype=F32, dgb=dgb)
+        assert rel_err(dx, xr.grad + dres) < 1e-4
+        assert rel_err(dgb, gbr.grad) < 1e-2
+    else:
+        dw, db = torch.zeros(dim, device="cuda"), torch.zeros(dim, device="cuda")
+        use_res = dx_dtype == F32
+        dx = k.layer_norm_bwd(dy, x, mean, rstd, w, dres=dres if use_res else None, dx_dtype=dx_dtype, dw=dw, db=db)
+        assert rel_err(dx, xr.grad + (dres if use_res else 0)) < (1e-4 if dx_dtype == F32 else 1e-2)
+        assert rel_err(dw, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ GLU
+@pytest.mark.parametrize("H", [1024, 64])
+def test_glu(k, H):
+    torch.manual_seed(4)
+    u = randn(333, 2 * H, dtype=BF16)
+    ur = u.float().requires_grad_(True)
+    a, g = ur.chunk(2, dim=-1)
+    ref = a * F.silu(g)
+    h = k.glu_fwd(u, 0.0, 0)
+    assert rel_err(h, ref) < 1e-2
+    dh = randn(333, H, dtype=BF16)
+    ref.backward(dh.float())
+    db = torch.zeros(2 * H, device="cuda")
+    du = k.glu_bwd(dh, u, db, 0.0, 0)
+    assert rel_err(du, ur.grad) < 1e-2
+    assert rel_err(db, ur.grad.sum(0)) < 1e-2
+    # dropout: same mask in forward and backward, keep-rate close to 1-p
+    hd = k.glu_fwd(u, 0.25, 1234)
+    kept = (hd != 0).float().mean()
+    assert abs(float(kept) - 0.75) < 0.02
+    dud = k.glu_bwd(dh, u, None, 0.25, 1234)
+    m = (hd != 0)
+    assert rel_err(dud[:, :H][m], (ur.grad[:, :H] / 0.75)[m]) < 2e-2
+    assert float(dud[:, :H][~m & (ref != 0)].abs().max()) == 0
+
+
+# ------------------------------------------------------------------ tuple embedding
+@pytest.mark.parametrize("F_", [12, 10])
+def test_embed_ln(k, F_):
+    torch.manual_seed(5)
+    sizes = [260, 132, 92, 132, 133, 125, 26, 69, 16, 16, 165, 85][:F_]
+    n = 1000
+    table = randn(sum(sizes), 128)
+    tokens = torch.stack([torch.randint(0, v, (n,), device="cuda") for v in sizes], dim=-1)
+    tokens[::7] = 0
+    w, b = randn(F_ * 128) * 0.2 + 1, randn(F_ * 128) * 0.1
+    tr = table.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    offs = [0]
+    for v in sizes[:-1]:
+        offs.append(offs[-1] + v)
+    parts = []
+    for f in range(F_):
+        blk = tr[offs[f]:offs[f] + sizes[f]]
+        parts.append(F.embedding(tokens[:, f], blk, padding_idx=0))
+    ref = F.layer_norm(torch.cat(parts, -1), (F_ * 128,), wr, br)
+    out, mean, rstd = k.embed_ln_fwd(tokens, table, sizes, w, b)
+    assert rel_err(out, ref) < 1e-2
+    dy = randn(n, F_ * 128, dtype=BF16)
+    ref.backward(dy.float())
+    dtable, dw, db = torch.zeros_like(table), torch.zeros_like(w), torch.zeros_like(b)
+    k.embed_ln_bwd(dy, tokens, table, sizes, w, mean, rstd, dtable, dw, db)
+    assert rel_err(dtable, tr.grad) < 1e-4
+    assert rel_err(dw, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ attention
+def ref_attention(qkv, mask, logslopes, B, T, H, causal):
+    qkv = qkv.view(B, T, -1)
+    q = qkv[..., :H * 64].view(B, T, H, 64).transpose(1, 2)
+    kk, v = qkv[..., H * 64:H * 64 + 64], qkv[..., H * 64 + 64:]
+    pos = torch.arange(T, device=qkv.device)
+    bias = -(pos[None, :] - pos[:, None]).abs().float()[None] * logslopes.exp().view(H, 1, 1)
+    allowed = mask[:, None, None, :].expand(B, 1, T, T)
+    if causal:
+        allowed = allowed & (pos[None, :] <= pos[:, None])[None, None]
+    s = torch.einsum("bhid,bjd->bhij", q, kk) * 0.125 + bias[None]
+    s = s.masked_fill(~allowed, -1e30)
+    p = s.softmax(-1)
+    return torch.einsum("bhij,bjd->bhid", p, v).transpose(1, 2).reshape(B * T, H * 64)
+
+
+@pytest.mark.parametrize("B,T,causal", [(2, 64, False), (3, 47, True), (2, 200, False), (2, 511, True), (1, 130, True)])
+def test_attention_fwd_bwd(k, B, T, causal):
+    torch.manual_seed(6)
+    H = 4
+    qkv = randn(B * T, H * 64 + 128, dtype=BF16)
+    lengths = torch.randint(T // 2, T + 1, (B,), device="cuda")
+    lengths[0] = T
+    mask = torch.arange(T, device="cuda")[None] < lengths[:, None]
+    logslopes = torch.log(torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda")) + 0.1
+    qr = qkv.float().requires_grad_(True)
+    lr = logslopes.clone().requires_grad_(True)
+    ref = ref_attention(qr, mask, lr, B, T, H, causal)
+    out, lse = k.attention_fwd(qkv, mask, logslopes, B, T, H, causal, 0.0, 0)
+    assert rel_err(out, ref) < 1.5e-2
+    dout = randn(B * T, H * 64, dtype=BF16)
+    ref.backward(dout.float())
+    dls = torch.zeros(H, device="cuda")
+    dqkv = k.attention_bwd(qkv, mask, logslopes, out, dout, lse, dls, B, T, H, causal, 0.0, 0)
+    assert cos_dist(dqkv[:, :256], qr.grad[:, :256]) < 1e-3
+    assert cos_dist(dqkv[:, 256:320], qr.grad[:, 256:320]) < 1e-3
+    assert cos_dist(dqkv[:, 320:], qr.grad[:, 320:]) < 1e-3
+    assert rel_err(dqkv, qr.grad) < 3e-2
+    assert rel_err(dls, lr.grad) < 3e-2
+
+
+def test_attention_dropout_consistency(k):
+    """Backward must regenerate the forward's dropout mask: finite-difference-free check via linearity in V."""
+    torch.manual_seed(7)
+    B, T, H = 2, 96, 4
+    qkv = randn(B * T, H * 64 + 128, dtype=BF16)
+    mask = torch.ones(B, T, dtype=torch.bool, device="cuda")
+    ls = torch.log(torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda"))
+    out, lse = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 99)
+    out2, _ = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 99)
+    assert torch.equal(out, out2)
+    out3, _ = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 100)
+    assert not torch.equal(out, out3)
+    # O is linear in V: <dO, O> == <dV, V> when dO is the upstream gradient
+    dout = randn(B * T, H * 64, dtype=BF16)
+    dqkv = k.attention_bwd(qkv, mask, ls, out, dout, lse, torch.zeros(H, device="cuda"), B, T, H, False, 0.3, 99)
+    lhs = float((dout.float() * out.float()).sum())
+    rhs = float((dqkv[:, 320:].float() * qkv[:, 320:].float()).sum())
+    assert abs(lhs - rhs) / abs(lhs) < 3e-2
+
+
+# ------------------------------------------------------------------ latent levels
+def test_latent_level(k):
+    torch.manual_seed(8)
+    B, T, D, z, col0 = 3, 70, 256, 8, 52
+    hidden = randn(B, T, D)
+    lengths = torch.tensor([70, 50, 61], device="cuda")
+    mask = torch.arange(T, device="cuda")[None] < lengths[:, None]
+    seg = 4 + torch.cumsum((torch.rand(B, T, device="cuda") < 0.4).long(), 1)
+    seg = seg * mask
+    S = T + 4
+    style = torch.zeros(B, T, 64, device="cuda")
+    style[..., :col0] = randn(B, T, col0) * mask[..., None]
+    W, bias = randn(z, D + col0) * 0.1, randn(z) * 0.1
+    hr, sr = hidden.clone().requires_grad_(True), style[..., :col0].clone().requires_grad_(True)
+    Wr, br = W.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    x = torch.cat([hr * mask[..., None], sr], -1)
+    onehot = F.one_hot(seg, S).float()
+    counts = onehot.sum(1).clamp(min=1)
+    pooled = torch.einsum("bts,btd->bsd", onehot, x) / counts[..., None]
+    lm = (pooled != 0).all(-1)
+    lat_ref = (pooled @ Wr.t() + br) * lm[..., None]
+    emb_ref = torch.gather(lat_ref, 1, seg[..., None].expand(-1, -1, z)) * mask[..., None]
+    st = style.clone()
+    lat, lmask, pooled_k, counts_k = k.latent_level_fwd(hidden, st, mask, seg, W, bias, col0, S, z)
+    assert torch.equal(lmask, lm)
+    assert torch.equal(counts_k.view(B, S).long(), onehot.sum(1).long())
+    assert rel_err(lat, lat_ref) < 1e-5
+    assert rel_err(st[..., col0:col0 + z], emb_ref) < 1e-5
+    # backward
+    d_emb, d_lat_direct = randn(B, T, z), randn(B, S, z)
+    (emb_ref * d_emb).sum().add((lat_ref * d_lat_direct).sum()).backward()
+    d_style = torch.zeros(B, T, 64, device="cuda")
+    d_style[..., col0:col0 + z] = d_emb
+    d_hidden = torch.zeros(B, T, D, device="cuda")
+    dW, db = torch.zeros_like(W), torch.zeros_like(bias)
+    k.latent_level_bwd(d_style, col0, d_lat_direct, mask, seg, W, pooled_k, counts_k, lmask, d_hidden, dW, db, S, z)
+    assert rel_err(d_hidden, hr.grad) < 1e-4
+    assert rel_err(d_style[..., :col0], sr.grad) < 1e-4
+    assert rel_err(dW, Wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
+def test_latent_level_mean_mode(k):
+    torch.manual_seed(9)
+    B, T, D, z = 2, 40, 256, 32
+    hidden = randn(B, T, D)
+    mask = torch.arange(T, device="cuda")[None] < torch.tensor([40, 25], device="cuda")[:, None]
+    W, bias = randn(z, D) * 0.1, randn(z) * 0.1
+    style = torch.zeros(B, T, 64, device="cuda")
+    lat, lmask, _, _ = k.latent_level_fwd(hidden, style, mask, None, W, bias, 0, 2, z)
+    pooled = (hidden * mask[..., None]).sum(1) / mask.sum(1, keepdim=True)
+    ref = pooled @ W.t() + bias
+    assert rel_err(lat[:, 1], ref) < 1e-5
+    assert rel_err(style[..., :z], ref[:, None] * mask[..., None]) < 1e-5
+
+
+@pytest.mark.parametrize("d,n_y", [(4, 700), (8, 300), (20, 129), (32, 5)])
+def test_mmd(k, d, n_y):
+    torch.manual_seed(10)
+    z = randn(256, d)
+    y = randn(n_y, d) * 0.7 + 0.2
+    w = torch.rand(n_y, device="cuda") > 0.2
+    yr = y.clone().requires_grad_(True)
+
+    def kern(a, b):
+        return torch.exp(-((a[:, None] - b[None]) ** 2).mean(-1) / d).mean()
+    ys = yr[w]
+    ref = kern(z, z) + kern(ys, ys) - 2 * kern(z, ys)
+    ref.backward()
+    loss, grad = k.mmd_fwd_bwd(z, y, w)
+    assert abs(float(loss) - float(ref)) < 1e-5 + 1e-4 * abs(float(ref))
+    assert rel_err(grad, yr.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ heads
+@pytest.mark.parametrize("V", [132, 165, 85, 260])
+def test_ce_rows(k, V):
+    torch.manual_seed(11)
+    n = 999
+    logits = randn(n, V, scale=3.0)
+    labels = torch.randint(4, V, (n,), device="cuda")
+    labels[::3] = -100
+    lr = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, labels, ignore_index=-100, reduction="sum")
+    ref.backward()
+    ls, cnt = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    vpad = (V + 7) // 8 * 8
+    dl = torch.empty(n, vpad, dtype=BF16, device="cuda")
+    am = torch.empty(n, dtype=torch.int32, device="cuda")
+    k.ce_rows(logits, labels, V, ls, cnt, dl, am)
+    assert abs(float(ls) - float(ref)) / float(ref) < 1e-5
+    assert int(cnt) == int((labels != -100).sum())
+    assert rel_err(dl[:, :V], lr.grad) < 1e-2
+    assert float(dl[:, V:].abs().max()) == 0 if vpad > V else True
+    assert torch.equal(am.long(), logits.argmax(-1))
+
+
+def test_clf_heads(k):
+    torch.manual_seed(12)
+    n, in_dim = 1500, 64
+    ncls = [10, 3, 3, 14, 11, 2, 2, 2, 2]
+    tot = sum(ncls)
+    x = randn(n, in_dim)
+    rowmask = torch.rand(n, device="cuda") > 0.3
+    labels = torch.stack([torch.randint(0, c, (n,), device="cuda") for c in ncls], -1)
+    W, b = randn(tot, in_dim) * 0.2, randn(tot) * 0.1
+    cw = torch.rand(tot, device="cuda") + 0.5
+    Wr, br = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    off, total = 0, 0
+    per_head = []
+    for g, c in enumerate(ncls):
+        lg = x[rowmask] @ Wr[off:off + c].t() + br[off:off + c]
+        l = F.cross_entropy(lg, labels[rowmask][:, g], weight=cw[off:off + c])
+        per_head.append(l)
+        total = total + l
+        off += c
+    loss_ref = total / len(ncls)
+    loss_ref.backward()
+    num, den = torch.zeros(len(ncls), device="cuda"), torch.zeros(len(ncls), device="cuda")
+    k.clf_heads(x, rowmask, labels, W, b, cw, ncls, 0.0, 0, num=num, den=den)
+    assert rel_err(num / den, torch.stack(per_head)) < 1e-5
+    scale = (1.0 / len(ncls)) / den
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    k.clf_heads(x, rowmask, labels, W, b, cw, ncls, 0.0, 0, dlogit_scale=scale, dW=dW, db=db)
+    assert rel_err(dW, Wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    assert rel_err(k.clf_logits(x, W, b), x @ W.t() + b) < 1e-5
