@@ -442,7 +442,9 @@ extern "C" int spb_layer_norm_fwd(const void* x, int x_fp32, int ldx, const floa
     if (dim == 256 && x_fp32 && !y_fp32 && !ada) LN_FWD(1, float, __nv_bfloat16, false);
     else if (dim == 256 && x_fp32 && !y_fp32 && ada) LN_FWD(1, float, __nv_bfloat16, true);
     else if (dim == 256 && x_fp32 && y_fp32 && !ada) LN_FWD(1, float, float, false);
+    else if (dim == 256 && x_fp32 && y_fp32 && ada) LN_FWD(1, float, float, true);
     else if (dim == 256 && !x_fp32 && !y_fp32 && !ada) LN_FWD(1, __nv_bfloat16, __nv_bfloat16, false);
+    else if (dim == 256 && !x_fp32 && y_fp32 && !ada) LN_FWD(1, __nv_bfloat16, float, false);
     else if (dim == 1536 && !x_fp32 && !y_fp32 && !ada) LN_FWD(6, __nv_bfloat16, __nv_bfloat16, false);
     else if (dim == 1280 && !x_fp32 && !y_fp32 && !ada) LN_FWD(5, __nv_bfloat16, __nv_bfloat16, false);
     else if (dim == 512 && x_fp32 && !y_fp32 && !ada) LN_FWD(2, float, __nv_bfloat16, false);

@@ -1,0 +1,502 @@
+"""Autograd boundaries of the B200 path: each Function below is a hand-scheduled forward + backward over the
+C-ABI kernels (scoreperformer_b200.kernels).  PyTorch only owns the tensors and the graph edges between
+these few coarse nodes; no arithmetic on activations happens in Python.
+
+Numerics: bf16 tensor-core operands, fp32 accumulation, fp32 residual stream / LayerNorm statistics / softmax /
+losses -- i.e. what `torch.autocast(bfloat16)` does to the reference modules ("fp16+GradScaler vs bf16").
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import kernels as K
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+# ----------------------------------------------------------------------------- generic Linear
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b with bf16 operands (nn.Linear under autocast).  x: [n, in] fp32 or bf16; W fp32 [out, in].
+
+    `w_is_kn=True` multiplies by a weight stored [in, out] (the tied head's `x @ project_emb.weight`,
+    models/scoreperformer/embeddings.py:346)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_fp32: bool, w_is_kn: bool):
+        x16 = K.cast_bf16(x.contiguous()) if x.dtype == F32 else x
+        w16 = K.cast_bf16(weight.contiguous())
+        y = K.gemm(x16, w16, trans_b=w_is_kn, bias=bias, out_dtype=F32 if out_fp32 else BF16)
+        ctx.saved = (x16, w16)
+        ctx.meta = (x.dtype, w_is_kn, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved
+        x_dtype, w_is_kn, has_bias = ctx.meta
+        dy = dy.contiguous()
+        dy16 = K.cast_bf16(dy) if dy.dtype == F32 else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx[n, in] = dy[n, out] @ W[out, in]   (B operand must be [in, out]-indexed: MN-major unless stored [in, out])
+            dx = K.gemm(dy16, w16, trans_b=not w_is_kn, out_dtype=x_dtype)
+        if ctx.needs_input_grad[1]:
+            if w_is_kn:   # dW[in, out] = x^T dy
+                dw = K.gemm(x16, dy16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            else:         # dW[out, in] = dy^T x
+                dw = K.gemm(dy16, x16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dy16)
+        return dx, dw, db, None, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, out_fp32: bool = False, w_is_kn: bool = False) -> Tensor:
+    shape = x.shape
+    y = LinearFn.apply(x.reshape(-1, shape[-1]), weight, bias, out_fp32, w_is_kn)
+    return y.view(*shape[:-1], y.shape[-1])
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(dim) with fp32 statistics; x fp32 or bf16 [n, dim]; output dtype selectable."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_fp32: bool, eps: float):
+        x = x.contiguous()
+        y, mean, rstd = K.layer_norm_fwd(x, weight, bias, out_dtype=F32 if out_fp32 else BF16, eps=eps)
+        ctx.saved = (x, mean, rstd, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, weight = ctx.saved
+        dy = dy.contiguous()
+        dy16 = K.cast_bf16(dy) if dy.dtype == F32 else dy
+        dw = torch.zeros_like(weight)
+        db = torch.zeros_like(weight)
+        dx = K.layer_norm_bwd(dy16, x, mean, rstd, weight, dx_dtype=BF16, dw=dw, db=db)
+        if x.dtype == F32:
+            dx = dx.float()
+        return dx, dw, db, None, None
+
+
+def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, out_fp32: bool = False, eps: float = 1e-5) -> Tensor:
+    shape = x.shape
+    return LayerNormFn.apply(x.reshape(-1, shape[-1]), weight, bias, out_fp32, eps).view(shape)
+
+
+# ----------------------------------------------------------------------------- tuple-token embedding (a1/a2)
+class TupleEmbedFn(torch.autograd.Function):
+    """project_emb(LayerNorm(cat_f table_f[tokens_f])) -> bf16 [n, dim]  (models/scoreperformer/embeddings.py:121-143)."""
+
+    @staticmethod
+    def forward(ctx, tokens, table, ln_w, ln_b, proj_w, proj_b, sizes: Tuple[int, ...]):
+        x16, mean, rstd = K.embed_ln_fwd(tokens, table.contiguous(), sizes, ln_w, ln_b)
+        w16 = K.cast_bf16(proj_w.contiguous())
+        y = K.gemm(x16, w16, bias=proj_b, out_dtype=BF16)
+        ctx.saved = (tokens, table, ln_w, mean, rstd, x16, w16)
+        ctx.sizes = sizes
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        tokens, table, ln_w, mean, rstd, x16, w16 = ctx.saved
+        dy16 = dy if dy.stride(-1) == 1 else dy.contiguous()
+        assert dy16.dtype == BF16
+        dproj_w = K.gemm(dy16, x16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+        dproj_b = K.colsum(dy16)
+        dx16 = K.gemm(dy16, w16, trans_b=True, out_dtype=BF16)
+        dtable = torch.zeros_like(table)
+        dln_w = torch.zeros_like(ln_w)
+        dln_b = torch.zeros_like(ln_w)
+        K.embed_ln_bwd(dx16, tokens, table, ctx.sizes, ln_w, mean, rstd, dtable, dln_w, dln_b)
+        return None, dtable, dln_w, dln_b, dproj_w, dproj_b, None
+
+
+# ----------------------------------------------------------------------------- stand-alone attention core / GLU
+class AttentionCoreFn(torch.autograd.Function):
+    """softmax(scale q k^T - slope|i-j| + masks) v for MQA; qkv bf16 [B*T, H*64+128] (modules/transformer/attend.py:58-126)."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, logslopes, B, T, H, causal, dropout_p, seed):
+        ls = logslopes.detach().reshape(-1).contiguous()
+        o, lse = K.attention_fwd(qkv, mask, ls, B, T, H, causal, dropout_p, seed)
+        ctx.saved = (qkv, mask, ls, o, lse)
+        ctx.meta = (B, T, H, causal, dropout_p, seed, logslopes.shape)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, mask, ls, o, lse = ctx.saved
+        B, T, H, causal, dropout_p, seed, ls_shape = ctx.meta
+        dls = torch.zeros(H, dtype=F32, device=qkv.device)
+        dqkv = K.attention_bwd(qkv, mask, ls, o, do.contiguous(), lse, dls, B, T, H, causal, dropout_p, seed)
+        return dqkv, None, dls.view(ls_shape), None, None, None, None, None, None
+
+
+class GLUFn(torch.autograd.Function):
+    """value * silu(gate) with dropout; u bf16 [n, 2H] (modules/transformer/feedforward.py:13-22,59)."""
+
+    @staticmethod
+    def forward(ctx, u, dropout_p, seed):
+        u = u.contiguous()
+        ctx.saved = (u, dropout_p, seed)
+        return K.glu_fwd(u, dropout_p, seed)
+
+    @staticmethod
+    def backward(ctx, dh):
+        u, dropout_p, seed = ctx.saved
+        return K.glu_bwd(dh.contiguous(), u, None, dropout_p, seed), None, None
+
+
+# ----------------------------------------------------------------------------- transformer stack (a4-a7)
+@dataclass(frozen=True)
+class StackSpec:
+    depth: int
+    heads: int
+    dim: int
+    dim_head: int
+    ff_inner: int
+    causal: bool
+    ada: bool
+    attn_dropout: float
+    ff_dropout: float
+    training: bool
+    eps: float = 1e-5
+    return_hiddens: bool = False
+
+    @property
+    def n_norms(self) -> int:
+        return 2 * self.depth + 1
+
+
+PARAMS_PER_ATTN = 7   # norm_a, norm_b, to_q, to_k, to_v, to_out, logslopes
+PARAMS_PER_FF = 5     # norm_a, norm_b, proj_w, proj_b, out_w
+
+
+class TransformerStackFn(torch.autograd.Function):
+    """Pre-norm ('a','f') x depth stack + final norm (modules/transformer/transformer.py:139-232) as ONE graph node.
+
+    x fp32 [B, T, D] (the residual stream stays fp32), mask bool [B, T] or None, style fp32 [B, T, S] (AdaLN) or None.
+    params: per layer pair (norm_a, norm_b, to_q, to_k, to_v, to_out, logslopes), (norm_a, norm_b, proj_w, proj_b, out_w),
+    then the final norm (a, b); for AdaLN (norm_a, norm_b) are the `linear.weight [2D, S]` / `linear.bias [2D]` of each
+    AdaptiveLayerNorm (modules/layers.py:31-47) -- all of them are evaluated by one batched GEMM.
+    Returns (out fp32 [B,T,D], hiddens fp32 [depth, B, T, D] = attention-layer inputs, kv bf16 [depth, B*T, 128]).
+    """
+
+    @staticmethod
+    def forward(ctx, spec: StackSpec, x, mask, style, seeds, *params):
+        B, T, D = x.shape
+        N = B * T
+        H, dh = spec.heads, spec.dim_head
+        x2 = x.contiguous().view(N, D)
+        keep = any(ctx.needs_input_grad)
+        layers: List[dict] = []
+        gb_all = style16 = w_ada16 = None
+        if spec.ada:
+            norm_w = [params[_norm_index(spec, i)] for i in range(spec.n_norms)]
+            norm_b = [params[_norm_index(spec, i) + 1] for i in range(spec.n_norms)]
+            style16 = K.cast_bf16(style.contiguous().view(N, -1))
+            w_ada16 = K.cast_bf16(torch.cat(norm_w, dim=0))
+            gb_all = K.gemm(style16, w_ada16, bias=torch.cat(norm_b, dim=0), out_dtype=BF16)   # [N, n_norms * 2D]
+
+        def norm_fwd(i_norm, xin, out_dtype=BF16):
+            if spec.ada:
+                gb = gb_all[:, i_norm * 2 * D:(i_norm + 1) * 2 * D]
+                y, mean, rstd = K.layer_norm_fwd(xin, None, None, gb, out_dtype=out_dtype, eps=spec.eps)
+            else:
+                j = _norm_index(spec, i_norm)
+                y, mean, rstd = K.layer_norm_fwd(xin, params[j], params[j + 1], out_dtype=out_dtype, eps=spec.eps)
+            return y, mean, rstd
+
+        n_keep = spec.depth if spec.return_hiddens else 0
+        hiddens = torch.empty((n_keep, N, D), dtype=F32, device=x.device)
+        kvs = torch.empty((n_keep, N, 2 * dh), dtype=BF16, device=x.device)
+        cur = x2
+        p_attn = spec.attn_dropout if spec.training else 0.0
+        p_ff = spec.ff_dropout if spec.training else 0.0
+        for l in range(spec.depth):
+            base = l * (PARAMS_PER_ATTN + PARAMS_PER_FF)
+            # ---- attention sub-layer
+            if spec.return_hiddens:
+                hiddens[l].copy_(cur)
+            to_q, to_k, to_v, to_out, logslopes = params[base + 2:base + 7]
+            xn, mean, rstd = norm_fwd(2 * l, cur)
+            wqkv16 = K.cast_bf16(torch.cat([to_q, to_k, to_v], dim=0))
+            qkv = K.gemm(xn, wqkv16, out_dtype=BF16)
+            ls = logslopes.detach().reshape(-1).contiguous()
+            o, lse = K.attention_fwd(qkv, mask, ls, B, T, H, spec.causal, p_attn, seeds[2 * l])
+            wo16 = K.cast_bf16(to_out.contiguous())
+            nxt = K.gemm(o, wo16, residual=cur, rowmask=None if mask is None else mask.view(-1), out_dtype=F32)
+            if spec.return_hiddens:
+                kvs[l].copy_(qkv[:, H * dh:])
+            rec_a = dict(x=cur, mean=mean, rstd=rstd, xn=xn, wqkv16=wqkv16, qkv=qkv, ls=ls, o=o, lse=lse, wo16=wo16) if keep else None
+            cur = nxt
+            # ---- feed-forward sub-layer
+            proj_w, proj_b, out_w = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
+            xn, mean, rstd = norm_fwd(2 * l + 1, cur)
+            w1_16 = K.cast_bf16(proj_w.contiguous())
+            u = K.gemm(xn, w1_16, bias=proj_b, out_dtype=BF16)
+            h = K.glu_fwd(u, p_ff, seeds[2 * l + 1])
+            w2_16 = K.cast_bf16(out_w.contiguous())
+            nxt = K.gemm(h, w2_16, residual=cur, out_dtype=F32)
+            rec_f = dict(x=cur, mean=mean, rstd=rstd, xn=xn, w1_16=w1_16, u=u, h=h, w2_16=w2_16) if keep else None
+            cur = nxt
+            layers.append((rec_a, rec_f))
+        out, mean, rstd = norm_fwd(2 * spec.depth, cur, out_dtype=F32)
+        if keep:
+            ctx.spec, ctx.shape, ctx.mask, ctx.seeds = spec, (B, T, D), mask, seeds
+            ctx.layers, ctx.final = layers, dict(x=cur, mean=mean, rstd=rstd)
+            ctx.ada = (gb_all, style16, w_ada16)
+            ctx.params = params
+            ctx.style_shape = None if style is None else style.shape
+        ctx.mark_non_differentiable(hiddens, kvs)
+        return out.view(B, T, D), hiddens.view(n_keep, B, T, D), kvs
+
+    @staticmethod
+    def backward(ctx, g_out, _g_hiddens, _g_kvs):
+        spec: StackSpec = ctx.spec
+        B, T, D = ctx.shape
+        N = B * T
+        H = spec.heads
+        params = ctx.params
+        mask = ctx.mask
+        gb_all, style16, w_ada16 = ctx.ada
+        grads: List[Optional[Tensor]] = [None] * len(params)
+        dgb_all = torch.empty_like(gb_all) if spec.ada else None
+        p_attn = spec.attn_dropout if spec.training else 0.0
+        p_ff = spec.ff_dropout if spec.training else 0.0
+
+        def norm_bwd(i_norm, dy16, rec, dres):
+            if spec.ada:
+                sl = slice(i_norm * 2 * D, (i_norm + 1) * 2 * D)
+                return K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], None, gb_all[:, sl], dres=dres, dx_dtype=F32,
+                                        dgb=dgb_all[:, sl])
+            j = _norm_index(spec, i_norm)
+            dw = torch.zeros_like(params[j])
+            db = torch.zeros_like(params[j])
+            dx = K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], params[j], dres=dres, dx_dtype=F32, dw=dw, db=db)
+            grads[j], grads[j + 1] = dw, db
+            return dx
+
+        g = norm_bwd(2 * spec.depth, K.cast_bf16(g_out.contiguous().view(N, D)), ctx.final, None)
+        for l in reversed(range(spec.depth)):
+            base = l * (PARAMS_PER_ATTN + PARAMS_PER_FF)
+            rec_a, rec_f = ctx.layers[l]
+            # ---- feed-forward backward:  x_out = x + W2 glu(W1 LN(x) + b1)
+            g16 = K.cast_bf16(g)
+            grads[base + PARAMS_PER_ATTN + 4] = K.gemm(g16, rec_f["h"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
+            db1 = torch.zeros(2 * spec.ff_inner, dtype=F32, device=g.device)
+            du = K.glu_bwd(dh, rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
+            grads[base + PARAMS_PER_ATTN + 3] = db1
+            grads[base + PARAMS_PER_ATTN + 2] = K.gemm(du, rec_f["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            dxn = K.gemm(du, rec_f["w1_16"], trans_b=True, out_dtype=BF16)
+            g = norm_bwd(2 * l + 1, dxn, rec_f, g)
+            # ---- attention backward:  x_out = x + mask * Wo attn(Wqkv LN(x))
+            g16 = K.cast_bf16(g, None if mask is None else mask.view(-1))
+            grads[base + 5] = K.gemm(g16, rec_a["o"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            do = K.gemm(g16, rec_a["wo16"], trans_b=True, out_dtype=BF16)
+            dls = torch.zeros(H, dtype=F32, device=g.device)
+            dqkv = K.attention_bwd(rec_a["qkv"], mask, rec_a["ls"], rec_a["o"], do, rec_a["lse"], dls, B, T, H, spec.causal, p_attn,
+                                   ctx.seeds[2 * l])
+            grads[base + 6] = dls.view(params[base + 6].shape)
+            dwqkv = K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            hq = H * spec.dim_head
+            grads[base + 2], grads[base + 3], grads[base + 4] = dwqkv[:hq], dwqkv[hq:hq + spec.dim_head], dwqkv[hq + spec.dim_head:]
+            dxn = K.gemm(dqkv, rec_a["wqkv16"], trans_b=True, out_dtype=BF16)
+            g = norm_bwd(2 * l, dxn, rec_a, g)
+        d_style = None
+        if spec.ada:
+            dw_ada = K.gemm(dgb_all, style16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)   # [n_norms*2D, S]
+            db_ada = K.colsum(dgb_all)
+            for i in range(spec.n_norms):
+                j = _norm_index(spec, i)
+                grads[j] = dw_ada[i * 2 * D:(i + 1) * 2 * D]
+                grads[j + 1] = db_ada[i * 2 * D:(i + 1) * 2 * D]
+            if ctx.needs_input_grad[3]:
+                d_style = K.gemm(dgb_all, w_ada16, trans_b=True, out_dtype=F32).view(ctx.style_shape)
+        return (None, g.view(B, T, D), None, d_style, None) + tuple(grads)
+
+
+def _norm_index(spec: StackSpec, i_norm: int) -> int:
+    """Index into the flat params tuple of the first tensor of norm number i_norm (0 .. 2*depth)."""
+    if i_norm == 2 * spec.depth:
+        return spec.depth * (PARAMS_PER_ATTN + PARAMS_PER_FF)
+    l, is_ff = divmod(i_norm, 2)
+    return l * (PARAMS_PER_ATTN + PARAMS_PER_FF) + (PARAMS_PER_ATTN if is_ff else 0)
+
+
+# ----------------------------------------------------------------------------- hierarchical latents (a8)
+class LatentLevelsFn(torch.autograd.Function):
+    """All VAE levels of MMDTupleTransformer._forward_latents (mmd_transformer.py:242-278, 304-368), hierarchical with context.
+
+    hidden fp32 [B,T,D]; mask bool [B,T]; segments: per level int64 [B,T] or None ('mean'); S: per-level slot count.
+    Returns style fp32 [B,T,sum z] (the un-dropped, masked embeddings) followed by per level (latents [B,S,z], lmask [B,S]).
+    """
+
+    @staticmethod
+    def forward(ctx, hidden, mask, segments: Sequence[Optional[Tensor]], slots: Sequence[int], zs: Sequence[int], *wb):
+        B, T, D = hidden.shape
+        hidden = hidden.contiguous()
+        total = int(sum(zs))
+        style = torch.zeros((B, T, total), dtype=F32, device=hidden.device)
+        outs, saved = [], []
+        col = 0
+        for lvl, (seg, S, z) in enumerate(zip(segments, slots, zs)):
+            W, b = wb[2 * lvl].contiguous(), wb[2 * lvl + 1].contiguous()
+            lat, lmask, pooled, counts = K.latent_level_fwd(hidden, style, mask, seg, W, b, col, S, z)
+            outs += [lat, lmask]
+            saved.append((seg, S, z, col, W, pooled, counts, lmask))
+            col += z
+        ctx.saved = saved
+        ctx.mask = mask
+        ctx.shape = (B, T, D)
+        ctx.mark_non_differentiable(*[o for o in outs[1::2]])
+        return (style, *outs)
+
+    @staticmethod
+    def backward(ctx, d_style, *d_outs):
+        B, T, D = ctx.shape
+        d_style = d_style.contiguous().clone() if d_style is not None else None
+        if d_style is None:
+            d_style = torch.zeros((B, T, sum(s[2] for s in ctx.saved)), dtype=F32, device=ctx.mask.device)
+        d_hidden = torch.zeros((B, T, D), dtype=F32, device=d_style.device)
+        grads_wb: List[Optional[Tensor]] = [None] * (2 * len(ctx.saved))
+        for lvl in reversed(range(len(ctx.saved))):
+            seg, S, z, col, W, pooled, counts, lmask = ctx.saved[lvl]
+            d_lat = d_outs[2 * lvl]
+            d_lat = None if d_lat is None else d_lat.contiguous()
+            dW = torch.zeros_like(W)
+            db = torch.zeros(z, dtype=F32, device=W.device)
+            K.latent_level_bwd(d_style, col, d_lat, ctx.mask, seg, W, pooled, counts, lmask, d_hidden, dW, db, S, z)
+            grads_wb[2 * lvl], grads_wb[2 * lvl + 1] = dW, db
+        return (d_hidden, None, None, None, None) + tuple(grads_wb)
+
+
+class MMDFn(torch.autograd.Function):
+    """Fused pairwise-RBF MMD between the prior sample z and the valid latents (mmd_transformer.py:505-534)."""
+
+    @staticmethod
+    def forward(ctx, y, w, z_prior):
+        loss, grad = K.mmd_fwd_bwd(z_prior.contiguous(), y.contiguous(), w.contiguous())
+        ctx.saved = grad
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved * g, None, None
+
+
+# ----------------------------------------------------------------------------- tied LM head + masked CE (a10)
+class TiedHeadCEFn(torch.autograd.Function):
+    """loss = mean over labelled fields of CE(LN(h @ Wp)[field] @ table_field^T, labels[field]).
+
+    models/scoreperformer/embeddings.py:345-353 + wrappers.py:49-59.  Only the `fields` that carry labels are contracted;
+    the gradient wrt logits (softmax - onehot) is produced in the same pass as the loss, so fp32 logits are consumed
+    where they are produced and only the bf16 dlogits of the labelled fields are kept for the two backward GEMMs.
+    Returns (loss, per_field_loss [n_fields_total] (nan where inactive), counts).
+    """
+
+    @staticmethod
+    def forward(ctx, hidden, proj_w, ln_w, ln_b, table, labels, sizes: Tuple[int, ...], fields: Tuple[int, ...], emb: int,
+                ignore_index: int):
+        n = hidden.shape[0]
+        dev = hidden.device
+        h16 = K.cast_bf16(hidden.contiguous()) if hidden.dtype == F32 else hidden.contiguous()
+        wp16 = K.cast_bf16(proj_w.contiguous())                    # [dim, F*emb]
+        e_raw = K.gemm(h16, wp16, trans_b=True, out_dtype=BF16)     # [n, F*emb]
+        e, mean, rstd = K.layer_norm_fwd(e_raw, ln_w, ln_b, out_dtype=BF16)
+        table16 = K.cast_bf16(table.contiguous())
+        offs = [0]
+        for v in sizes[:-1]:
+            offs.append(offs[-1] + v)
+        nf = len(sizes)
+        loss_sum = torch.zeros(nf, dtype=F32, device=dev)
+        count = torch.zeros(nf, dtype=F32, device=dev)
+        dlogits = {}
+        need_grad = any(ctx.needs_input_grad)
+        for f in fields:
+            V = sizes[f]
+            logits = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + V], out_dtype=F32)
+            dl = torch.empty((n, (V + 7) // 8 * 8), dtype=BF16, device=dev) if need_grad else None
+            K.ce_rows(logits, labels[:, f], V, loss_sum[f:f + 1], count[f:f + 1], dl, None, ignore_index)
+            dlogits[f] = dl
+        active = count > 0
+        per_field = loss_sum / count.clamp(min=1.0)
+        n_active = active.sum().clamp(min=1)
+        loss = (per_field * active).sum() / n_active
+        ctx.saved = (h16, wp16, e_raw, e, mean, rstd, ln_w, table16, dlogits, count, active, n_active)
+        ctx.meta = (sizes, fields, emb, offs, hidden.dtype)
+        ctx.mark_non_differentiable(per_field, count)
+        return loss, per_field, count
+
+    @staticmethod
+    def backward(ctx, g, _g1, _g2):
+        h16, wp16, e_raw, e, mean, rstd, ln_w, table16, dlogits, count, active, n_active = ctx.saved
+        sizes, fields, emb, offs, h_dtype = ctx.meta
+        n = h16.shape[0]
+        coef = (g * active.float() / (count.clamp(min=1.0) * n_active)).contiguous()       # [n_fields] device scalars
+        de = torch.zeros_like(e)
+        dtable = torch.zeros((sum(sizes), emb), dtype=F32, device=h16.device)
+        for f in fields:
+            V, dl = sizes[f], dlogits[f]
+            a = dl[:, :V] if dl.shape[1] != V else dl
+            K.gemm(a, table16[offs[f]:offs[f] + V], trans_b=True, out=de[:, f * emb:(f + 1) * emb], alpha=coef[f:f + 1])
+            K.gemm(a, e[:, f * emb:(f + 1) * emb], trans_a=True, trans_b=True, out=dtable[offs[f]:offs[f] + V], split_k=0,
+                   alpha=coef[f:f + 1])
+        dln_w, dln_b = torch.zeros_like(ln_w), torch.zeros_like(ln_w)
+        de_raw = K.layer_norm_bwd(de, e_raw, mean, rstd, ln_w, dx_dtype=BF16, dw=dln_w, db=dln_b)
+        dproj = K.gemm(h16, de_raw, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)     # [dim, F*emb]
+        dh = K.gemm(de_raw, wp16, out_dtype=h_dtype)                                           # [n, dim]
+        return dh, dproj, dln_w, dln_b, dtable, None, None, None, None, None
+
+
+def tied_head_logits(hidden: Tensor, proj_w: Tensor, ln_w: Tensor, ln_b: Tensor, table: Tensor, sizes: Sequence[int],
+                     fields: Sequence[int], emb: int) -> List[Tensor]:
+    """Inference-side logits (fp32 [n, V_f] per requested field); no autograd."""
+    with torch.no_grad():
+        h16 = K.cast_bf16(hidden.contiguous()) if hidden.dtype == F32 else hidden.contiguous()
+        e_raw = K.gemm(h16, K.cast_bf16(proj_w.contiguous()), trans_b=True, out_dtype=BF16)
+        e, _, _ = K.layer_norm_fwd(e_raw, ln_w, ln_b, out_dtype=BF16, need_stats=False)
+        table16 = K.cast_bf16(table.contiguous())
+        offs = [0]
+        for v in sizes[:-1]:
+            offs.append(offs[-1] + v)
+        return [K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + sizes[f]], out_dtype=F32) for f in fields]
+
+
+# ----------------------------------------------------------------------------- classifier heads (a11)
+class ClassifierHeadsFn(torch.autograd.Function):
+    """loss_weight * mean_g weightedCE(Linear_g(dropout(x[rowmask])), labels[rowmask, g])  (models/classifiers/model.py:202-223).
+
+    x fp32 [n, in_dim] is treated as detached (detach_inputs: true in every recipe); W/bias are the concatenated heads.
+    Returns (loss, per_head_loss [n_heads])."""
+
+    @staticmethod
+    def forward(ctx, x, rowmask, labels, W, bias, class_w, n_classes: Tuple[int, ...], dropout_p: float, seed: int, loss_weight: float):
+        x = x.detach().contiguous()
+        W, bias = W.contiguous(), bias.contiguous()
+        g = len(n_classes)
+        num = torch.zeros(g, dtype=F32, device=x.device)
+        den = torch.zeros(g, dtype=F32, device=x.device)
+        K.clf_heads(x, rowmask, labels, W, bias, class_w, n_classes, dropout_p, seed, num=num, den=den)
+        per_head = num / den.clamp(min=1e-20)
+        loss = loss_weight * per_head.sum() / g
+        ctx.saved = (x, rowmask, labels, W, bias, class_w, den)
+        ctx.meta = (n_classes, dropout_p, seed, loss_weight)
+        ctx.mark_non_differentiable(per_head)
+        return loss, per_head
+
+    @staticmethod
+    def backward(ctx, gl, _g):
+        x, rowmask, labels, W, bias, class_w, den = ctx.saved
+        n_classes, dropout_p, seed, loss_weight = ctx.meta
+        scale = (gl * loss_weight / len(n_classes)) / den.clamp(min=1e-20)
+        dW, db = torch.zeros_like(W), torch.zeros_like(bias)
+        K.clf_heads(x, rowmask, labels, W, bias, class_w, n_classes, dropout_p, seed, dlogit_scale=scale.contiguous(), dW=dW, db=db)
+        return None, None, None, dW, db, None, None, None, None, None

@@ -1,0 +1,64 @@
+"""End-to-end parity of the sm_100a training step against the CPU oracle and the reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    return parity.build_model(dropout=False, device="cuda")
+
+
+@pytest.mark.parametrize("name", ["train_b2_t48.npz", "train_b3_t33.npz"])
+def test_step_matches_reference_golden(model, name):
+    """Losses / hidden states / selected gradients against vectors produced by the UNMODIFIED reference."""
+    g = parity.golden(name)
+    batch = parity.make_batch(int(g["B"]), int(g["T"]), seed=int(g["seed"]))
+    out = parity.run_product_step(model, batch, parity.z_from_golden(g))
+    for key, want in zip(g["loss_keys"], g["loss_vals"]):
+        got = float(out.losses[str(key)])
+        assert abs(got - want) <= 2e-2 * max(abs(want), 1e-2), f"{key}: {got} vs reference {want}"
+    assert abs(float(out.loss) - float(g["loss"])) <= 2e-2 * abs(float(g["loss"]))
+    for name_, t in (("score_hidden", out.score_encoder.hidden_state), ("perf_hidden", out.perf_encoder.hidden_state),
+                     ("embeddings", out.perf_encoder.embeddings), ("dec_hidden", out.perf_decoder.hidden_state)):
+        want = torch.from_numpy(g[name_])
+        err = float((t.detach().float().cpu() - want).abs().max() / want.abs().max())
+        assert err < 6e-2, f"{name_}: {err}"
+    sd = dict(model.state_dict(keep_vars=True))
+    for k in g.files:
+        if k.startswith("grad/"):
+            cd = parity.cosine_distance(sd[k[5:]].grad.float().cpu(), torch.from_numpy(g[k]))
+            assert cd <= 5e-3, f"{k}: cosine distance {cd}"
+    for key in ("Velocity", "Tempo", "RelOnsetDev", "RelPerfDuration", "Bar", "NotesInOnset"):
+        want = torch.from_numpy(g[f"logits/{key}"])
+        got = out.perf_decoder.logits[key].float().cpu()
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < 4e-2, f"logits/{key}: {err}"
+
+
+@pytest.mark.parametrize("B,T,seed", [(2, 48, 1), (4, 256, 1234), (3, 130, 7)])
+def test_step_matches_oracle(model, B, T, seed):
+    """Full gradient check (every parameter) against the oracle on the same seeded batch; C1 is (4, 256)."""
+    torch.manual_seed(seed)
+    batch = parity.make_batch(B, T, seed=seed)
+    z = [torch.randn(256, d) for d in (32, 20, 8, 4)]
+    parity.compare_step(model, batch, z)
+
+
+def test_dropout_training_step_runs():
+    """Recipe dropouts on: finite loss and gradients, different seeds give different losses."""
+    m = parity.build_model(dropout=True, device="cuda")
+    batch = {k: v.cuda() for k, v in parity.make_batch(4, 128, seed=3).items()}
+    m.train()
+    torch.manual_seed(1)
+    l1 = m(**batch).loss
+    l1.backward()
+    torch.manual_seed(2)
+    l2 = m(**batch).loss
+    assert torch.isfinite(l1) and torch.isfinite(l2) and float(l1) != float(l2)
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
