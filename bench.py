@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the ScorePerformer training step (BASELINE.json: train note-tuples/s at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a arm
+    python bench.py --impl reference ...                      # the reference algorithm on the host CPU (oracle port)
+
+A "step" is one full training step of the default recipe (forward, backward, gradient all-reduce when N > 1, clip,
+AdamW) on one synthetic SPMuple batch of `configs[1]`: B=64 sequences x T=512 notes per GPU, bf16 tensor-core math,
+fp32 master weights, recipe dropouts ON.  `value` times K steps with the batch resident in HBM; `e2e` times the same
+steps fed from pinned host memory (H2D of the int64 batch every step, D2H of the loss every step).
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train note-tuples/sec"
+UNIT = "note-tuples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU (configs[1]: 64)")
+    ap.add_argument("--seq", type=int, default=512, help="notes per sequence (configs[1]: 512)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel launch table of one step")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thread = [], None, None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- algorithmic work
+def algorithmic_flops_per_tuple(T: int) -> float:
+    """fwd+bwd FLOPs per note-tuple of a training step: 3 * (24.28 MF + 8192 * T)."""
+    return 3.0 * (24.28e6 + 8192.0 * T)
+
+
+# ----------------------------------------------------------------------------- reference arm / CPU baseline (oracle port)
+def cpu_reference_throughput(batch: int, seq: int, steps: int, warmup: int):
+    """Times the reference algorithm's training forward+backward on the host cores (oracle port, fp32, all threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from tests import parity
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = parity.build_model(dropout=False, device="cpu")
+    sd = parity.oracle_state(model)
+    spec = parity.oracle_spec(model)
+    import model_oracle as mo
+    data = parity.make_batch(batch, seq, seed=1234)
+    z = [torch.randn(256, d) for d in (32, 20, 8, 4)]
+    times = []
+    for i in range(warmup + steps):
+        for t in set(id(v) for v in sd.values()):
+            pass
+        for v in sd.values():
+            if v.grad is not None:
+                v.grad = None
+        t0 = time.perf_counter()
+        out = mo.scoreperformer_forward(sd, data, spec, z)
+        out["loss"].backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return batch * seq / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b, t = 2, args.seq
+    value, ms, cores = cpu_reference_throughput(b, t, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"ScorePerformer default recipe training step, seq={args.seq} (configs[1]); reference arm sample "
+                               f"B={b} sequences per step on the host CPU", "global_batch": b, "seq_len": t},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"fwd+bwd of B={b} x T={t} per step, fp32, dropouts off, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist
+    from scoreperformer_b200 import kernels as K
+    from scoreperformer_b200.models import ScorePerformer
+    from scoreperformer_b200.parallel import GradientBuckets
+    from scoreperformer_b200.recipes import default_model_config
+    from scoreperformer_b200.synthetic import make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device: scoreperformer_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(23)
+    model = ScorePerformer.init(default_model_config(dropout=True)).to(dev)
+    model.train()
+    model.perf_encoder.exact_latent_shapes = False          # static segment tables: no host sync inside the step
+    model.perf_decoder.label_fields = (3, 5, 10, 11)        # MixedLM collator labels (base.yaml:64-65): no probe sync
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=1e-6, fused=True)
+    buckets = GradientBuckets(model) if world > 1 else None
+    params = [p for p in model.parameters()]
+
+    B, T = args.batch, args.seq
+    host_batch = {k: v.pin_memory() for k, v in make_batch(B, T, seed=1234 + rank).items()}
+    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_batch.values())
+
+    def step(batch):
+        out = model(**batch)
+        out.loss.backward()
+        if buckets is not None:
+            buckets.sync_gradients()
+        torch.nn.utils.clip_grad_norm_(params, 2.0, foreach=True)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return out.loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, feed):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            feed()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step(dev_batch)
+
+    if args.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    K.LAUNCHES = 0
+    ms_total = timed(args.steps, lambda: step(dev_batch))
+    launches = K.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e_step():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
+        loss = step(batch)
+        return float(loss)                                   # D2H read of the step's result (sync)
+
+    e2e_step()
+    ms_e2e = timed(args.steps, e2e_step)
+
+    ms_step = ms_total / args.steps
+    tuples = B * T * world
+    value = tuples / (ms_step / 1e3)
+    e2e_value = tuples / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel family (the tcgen05 GEMM): time every GEMM launch of one step with CUDA events
+    peaks = load_peaks()
+    roofline = None
+    if rank == 0:
+        records = []
+        orig = K.gemm
+
+        def timed_gemm(a, b, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = orig(a, b, **kw)
+            e.record()
+            m, k_ = (a.shape[1], a.shape[0]) if kw.get("trans_a") else a.shape
+            n = b.shape[1] if kw.get("trans_b") else b.shape[0]
+            records.append((s, e, 2.0 * m * n * k_, (m, n, k_)))
+            return out
+        K.gemm = timed_gemm
+        import scoreperformer_b200.fused as fused_mod
+        fused_mod.K.gemm = timed_gemm
+        step(dev_batch)
+        torch.cuda.synchronize()
+        K.gemm = orig
+        fused_mod.K.gemm = orig
+        tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in records)
+        tot_fl = sum(f for _, _, f, _ in records)
+        achieved = tot_fl / (tot_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA), all launches of one step",
+                    "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                    "traffic": None, "launches_per_step": len(records), "gemm_ms_per_step": tot_ms,
+                    "gemm_share_of_step": tot_ms / ms_step, "peak_source": peaks["source"],
+                    "step_algorithmic_tflops": algorithmic_flops_per_tuple(T) * B * T / (ms_step / 1e3) / 1e12,
+                    "step_frac_of_peak": algorithmic_flops_per_tuple(T) * B * T / (ms_step / 1e3) / 1e12 / peaks["tflops"]}
+        if args.profile_kernels:
+            agg = {}
+            for s, e, f, shp in records:
+                a = agg.setdefault(shp, [0, 0.0, 0.0])
+                a[0] += 1
+                a[1] += s.elapsed_time(e)
+                a[2] += f
+            for shp, (c, ms_, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                print(f"# gemm M,N,K={shp}: {c} launches, {ms_:.3f} ms, {f / ms_ / 1e9:.1f} TFLOP/s", file=sys.stderr)
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, ms_cpu, cores = cpu_reference_throughput(4, 256, steps=3, warmup=1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "configs[0]: fwd+bwd of B=4 x T=256 (1024 note-tuples) per step, fp32 oracle port of the reference "
+                                  "path, 1 warm-up + 3 timed steps", "ms_per_step": ms_cpu}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "ScorePerformer default recipe (recipes/scoreperformer/base.yaml) training step: fwd+bwd+clip+AdamW, "
+                                   "bf16 tensor-core math / fp32 master weights, recipe dropouts on (configs[1])",
+                       "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world}",
+                       "l2": "per-step activations (>3 GB) far exceed the 126 MB L2; no explicit flush needed"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "gpu_launches_per_step": launches / args.steps,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

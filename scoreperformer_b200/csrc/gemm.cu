@@ -135,35 +135,82 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+        // Each warp drains its 32 accumulator rows 64 columns at a time: TMEM -> registers -> padded smem (row stride 68
+        // floats keeps float4 accesses conflict-free) -> 4 rows x 8 lanes x 8 columns per pass, so every global access
+        // is a 16/32-byte vector and a warp instruction covers four full 128/256-byte row segments.
+        constexpr int SST = 68;
+        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * SST);
         const int row_base = m0 + q * 32;
         float* Cf = reinterpret_cast<float*>(p.C);
         __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+        const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 1.f;
+        const int sub_row = lane >> 3;          // 0..3
+        const int sub_col = (lane & 7) * 8;     // 0..56
+        const bool vec_ok = (p.ldc % 8 == 0) && (p.residual == nullptr || p.ldr % 4 == 0);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            const int col = n0 + c * 32 + lane;
-            if (n0 + c * 32 >= p.N) break;
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            tmem_ld_wait();
+        for (int c = 0; c < BN / 64; ++c) {
+            const int col0 = n0 + c * 64;
+            if (col0 >= p.N) break;
+            {
+                uint32_t v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(v[j]);
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + half * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stage + lane * SST + half * 32 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            }
             __syncwarp();
-            const bool col_ok = col < p.N;
-            const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + col) : 0.f;
-            const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 1.f;
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
+            const int col = col0 + sub_col;
+            float bias[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bias[j] = (p.bias != nullptr && col + j < p.N) ? __ldg(p.bias + col + j) : 0.f;
+            const bool full = vec_ok && (col + 8 <= p.N);
+#pragma unroll 2
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + sub_row;
                 const int row = row_base + r;
-                if (row >= p.M) break;
-                float val = stage[r * 33 + lane] * alpha + bias;
-                if (col_ok) {
-                    if (p.rowmask != nullptr) val = p.rowmask[row] ? val : 0.f;
-                    if (p.residual != nullptr) val += p.residual[(size_t)row * p.ldr + col];
-                    const size_t off = (size_t)row * p.ldc + col;
-                    if (p.atomic) atomicAdd(Cf + off, val);
-                    else if (p.c_fp32) Cf[off] = val;
-                    else Cb[off] = __float2bfloat16_rn(val);
+                if (row >= p.M || col >= p.N) continue;
+                const float4 a0 = *reinterpret_cast<const float4*>(stage + r * SST + sub_col);
+                const float4 a1 = *reinterpret_cast<const float4*>(stage + r * SST + sub_col + 4);
+                float val[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const bool keep = p.rowmask == nullptr || p.rowmask[row] != 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) val[j] = keep ? val[j] * alpha + bias[j] : 0.f;
+                const size_t off = (size_t)row * p.ldc + col;
+                if (full) {
+                    if (p.residual != nullptr) {
+                        const float4 r0 = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col);
+                        const float4 r1 = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col + 4);
+                        val[0] += r0.x; val[1] += r0.y; val[2] += r0.z; val[3] += r0.w;
+                        val[4] += r1.x; val[5] += r1.y; val[6] += r1.z; val[7] += r1.w;
+                    }
+                    if (p.atomic) {   // split-K / accumulate: two 16-byte vector reductions per lane
+                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(Cf + off), "f"(val[0]), "f"(val[1]), "f"(val[2]), "f"(val[3]) : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(Cf + off + 4), "f"(val[4]), "f"(val[5]), "f"(val[6]), "f"(val[7]) : "memory");
+                    } else if (p.c_fp32) {
+                        *reinterpret_cast<float4*>(Cf + off) = make_float4(val[0], val[1], val[2], val[3]);
+                        *reinterpret_cast<float4*>(Cf + off + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                    } else {
+                        uint4 o;
+                        o.x = pack_bf16x2(val[0], val[1]); o.y = pack_bf16x2(val[2], val[3]);
+                        o.z = pack_bf16x2(val[4], val[5]); o.w = pack_bf16x2(val[6], val[7]);
+                        *reinterpret_cast<uint4*>(Cb + off) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (col + j < p.N) {
+                            float vj = val[j];
+                            if (p.residual != nullptr) vj += p.residual[(size_t)row * p.ldr + col + j];
+                            if (p.atomic) atomicAdd(Cf + off + j, vj);
+                            else if (p.c_fp32) Cf[off + j] = vj;
+                            else Cb[off + j] = __float2bfloat16_rn(vj);
+                        }
+                    }
                 }
             }
             __syncwarp();
