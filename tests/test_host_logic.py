@@ -1,0 +1,137 @@
+"""CPU: host-side logic -- drop-in API surface, config plumbing, C-ABI symbol table, gradient buckets over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests import parity
+from scoreperformer_b200 import lib as spb_lib
+from scoreperformer_b200.config import load_recipe, wrap
+from scoreperformer_b200.models import EVALUATORS, MODELS
+from scoreperformer_b200.recipes import default_model_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_registries_and_state_dict_layout():
+    assert set(MODELS) == {"Performer", "ScorePerformer"} and set(EVALUATORS) == {"ScorePerformerEvaluator"}
+    model = parity.build_model()
+    sd = model.state_dict()
+    assert len(sd) == 463
+    assert sum(p.numel() for p in model.parameters()) == 11_603_049
+    # tied tables: one storage under every alias
+    a = sd["perf_decoder.model.token_emb.embs.Velocity.index_weight"]
+    for alias in ("score_encoder", "perf_encoder", "perf_decoder.model.lm_head"):
+        key = f"{alias}.token_emb.embs.Velocity.index_weight" if "lm_head" not in alias else f"{alias}.embs.Velocity.index_weight"
+        assert sd[key].data_ptr() == a.data_ptr(), key
+    assert sd["perf_decoder.model.lm_head.project_emb.weight"].data_ptr() == sd["perf_decoder.model.token_emb.project_emb.weight"].data_ptr()
+    g = parity.golden("train_b2_t48.npz")
+    for k in g["grad_norm_keys"]:
+        assert str(k) in sd, k
+    assert sd["perf_encoder.vae_head.onset_mean.linear.weight"].shape == (4, 316)
+    assert sd["perf_decoder.model.transformer.final_norm.linear.weight"].shape == (512, 64)
+
+
+def test_outputs_and_forward_signature_match_reference_names():
+    import dataclasses
+    import inspect
+    from scoreperformer_b200.models.scoreperformer.model import ScorePerformer, ScorePerformerOutputs, ScorePerformerEncoderOutputs
+    from scoreperformer_b200.models.scoreperformer.mmd_transformer import MMDTupleTransformerOutput
+    assert [f.name for f in dataclasses.fields(ScorePerformerOutputs)] == \
+        ["perf_decoder", "score_encoder", "perf_encoder", "classifiers", "loss", "losses"]
+    assert [f.name for f in dataclasses.fields(ScorePerformerEncoderOutputs)] == \
+        ["score_embeddings", "score_mask", "perf_embeddings", "score_encoder", "perf_encoder"]
+    assert [f.name for f in dataclasses.fields(MMDTupleTransformerOutput)][-6:] == \
+        ["latents", "embeddings", "full_embeddings", "dropout_mask", "loss", "losses"]
+    assert list(inspect.signature(ScorePerformer.forward).parameters)[1:] == \
+        ["perf", "perf_mask", "score", "score_mask", "noisy_perf", "noisy_perf_mask", "masked_perf", "labels", "bars", "beats",
+         "onsets", "directions", "deadpan_mask"]
+
+
+def test_cpu_forward_fails_loudly():
+    model = parity.build_model()
+    batch = parity.make_batch(1, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        model(**batch)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference recipes only exist in the authoring container")
+def test_unmodified_recipes_load_and_match_builtin_default():
+    cfg = load_recipe("scoreperformer/base.yaml", os.path.join(REF, "recipes"))["model"]
+    builtin = default_model_config()
+    for stack in ("score_encoder", "perf_encoder", "perf_decoder"):
+        got = {k: v for k, v in cfg[stack].items()}
+        want = {k: v for k, v in builtin[stack].items()}
+        want["token_embeddings"] = {k: v for k, v in want["token_embeddings"].items() if k != "token_values"}
+        assert got == want, stack
+    assert cfg["classifiers"]["classifier"] == builtin["classifiers"]["classifier"]
+    assert cfg["dim"] == 256 and cfg["mode"] == "mixlm" and cfg["tie_token_emb"] is True
+    for name in ("no_classifiers.yaml", "custom_hierarchy.yaml", "minimal.yaml", "ablation/no_saln.yaml", "ablation/no_score_enc.yaml",
+                 "ablation/no_masked_seq.yaml", "ablation/no_cont_tokens.yaml", "ablation/no_io_tie.yaml"):
+        assert "model" in load_recipe("scoreperformer/" + name, os.path.join(REF, "recipes")), name
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference recipes only exist in the authoring container")
+@pytest.mark.parametrize("name", ["no_classifiers.yaml", "custom_hierarchy.yaml", "ablation/no_saln.yaml", "ablation/no_score_enc.yaml",
+                                  "ablation/no_masked_seq.yaml", "ablation/no_cont_tokens.yaml", "ablation/no_io_tie.yaml"])
+def test_variant_recipes_construct(name):
+    """Every shipped recipe must construct (API surface); only the default family has a CUDA forward in round 1."""
+    import copy
+    cfg = load_recipe("scoreperformer/" + name, os.path.join(REF, "recipes"))["model"]
+    base = default_model_config()
+    cfg["num_tokens"], cfg["num_score_tokens"] = base["num_tokens"], base["num_score_tokens"]
+    for stack in ("score_encoder", "perf_encoder", "perf_decoder"):
+        if cfg.get(stack) is not None:
+            keys = base["num_score_tokens"] if stack == "score_encoder" else base["num_tokens"]
+            cfg[stack]["token_embeddings"]["token_values"] = {k: base["perf_decoder"]["token_embeddings"]["token_values"][k] for k in keys}
+    if cfg.get("classifiers") is not None:
+        cfg["classifiers"]["num_classes"] = base["classifiers"]["num_classes"]
+        cfg["classifiers"]["class_samples"] = base["classifiers"]["class_samples"]
+    model = MODELS["ScorePerformer"].init(wrap(copy.deepcopy(cfg)))
+    assert sum(p.numel() for p in model.parameters()) > 1_000_000
+
+
+def test_constructor_error_behaviour():
+    from scoreperformer_b200.modules.transformer import FeedForward
+    ff = FeedForward.init({"mult": 2, "glu": True, "bogus_key": 1, "_private": 2}, dim=64)      # unknown keys dropped with a warning
+    assert ff.inner_dim == 128
+    with pytest.raises(RuntimeError, match="mandatory"):
+        FeedForward.init({"dim": "???"})
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library must export exactly what include/spb200.h declares (no compute calls here)."""
+    path = spb_lib.build()
+    handle = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "spb200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(spb_\w+)\(", header, flags=re.M))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in spb200.h but not exported"
+    assert declared - {"spb_last_error", "spb_abi_version"} == set(spb_lib.SIGNATURES), "lib.py binding table out of sync with the header"
+    assert spb_lib.lib().spb_abi_version() == 1
+    # error path works without a GPU: bad arguments are rejected before any launch
+    rc = spb_lib.lib().spb_gemm_bf16(None, None, None, 0, 0, 0, 0, 0, 8, 8, 8, None, None, 0, None, 0, 1, 0, None, None)
+    assert rc == -1 and b"null operand" in spb_lib.lib().spb_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scoreperformer_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "model_oracle" not in src and "import oracle" not in src and "ref_shim" not in src, os.path.join(dirpath, f)
+
+
+def test_gradient_buckets_gloo_world2():
+    """N>1 path on CPU: two gloo ranks with different gradients end up with the mean in every p.grad."""
+    script = os.path.join(ROOT, "tests", "ddp_gloo_worker.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29613", script], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("DDP-OK") == 2, res.stdout[-2000:]
