@@ -574,3 +574,94 @@ extern "C" int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mas
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
+
+// ------------------------------------------------------------------------------------------- incremental decode
+// One new query position per sequence against a KV cache (modules/transformer/attention.py:155-156 + transformer.py:161-186).
+// grid (B), 32*H threads: warp h = head h.  Scores: lane <-> key (16-byte loads of the key row); PV: lane <-> 2 value dims.
+namespace {
+constexpr int DEC_MAX_T = 4096;
+
+__global__ void attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ kv, int ld_kv,
+                                   long long kv_batch_stride, const uint8_t* __restrict__ key_mask, int mask_stride,
+                                   const float* __restrict__ logslopes, __nv_bfloat16* __restrict__ out, int ld_out, int n_keys,
+                                   int q_pos, float scale) {
+    extern __shared__ float sp[];                  // [H][n_keys]
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* p = sp + (size_t)h * n_keys;
+    const __nv_bfloat16* kvb = kv + (size_t)b * kv_batch_stride;
+    const float slope = __expf(logslopes[h]);
+    float qv[DH];
+    {
+        const __nv_bfloat16* qr = q + (size_t)b * ld_q + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(qr + c * 8);
+            const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            qv[c * 8 + 0] = a.x; qv[c * 8 + 1] = a.y; qv[c * 8 + 2] = b2.x; qv[c * 8 + 3] = b2.y;
+            qv[c * 8 + 4] = c2.x; qv[c * 8 + 5] = c2.y; qv[c * 8 + 6] = d.x; qv[c * 8 + 7] = d.y;
+        }
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < n_keys; j += 32) {
+        const bool ok = (key_mask == nullptr || key_mask[(size_t)b * mask_stride + j]) && j <= q_pos;
+        float s = -INFINITY;
+        if (ok) {
+            const __nv_bfloat16* kr = kvb + (size_t)j * ld_kv;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH / 8; ++c) {
+                const uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
+                const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+                acc += qv[c * 8] * a.x + qv[c * 8 + 1] * a.y + qv[c * 8 + 2] * b2.x + qv[c * 8 + 3] * b2.y + qv[c * 8 + 4] * c2.x +
+                       qv[c * 8 + 5] * c2.y + qv[c * 8 + 6] * d.x + qv[c * 8 + 7] * d.y;
+            }
+            s = acc * scale - slope * fabsf((float)(q_pos - j));
+        }
+        p[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    const float m_use = mx == -INFINITY ? 0.f : mx;
+    float sum = 0.f;
+    for (int j = lane; j < n_keys; j += 32) {
+        const float e = __expf(p[j] - m_use);
+        p[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < n_keys; ++j) {
+        const float pj = p[j];
+        if (pj == 0.f) continue;
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kvb + (size_t)j * ld_kv + DH + lane * 2));
+        o0 += pj * v.x;
+        o1 += pj * v.y;
+    }
+    *reinterpret_cast<uint32_t*>(out + (size_t)b * ld_out + h * DH + lane * 2) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+}  // namespace
+
+// q bf16 [B, >= H*64] (row stride ld_q); kv bf16 cache [B][n_keys rows of (k | v) = 128 columns] (row stride ld_kv, batch stride in
+// elements); key_mask [B, mask_stride] or NULL; out bf16 [B, H*64].  The query sits at position q_pos (keys j <= q_pos attend).
+extern "C" int spb_attention_decode(const void* q, int ld_q, const void* kv, int ld_kv, long long kv_batch_stride, const uint8_t* key_mask,
+                                    int mask_stride, const float* logslopes, void* out, int ld_out, int B, int H, int dim_head,
+                                    int n_keys, int q_pos, cudaStream_t stream) {
+    if (B <= 0 || n_keys <= 0) return SPB_OK;
+    SPB_CHECK_ARG(q && kv && logslopes && out, "spb_attention_decode: null pointer");
+    SPB_CHECK_ARG(dim_head == DH && H >= 1 && H <= 32, "spb_attention_decode: dim_head must be %d, 1..32 heads", DH);
+    SPB_CHECK_ARG(n_keys <= DEC_MAX_T, "spb_attention_decode: at most %d cached keys", DEC_MAX_T);
+    SPB_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 2 == 0, "spb_attention_decode: unaligned leading dims");
+    const size_t smem = (size_t)H * n_keys * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    attn_decode_kernel<<<B, 32 * H, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), ld_q, reinterpret_cast<const __nv_bfloat16*>(kv),
+                                                   ld_kv, kv_batch_stride, key_mask, mask_stride, logslopes,
+                                                   reinterpret_cast<__nv_bfloat16*>(out), ld_out, n_keys, q_pos, 1.f / sqrtf((float)dim_head));
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}

@@ -216,6 +216,18 @@ def attention_bwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, ou
     return dqkv
 
 
+def attention_decode(q: Tensor, kv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, H: int, n_keys: int, q_pos: int) -> Tensor:
+    """q bf16 [B, >=H*64]; kv bf16 [B, cap, 128] (k | v); returns bf16 [B, H*64]."""
+    _require_cuda(q, kv)
+    assert q.dtype == BF16 and kv.dtype == BF16 and q.stride(1) == 1 and kv.stride(2) == 1
+    B = q.shape[0]
+    out = torch.empty((B, H * 64), dtype=BF16, device=q.device)
+    _call("spb_attention_decode", _p(q), q.stride(0), _p(kv), kv.stride(1), kv.stride(0), _p(key_mask),
+          key_mask.stride(0) if key_mask is not None else 0, _p(logslopes), _p(out), out.stride(0), B, H, 64, n_keys, q_pos, _stream())
+    _count()
+    return out
+
+
 # ----------------------------------------------------------------------------- latent levels / MMD
 def latent_level_fwd(hidden: Tensor, style: Tensor, mask: Tensor, segments: Optional[Tensor], W: Tensor, bias: Tensor, col0: int,
                      S: int, z: int):

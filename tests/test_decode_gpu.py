@@ -1,0 +1,88 @@
+"""KV-cached rendering on the GPU: the batched renderer and the reference-contract cache path against the reference's tokens."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    g = parity.golden("render_t24.npz")
+    model = parity.build_model(dropout=False, device="cuda").eval()
+    batch = parity.make_batch(1, int(g["T"]), seed=int(g["seed"]), full_length=True, deadpan_last=False)
+    return g, model, batch
+
+
+def _encoders(model, batch):
+    dev = next(model.parameters()).device
+    b = {k: v.to(dev) for k, v in batch.items()}
+    with torch.inference_mode():
+        enc = model.forward_encoders(perf=b["perf"], perf_mask=b["perf_mask"], score=b["score"], score_mask=b["score_mask"], bars=b["bars"],
+                                     beats=b["beats"], onsets=b["onsets"], deadpan_mask=b["deadpan_mask"], compute_loss=False)
+    return b, enc
+
+
+def test_eval_encoders_match_reference(setup):
+    g, model, batch = setup
+    _, enc = _encoders(model, batch)
+    for name, got in (("score_embeddings", enc.score_embeddings), ("perf_embeddings", enc.perf_embeddings)):
+        want = torch.from_numpy(g[name])
+        err = float((got.float().cpu() - want).abs().max() / want.abs().max())
+        assert err < 5e-2, (name, err)
+
+
+def test_render_batch_teacher_forced_matches_reference_tokens(setup):
+    """Every step predicted from the reference's own prefix: tokens must equal the reference's greedy tokens, except
+    where the reference's top-2 logit gap is within bf16 noise."""
+    g, model, batch = setup
+    from scoreperformer_b200.decode import render_batch
+    b, enc = _encoders(model, batch)
+    ref_tokens = torch.from_numpy(g["tokens_out"]).cuda()
+    tokens_in = torch.from_numpy(g["tokens_in"]).cuda()
+    # use the reference's encoder outputs so that only the decoder path is compared
+    score = torch.from_numpy(g["score_embeddings"]).cuda()
+    style = torch.from_numpy(g["perf_embeddings"]).cuda()
+    pred = render_batch(model, tokens_in, b["masked_perf"], score, style, mask=b["perf_mask"], teacher=ref_tokens)
+    fields = [3, 5, 10, 11]
+    diff = (pred[:, 1:, fields] != ref_tokens[:, 1:, fields])
+    n_diff, n_all = int(diff.sum()), diff.numel()
+    assert n_diff <= max(2, n_all // 20), f"{n_diff} of {n_all} greedy tokens differ from the reference"
+    # untouched fields stay untouched
+    keep = [f for f in range(12) if f not in fields]
+    assert torch.equal(pred[..., keep], tokens_in[..., keep])
+
+
+def test_render_batch_free_running_is_batched_and_deterministic(setup):
+    g, model, batch = setup
+    from scoreperformer_b200.decode import render_batch
+    b, enc = _encoders(model, batch)
+    tokens_in = torch.from_numpy(g["tokens_in"]).cuda()
+    rep = lambda t: t.repeat(3, *([1] * (t.dim() - 1)))
+    out3 = render_batch(model, rep(tokens_in), rep(b["masked_perf"]), rep(enc.score_embeddings), rep(enc.perf_embeddings),
+                        mask=rep(b["perf_mask"]))
+    assert torch.equal(out3[0], out3[1]) and torch.equal(out3[0], out3[2])
+    assert int((out3 == 1).sum()) == int((tokens_in[:, 0] == 1).sum()) * 3          # every MASK after note 0 was filled
+    ref_tokens = torch.from_numpy(g["tokens_out"]).cuda()
+    agree = float((out3[0] == ref_tokens[0]).float().mean())
+    assert agree > 0.9, agree
+
+
+def test_unmask_tokens_cache_contract(setup):
+    """The reference-signature `unmask_tokens` (batch 1, caches returned) agrees with the batched renderer."""
+    g, model, batch = setup
+    from scoreperformer_b200.decode import render_batch
+    from scoreperformer_b200.modules.sampling import top_k
+    b, enc = _encoders(model, batch)
+    tokens_in = torch.from_numpy(g["tokens_in"]).cuda()
+    T = 10
+    out, caches = model.perf_decoder.unmask_tokens(tokens_in[:, :T], b["masked_perf"][:, :T], filter_logits_fn=top_k, filter_kwargs={"k": 1},
+                                                   return_caches=True, disable_tqdm=True, context=enc.score_embeddings[:, :T],
+                                                   style_embeddings=enc.perf_embeddings[:, :T])
+    assert caches.token_emb.shape[1] == T - 1 and len(caches.transformer.attention) == 4 and len(caches.transformer.hiddens) == 5
+    assert caches.transformer.attention[0].keys.shape == (1, T - 1, 64)
+    want = render_batch(model, tokens_in[:, :T], b["masked_perf"][:, :T], enc.score_embeddings[:, :T], enc.perf_embeddings[:, :T])
+    assert float((out == want).float().mean()) > 0.95
