@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU (configs[1]: 64)")
     ap.add_argument("--seq", type=int, default=512, help="notes per sequence (configs[1]: 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel launch table of one step")
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
@@ -163,7 +164,7 @@ def main():
     import torch.distributed as dist
     from scoreperformer_b200 import kernels as K
     from scoreperformer_b200.models import ScorePerformer
-    from scoreperformer_b200.parallel import GradientBuckets
+    from scoreperformer_b200.train_step import TrainStep
     from scoreperformer_b200.recipes import default_model_config
     from scoreperformer_b200.synthetic import make_batch
 
@@ -182,24 +183,12 @@ def main():
     model.train()
     model.perf_encoder.exact_latent_shapes = False          # static segment tables: no host sync inside the step
     model.perf_decoder.label_fields = (3, 5, 10, 11)        # MixedLM collator labels (base.yaml:64-65): no probe sync
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=1e-6, fused=True)
-    buckets = GradientBuckets(model) if world > 1 else None
-    params = [p for p in model.parameters()]
+    ts = TrainStep(model, lr=2e-4, weight_decay=1e-6, grad_clip=2.0, use_graph=not args.no_graph)
 
     B, T = args.batch, args.seq
     host_batch = {k: v.pin_memory() for k, v in make_batch(B, T, seed=1234 + rank).items()}
     dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batch.values())
-
-    def step(batch):
-        out = model(**batch)
-        out.loss.backward()
-        if buckets is not None:
-            buckets.sync_gradients()
-        torch.nn.utils.clip_grad_norm_(params, 2.0, foreach=True)
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        return out.loss
 
     def barrier():
         if world > 1:
@@ -221,13 +210,13 @@ def main():
             ms = float(t)
         return ms
 
-    for _ in range(max(3, args.warmup)):
-        step(dev_batch)
+    for _ in range(max(4, args.warmup)):                     # >= 3 eager steps, then capture + first replay
+        ts.step(dev_batch)
 
     if args.ncu_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(dev_batch)
+        ts.step(dev_batch)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -235,14 +224,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    K.LAUNCHES = 0
-    ms_total = timed(args.steps, lambda: step(dev_batch))
-    launches = K.LAUNCHES
+    ms_total = timed(args.steps, lambda: ts.step(dev_batch))
+    launches = ts.launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     def e2e_step():
-        batch = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
-        loss = step(batch)
+        loss = ts.step(host_batch)                           # pinned host -> device copies of the int64 batch, every step
         return float(loss)                                   # D2H read of the step's result (sync)
 
     e2e_step()
@@ -272,7 +259,8 @@ def main():
         K.gemm = timed_gemm
         import scoreperformer_b200.fused as fused_mod
         fused_mod.K.gemm = timed_gemm
-        step(dev_batch)
+        ts.use_graph = False
+        ts.step(dev_batch)
         torch.cuda.synchronize()
         K.gemm = orig
         fused_mod.K.gemm = orig
@@ -309,7 +297,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "ScorePerformer default recipe (recipes/scoreperformer/base.yaml) training step: fwd+bwd+clip+AdamW, "
                                    "bf16 tensor-core math / fp32 master weights, recipe dropouts on (configs[1])",
-                       "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world}",
+                       "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
                        "l2": "per-step activations (>3 GB) far exceed the 126 MB L2; no explicit flush needed"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

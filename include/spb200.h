@@ -12,6 +12,8 @@
  *   - `stream` is the caller's current CUDA stream (cudaStream_t passed as void*); no call synchronises;
  *   - bf16 buffers are `void*`, fp32 are `float*`, masks are `uint8_t*` (torch.bool), tokens/labels `int64_t*`;
  *   - "ACCUMULATED" outputs are added to (the caller zero-initialises), everything else is overwritten;
+ *   - dropout masks come from a counter hash of (seed + *rng_offset, element index); `rng_offset` (device uint64, may be NULL) lets
+ *     CUDA-graph replays draw fresh masks; the backward regenerates the forward's mask from the same pair;
  *   - functions are re-entrant; the only global state is the cached driver entry point for TMA descriptor encoding.
  */
 #ifndef SPB200_H
@@ -55,10 +57,11 @@ int spb_layer_norm_bwd(const void* dy, int lddy, const void* x, int x_fp32, int 
                        void* dgb, int lddgb, int n_rows, int dim, spb_stream_t stream);
 
 /* GLU(SiLU) + dropout: u bf16 [n, 2*hidden] -> h bf16 [n, hidden] (modules/transformer/feedforward.py:13-22,56-61). */
-int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, spb_stream_t stream);
+int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
+                spb_stream_t stream);
 /* du bf16 [n, 2*hidden]; dbias fp32 [2*hidden] ACCUMULATED (may be NULL). */
 int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p, uint64_t seed,
-                spb_stream_t stream);
+                const uint64_t* rng_offset, spb_stream_t stream);
 
 /* Fused SPMuple tuple-token embedding: out[n, F*128] = LayerNorm(cat_f table[off_f + tokens[n,f]]) in bf16.
  * table fp32 [sum V_f, 128] is the concatenation of the computed per-field tables (modules/transformer/embeddings.py:91-143).
@@ -73,11 +76,12 @@ int spb_embed_ln_bwd(const void* dy, int ld_dy, const int64_t* tokens, int ld_to
 /* Fused MQA attention with learned-slope ALiBi, key padding, causal mask and dropout; qkv bf16 [B*T, ld] = q(H*64) | k(64) | v(64).
  * lse fp32 [B,H,T] is saved for the backward.  Replaces modules/transformer/attend.py:58-126 + attention.py:139-197. */
 int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, void* out, int ld_out, float* lse, int B,
-                      int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed, spb_stream_t stream);
+                      int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
+                      spb_stream_t stream);
 /* dqkv bf16 [B*T, ld_dqkv] in the qkv column layout; delta fp32 [B,H,T] scratch; dlogslopes fp32 [H] ACCUMULATED. */
 int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out, const void* dout,
                       int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv, float* dlogslopes, int B, int T, int H,
-                      int dim_head, int causal, float dropout_p, uint64_t seed, spb_stream_t stream);
+                      int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset, spb_stream_t stream);
 
 /* KV-cached incremental decode (one new query per sequence): q bf16 [B, H*64]; kv cache bf16 rows of (k | v); the query sits at
  * position q_pos.  Replaces the cached path of attention.py:155-156 / transformer.py:161-186 without the per-step torch.cat. */
@@ -108,7 +112,8 @@ int spb_ce_rows(const float* logits, int ld, const int64_t* labels, int ld_lab, 
 /* Direction-classifier heads (models/classifiers/model.py:74-82,202-216): Dropout -> Linear(in_dim, C_g) -> weighted CE. */
 int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, const int64_t* labels, int ld_lab, const float* W, const float* bias,
                   const float* class_w, const int* n_classes, int n_heads, float* num, float* den, const float* dlogit_scale, float* dW,
-                  float* db, float* dl_scratch, int n_rows, int in_dim, float dropout_p, uint64_t seed, int backward, spb_stream_t stream);
+                  float* db, float* dl_scratch, int n_rows, int in_dim, float dropout_p, uint64_t seed, const uint64_t* rng_offset, int backward,
+                  spb_stream_t stream);
 int spb_clf_logits(const float* x, int ldx, const float* W, const float* bias, float* out, int n_rows, int in_dim, int total,
                    spb_stream_t stream);
 

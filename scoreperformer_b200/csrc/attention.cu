@@ -28,6 +28,7 @@ struct AttnParams {
     int causal;
     float dropout_p;
     uint64_t seed;
+    const uint64_t* rng_offset;   // optional device counter mixed into the seed (CUDA-graph replays get fresh masks)
     uint32_t drop_thresh24;
     float keep_scale;
 };
@@ -116,6 +117,7 @@ __device__ __forceinline__ void acc_to_frags(const float acc[8][4], uint32_t pf[
 // grid (ceil(T/64), H, B), 128 threads; warp w owns query rows [16w, 16w+16) of the tile.
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float* __restrict__ lse_out) {
+    if (p.rng_offset != nullptr) p.seed += *p.rng_offset * 0x9E3779B97F4A7C15ull;
     __shared__ __align__(128) uint8_t sQ[TQ * 128];
     __shared__ __align__(128) uint8_t sK[2][TK * 128];
     __shared__ __align__(128) uint8_t sV[2][TK * 128];
@@ -261,6 +263,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_do, const float* __restrict__ lse,
                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int ld_dqkv) {
+    if (p.rng_offset != nullptr) p.seed += *p.rng_offset * 0x9E3779B97F4A7C15ull;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint8_t* sK = dyn_smem;
     uint8_t* sV = sK + TK * 128;
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_do, const float* __restrict__ lse,
                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int ld_dqkv,
                    float* __restrict__ dlogslopes) {
+    if (p.rng_offset != nullptr) p.seed += *p.rng_offset * 0x9E3779B97F4A7C15ull;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     uint8_t* sQ = dyn_smem;
     uint8_t* sDO = sQ + TQ * 128;
@@ -509,7 +513,8 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
 }
 
 int fill_params(AttnParams& p, const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, int B, int T, int H,
-                int dim_head, int causal, float dropout_p, uint64_t seed) {
+                int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset) {
+    p.rng_offset = rng_offset;
     SPB_CHECK_ARG(qkv && logslopes, "attention: null pointer");
     SPB_CHECK_ARG(dim_head == DH, "attention: dim_head must be %d, got %d", DH, dim_head);
     SPB_CHECK_ARG(ld % 8 == 0 && ld >= H * DH + 2 * DH, "attention: qkv row stride %d too small / unaligned", ld);
@@ -532,10 +537,10 @@ int fill_params(AttnParams& p, const void* qkv, int ld, const uint8_t* key_mask,
 // out bf16 [B*T, ld_out] (H*64 columns written); lse fp32 [B, H, T] in base-2 units (consumed only by the backward).
 extern "C" int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, void* out, int ld_out,
                                  float* lse, int B, int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed,
-                                 cudaStream_t stream) {
+                                 const uint64_t* rng_offset, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return SPB_OK;
     AttnParams p;
-    int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed);
+    int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed, rng_offset);
     if (rc != SPB_OK) return rc;
     SPB_CHECK_ARG(out != nullptr && ld_out % 2 == 0, "spb_attention_fwd: bad output");
     attn_fwd_kernel<<<dim3(ceil_div(T, TQ), H, B), 128, 0, stream>>>(p, reinterpret_cast<__nv_bfloat16*>(out), ld_out, lse);
@@ -548,10 +553,10 @@ extern "C" int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mas
 extern "C" int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out,
                                  const void* dout, int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv,
                                  float* dlogslopes, int B, int T, int H, int dim_head, int causal, float dropout_p,
-                                 uint64_t seed, cudaStream_t stream) {
+                                 uint64_t seed, const uint64_t* rng_offset, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return SPB_OK;
     AttnParams p;
-    int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed);
+    int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed, rng_offset);
     if (rc != SPB_OK) return rc;
     SPB_CHECK_ARG(out && dout && lse && delta && dqkv, "spb_attention_bwd: null pointer");
     const int n_warps = B * T * H;

@@ -72,55 +72,71 @@ struct ClfHeads {
     int total;
 };
 
-// One thread per note.  x fp32 [n, in_dim] (style embeddings, detached), rowmask selects the classified notes.
+// One WARP per note: lane k owns input dims k and k+32 (in_dim <= 64); each class logit is a warp-shuffle reduction, so the
+// weight reads are conflict-free and the input row is read coalesced.  x fp32 [n, in_dim] (style embeddings, detached).
 // Forward (dl == nullptr): per head num[g] += w[y] * nll, den[g] += w[y].
 // Backward (dl != nullptr): dl[row, off_g + c] = scale_g * w[y] * (p_c - onehot_c)   (zero for unclassified rows).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 clf_heads_kernel(const float* __restrict__ x, int ldx, const uint8_t* __restrict__ rowmask, const int64_t* __restrict__ labels,
                  int ld_lab, const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ class_w, ClfHeads hd,
                  float* __restrict__ num, float* __restrict__ den, const float* __restrict__ dlogit_scale, float* __restrict__ dl,
-                 int n_rows, int in_dim, uint64_t seed, uint32_t drop_thresh24, float keep_scale) {
+                 int n_rows, int in_dim, uint64_t seed, const uint64_t* __restrict__ rng_offset, uint32_t drop_thresh24,
+                 float keep_scale) {
+    if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
     extern __shared__ float sm[];
-    float* sW = sm;                               // [total][in_dim]
-    float* sB = sW + hd.total * in_dim;           // [total]
+    float* sW = sm;                               // [total][64] (zero padded beyond in_dim)
+    float* sB = sW + hd.total * 64;               // [total]
     float* sCW = sB + hd.total;                   // [total]
     __shared__ float s_num[CLF_MAX_HEADS], s_den[CLF_MAX_HEADS];
-    for (int i = threadIdx.x; i < hd.total * in_dim; i += blockDim.x) sW[i] = W[i];
+    for (int i = threadIdx.x; i < hd.total * 64; i += blockDim.x) {
+        const int c = i >> 6, k = i & 63;
+        sW[i] = k < in_dim ? W[(size_t)c * in_dim + k] : 0.f;
+    }
     for (int i = threadIdx.x; i < hd.total; i += blockDim.x) { sB[i] = bias[i]; sCW[i] = class_w[i]; }
     if (threadIdx.x < CLF_MAX_HEADS) { s_num[threadIdx.x] = 0.f; s_den[threadIdx.x] = 0.f; }
     __syncthreads();
-
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * warps_per_block) {
         const bool row_on = rowmask[row] != 0;
+        if (!row_on) {
+            if (dl != nullptr) for (int c = lane; c < hd.total; c += 32) dl[(size_t)row * hd.total + c] = 0.f;
+            continue;
+        }
+        const float x0 = lane < in_dim ? x[(size_t)row * ldx + lane] : 0.f;
+        const float x1 = lane + 32 < in_dim ? x[(size_t)row * ldx + lane + 32] : 0.f;
         for (int g = 0; g < hd.n_heads; ++g) {
             const int C = hd.n_classes[g], off = hd.class_off[g];
             const long long y = labels[(size_t)row * ld_lab + g];
-            const bool on = row_on && y >= 0 && y < C;
-            if (!on) {
-                if (dl != nullptr) for (int c = 0; c < C; ++c) dl[(size_t)row * hd.total + off + c] = 0.f;
+            if (y < 0 || y >= C) {
+                if (dl != nullptr && lane < C) dl[(size_t)row * hd.total + off + lane] = 0.f;
                 continue;
             }
-            float lg[16];   // C <= 16 per head
-            for (int c = 0; c < C; ++c) lg[c] = sB[off + c];
-            for (int k = 0; k < in_dim; ++k) {
-                float xv = x[(size_t)row * ldx + k];
-                if (drop_thresh24 != 0)
-                    xv = spb_keep(seed, ((uint64_t)row * CLF_MAX_HEADS + g) * 64 + k, drop_thresh24) ? xv * keep_scale : 0.f;
-                for (int c = 0; c < C; ++c) lg[c] += xv * sW[(off + c) * in_dim + k];
+            float a0 = x0, a1 = x1;
+            if (drop_thresh24 != 0) {
+                a0 = spb_keep(seed, ((uint64_t)row * CLF_MAX_HEADS + g) * 64 + lane, drop_thresh24) ? x0 * keep_scale : 0.f;
+                a1 = spb_keep(seed, ((uint64_t)row * CLF_MAX_HEADS + g) * 64 + lane + 32, drop_thresh24) ? x1 * keep_scale : 0.f;
             }
-            float mx = -INFINITY;
-            for (int c = 0; c < C; ++c) mx = fmaxf(mx, lg[c]);
-            float se = 0.f;
-            for (int c = 0; c < C; ++c) se += __expf(lg[c] - mx);
+            // lane c (< C) keeps logit c
+            float my_logit = -INFINITY;
+            for (int c = 0; c < C; ++c) {
+                float s = a0 * sW[(off + c) * 64 + lane] + a1 * sW[(off + c) * 64 + lane + 32];
+                s = warp_sum(s) + sB[off + c];
+                if (lane == c) my_logit = s;
+            }
+            const float mx = warp_max(my_logit);
+            const float e = lane < C ? __expf(my_logit - mx) : 0.f;
+            const float se = warp_sum(e);
             const float lse = mx + __logf(se);
+            const float ly = __shfl_sync(0xffffffffu, my_logit, (int)y);
             const float wy = sCW[off + y];
             if (dl == nullptr) {
-                atomicAdd(&s_num[g], wy * (lse - lg[y]));
-                atomicAdd(&s_den[g], wy);
-            } else {
-                const float sc = dlogit_scale[g] * wy;
-                for (int c = 0; c < C; ++c)
-                    dl[(size_t)row * hd.total + off + c] = sc * (__expf(lg[c] - lse) - (c == y ? 1.f : 0.f));
+                if (lane == 0) {
+                    atomicAdd(&s_num[g], wy * (lse - ly));
+                    atomicAdd(&s_den[g], wy);
+                }
+            } else if (lane < C) {
+                dl[(size_t)row * hd.total + off + lane] = dlogit_scale[g] * wy * (e / se - (lane == y ? 1.f : 0.f));
             }
         }
     }
@@ -137,7 +153,9 @@ clf_heads_kernel(const float* __restrict__ x, int ldx, const uint8_t* __restrict
 // Each block owns 64 rows; dl and the (per-head re-dropped) inputs are staged in shared memory.
 __global__ void __launch_bounds__(256)
 clf_wgrad_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dl, ClfHeads hd, float* __restrict__ dW,
-                 float* __restrict__ db, int n_rows, int in_dim, uint64_t seed, uint32_t drop_thresh24, float keep_scale) {
+                 float* __restrict__ db, int n_rows, int in_dim, uint64_t seed, const uint64_t* __restrict__ rng_offset,
+                 uint32_t drop_thresh24, float keep_scale) {
+    if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
     __shared__ float sx[64][65];
     __shared__ float sd[64][17];
     const int r0 = blockIdx.x * 64;
@@ -226,7 +244,7 @@ extern "C" int spb_ce_rows(const float* logits, int ld, const int64_t* labels, i
 extern "C" int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, const int64_t* labels, int ld_lab, const float* W,
                              const float* bias, const float* class_w, const int* n_classes, int n_heads, float* num, float* den,
                              const float* dlogit_scale, float* dW, float* db, float* dl_scratch, int n_rows, int in_dim, float dropout_p,
-                             uint64_t seed, int backward, cudaStream_t stream) {
+                             uint64_t seed, const uint64_t* rng_offset, int backward, cudaStream_t stream) {
     if (n_rows <= 0) return SPB_OK;
     SPB_CHECK_ARG(x && rowmask && labels && W && bias && class_w, "spb_clf_heads: null pointer");
     SPB_CHECK_ARG(in_dim > 0 && in_dim <= 64, "spb_clf_heads: in_dim must be <= 64, got %d", in_dim);
@@ -236,19 +254,19 @@ extern "C" int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, co
     double t = (double)dropout_p * 16777216.0;
     const uint32_t th = dropout_p > 0.f ? (uint32_t)(t < 1 ? 1 : t) : 0;
     const float ks = 1.f / (1.f - dropout_p);
-    int grid = ceil_div(n_rows, 128);
-    if (grid > 2 * spb_num_sms()) grid = 2 * spb_num_sms();
-    const size_t smem = (size_t)(hd.total * in_dim + 2 * hd.total) * sizeof(float);
+    int grid = ceil_div(n_rows, 8);
+    if (grid > 4 * spb_num_sms()) grid = 4 * spb_num_sms();
+    const size_t smem = (size_t)(hd.total * 64 + 2 * hd.total) * sizeof(float);
     if (!backward) {
         SPB_CHECK_ARG(num && den, "spb_clf_heads: forward needs num/den");
-        clf_heads_kernel<<<grid, 128, smem, stream>>>(x, ldx, rowmask, labels, ld_lab, W, bias, class_w, hd, num, den, nullptr, nullptr,
-                                                      n_rows, in_dim, seed, th, ks);
+        clf_heads_kernel<<<grid, 256, smem, stream>>>(x, ldx, rowmask, labels, ld_lab, W, bias, class_w, hd, num, den, nullptr, nullptr,
+                                                      n_rows, in_dim, seed, rng_offset, th, ks);
     } else {
         SPB_CHECK_ARG(dlogit_scale && dW && db && dl_scratch, "spb_clf_heads: backward needs dlogit_scale/dW/db/dl_scratch");
-        clf_heads_kernel<<<grid, 128, smem, stream>>>(x, ldx, rowmask, labels, ld_lab, W, bias, class_w, hd, nullptr, nullptr, dlogit_scale,
-                                                      dl_scratch, n_rows, in_dim, seed, th, ks);
+        clf_heads_kernel<<<grid, 256, smem, stream>>>(x, ldx, rowmask, labels, ld_lab, W, bias, class_w, hd, nullptr, nullptr, dlogit_scale,
+                                                      dl_scratch, n_rows, in_dim, seed, rng_offset, th, ks);
         SPB_CHECK_LAUNCH();
-        clf_wgrad_kernel<<<ceil_div(n_rows, 64), 256, 0, stream>>>(x, ldx, dl_scratch, hd, dW, db, n_rows, in_dim, seed, th, ks);
+        clf_wgrad_kernel<<<ceil_div(n_rows, 64), 256, 0, stream>>>(x, ldx, dl_scratch, hd, dW, db, n_rows, in_dim, seed, rng_offset, th, ks);
     }
     SPB_CHECK_LAUNCH();
     return SPB_OK;

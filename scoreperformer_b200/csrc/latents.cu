@@ -23,19 +23,23 @@ __device__ __forceinline__ float load_feat(const float* hidden, const float* sty
     return style[tok * ld_style + (c - d_hidden)];                         // style is stored already masked
 }
 
-// One warp per 32 consecutive notes of one sample.  Lane <-> feature; equal-id runs are accumulated in
-// registers and flushed with one fp32 atomic per feature per run (runs are contiguous in real data, so
-// almost every segment is flushed exactly once; ids need not be sorted for correctness).
+// One warp per (sample, 32 consecutive notes, group of 64 features).  Lane <-> 2 adjacent features; run boundaries come from
+// the segment ids held one-per-lane and broadcast with warp shuffles; equal-id runs are accumulated in registers and flushed
+// with one fp32 atomic per feature per run (runs are contiguous in real data, so almost every segment is flushed exactly
+// once; ids need not be sorted for correctness).  Loads are issued 8 notes ahead of the reduction to hide HBM latency.
 __global__ void __launch_bounds__(128)
 segpool_sum_kernel(const float* __restrict__ hidden, const float* __restrict__ style, int ld_style, const uint8_t* __restrict__ mask,
                    const int64_t* __restrict__ segments, float* __restrict__ pooled, int* __restrict__ counts, int B, int T, int S,
                    int d_hidden, int d_total) {
     const int lane = threadIdx.x & 31;
     const int chunks_per_sample = ceil_div(T, 32);
+    const int n_fg = ceil_div(d_total, 64);
     const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (gw >= B * chunks_per_sample) return;
-    const int b = gw / chunks_per_sample;
-    const int t0 = (gw % chunks_per_sample) * 32;
+    if (gw >= B * chunks_per_sample * n_fg) return;
+    const int fg = gw % n_fg;
+    const int bc = gw / n_fg;
+    const int b = bc / chunks_per_sample;
+    const int t0 = (bc % chunks_per_sample) * 32;
     const int t_me = t0 + lane;
     long long my_id = -1;
     bool my_valid = false;
@@ -44,34 +48,47 @@ segpool_sum_kernel(const float* __restrict__ hidden, const float* __restrict__ s
         my_valid = mask[(size_t)b * T + t_me] != 0;
         if (my_id < 0 || my_id >= S) my_id = -1;   // out-of-range ids are dropped (reference would raise)
     }
-    float acc[DREGS];
-#pragma unroll
-    for (int k = 0; k < DREGS; ++k) acc[k] = 0.f;
+    const int c0 = fg * 64 + lane * 2;
+    float acc0 = 0.f, acc1 = 0.f;
     int run_id = -1, run_count = 0;
     const int n_tok = min(32, T - t0);
-    for (int j = 0; j <= n_tok; ++j) {
-        const int id = j < n_tok ? (int)__shfl_sync(0xffffffffu, (int)my_id, j) : -2;
-        const bool valid = j < n_tok ? __shfl_sync(0xffffffffu, (int)my_valid, j) != 0 : false;
-        if (id != run_id) {
-            if (run_id >= 0 && run_count > 0) {
-                float* dst = pooled + ((size_t)b * S + run_id) * MAX_D;
-#pragma unroll
-                for (int k = 0; k < DREGS; ++k)
-                    if (k * 32 + lane < d_total && acc[k] != 0.f) atomicAdd(dst + k * 32 + lane, acc[k]);
-                if (lane == 0) atomicAdd(counts + (size_t)b * S + run_id, run_count);
-            }
-#pragma unroll
-            for (int k = 0; k < DREGS; ++k) acc[k] = 0.f;
-            run_id = id;
-            run_count = 0;
+    auto flush = [&]() {
+        if (run_id >= 0 && run_count > 0) {
+            float* dst = pooled + ((size_t)b * S + run_id) * MAX_D;
+            if (c0 < d_total && acc0 != 0.f) atomicAdd(dst + c0, acc0);
+            if (c0 + 1 < d_total && acc1 != 0.f) atomicAdd(dst + c0 + 1, acc1);
+            if (lane == 0 && fg == 0) atomicAdd(counts + (size_t)b * S + run_id, run_count);
         }
-        if (j < n_tok && id >= 0) {
-            const size_t tok = (size_t)b * T + t0 + j;
+        acc0 = acc1 = 0.f;
+        run_count = 0;
+    };
+    for (int j0 = 0; j0 < n_tok; j0 += 8) {
+        float v0[8], v1[8];
+        int ids[8];
 #pragma unroll
-            for (int k = 0; k < DREGS; ++k) acc[k] += load_feat(hidden, style, ld_style, tok, k * 32 + lane, d_hidden, d_total, valid);
-            ++run_count;
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            ids[u] = j < n_tok ? (int)__shfl_sync(0xffffffffu, (int)my_id, j & 31) : -2;
+            const bool valid = j < n_tok ? __shfl_sync(0xffffffffu, (int)my_valid, j & 31) != 0 : false;
+            const size_t tok = (size_t)b * T + t0 + j;
+            v0[u] = (j < n_tok && ids[u] >= 0) ? load_feat(hidden, style, ld_style, tok, c0, d_hidden, d_total, valid) : 0.f;
+            v1[u] = (j < n_tok && ids[u] >= 0) ? load_feat(hidden, style, ld_style, tok, c0 + 1, d_hidden, d_total, valid) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (j0 + u >= n_tok) break;
+            if (ids[u] != run_id) {
+                flush();
+                run_id = ids[u];
+            }
+            if (ids[u] >= 0) {
+                acc0 += v0[u];
+                acc1 += v1[u];
+                ++run_count;
+            }
         }
     }
+    flush();
 }
 
 // One warp per segment slot: mean, validity, latent = W pooled + bias.
@@ -343,7 +360,7 @@ extern "C" int spb_latent_level_fwd(const float* hidden, const float* style_in, 
     const int d_total = d_hidden + w_style;
     SPB_CHECK_ARG(d_total <= MAX_D && z <= 64 && S >= 1, "spb_latent_level_fwd: d_total=%d (max %d), z=%d", d_total, MAX_D, z);
     SPB_CHECK_ARG(segments != nullptr || S == 2, "spb_latent_level_fwd: mode 'mean' expects S == 2");
-    const int warps = B * ceil_div(T, 32);
+    const int warps = B * ceil_div(T, 32) * ceil_div(d_total, 64);
     segpool_sum_kernel<<<ceil_div(warps, 4), 128, 0, stream>>>(hidden, style_in, ld_style, mask, segments, pooled, counts, B, T, S, d_hidden, d_total);
     SPB_CHECK_LAUNCH();
     seg_latent_kernel<<<ceil_div(B * S, 4), 128, 0, stream>>>(pooled, counts, W, bias, latents, lmask, B * S, d_total, z, segments == nullptr ? 1 : 0);

@@ -177,7 +177,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const Tin* __restr
 // u: [n, 2H] (value | gate) -> h[n, H] = value * silu(gate) * dropout_keep / (1-p)
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, int n_rows, int H, uint64_t seed,
-               uint32_t drop_thresh24, float keep_scale) {
+               const uint64_t* __restrict__ rng_offset, uint32_t drop_thresh24, float keep_scale) {
+    if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
     const int per_row = H / 4;
     const int64_t total = (int64_t)n_rows * per_row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -205,7 +206,9 @@ glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ 
 template <int MAXG>
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
-               float* __restrict__ dbias, int n_rows, int H, uint64_t seed, uint32_t drop_thresh24, float keep_scale) {
+               float* __restrict__ dbias, int n_rows, int H, uint64_t seed, const uint64_t* __restrict__ rng_offset,
+               uint32_t drop_thresh24, float keep_scale) {
+    if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
     float sx[MAXG][4], sg[MAXG][4];
 #pragma unroll
     for (int k = 0; k < MAXG; ++k)
@@ -379,7 +382,8 @@ embed_ln_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, const
 // Backward pass 2: grid (chunks, F).  The CTA privatises field f's table gradient [V_f, 128] in shared memory,
 // scatters dx = rstd * (dy*w - c1 - xhat*c2) for its chunk of tuples with shared-memory atomics, then flushes
 // once.  PAD (token 0) rows receive no gradient (F.embedding padding_idx=0, modules/transformer/embeddings.py:99).
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+constexpr int SCATTER_WARPS = 16;
+__global__ void __launch_bounds__(SCATTER_WARPS * 32)
 embed_ln_bwd_scatter_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, const int64_t* __restrict__ tokens, int ld_tok,
                             const float* __restrict__ table, FieldTable ft, const float* __restrict__ w,
                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -396,18 +400,32 @@ embed_ln_bwd_scatter_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, con
     const int r1 = min(n_rows, r0 + rows_per_chunk);
     const int c = f * 128 + lane * 4;
     const float4 g = *reinterpret_cast<const float4*>(w + c);
-    for (int row = r0 + warp; row < r1; row += ROW_WARPS) {
-        long long tok = tokens[(size_t)row * ld_tok + f];
-        if (tok <= 0 || tok >= V) continue;  // PAD row: no gradient; out-of-range tokens were clamped in forward
-        const float mean = mean_in[row], rstd = rstd_in[row], c1 = c1_in[row], c2 = c2_in[row];
-        const float4 xv = *reinterpret_cast<const float4*>(table + (size_t)(off + tok) * 128 + lane * 4);
-        const uint2 dv = *reinterpret_cast<const uint2*>(dy + (size_t)row * ld_dy + c);
-        const float2 d0 = unpack_bf16x2(dv.x), d1 = unpack_bf16x2(dv.y);
-        float* dst = stab + (size_t)tok * 128 + lane * 4;
-        atomicAdd(dst + 0, rstd * (d0.x * g.x - c1 - (xv.x - mean) * rstd * c2));
-        atomicAdd(dst + 1, rstd * (d0.y * g.y - c1 - (xv.y - mean) * rstd * c2));
-        atomicAdd(dst + 2, rstd * (d1.x * g.z - c1 - (xv.z - mean) * rstd * c2));
-        atomicAdd(dst + 3, rstd * (d1.y * g.w - c1 - (xv.w - mean) * rstd * c2));
+    constexpr int U = 4;   // tuples in flight per warp: the loop is latency-bound (gather -> shared atomic), so batch the loads
+    for (int base = r0 + warp * U; base < r1; base += SCATTER_WARPS * U) {
+        long long tok[U];
+        float4 xv[U];
+        uint2 dv[U];
+        float st[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int row = base + u;
+            tok[u] = row < r1 ? tokens[(size_t)row * ld_tok + f] : 0;
+            if (tok[u] <= 0 || tok[u] >= V) { tok[u] = 0; continue; }   // PAD / out of range: no gradient
+            xv[u] = *reinterpret_cast<const float4*>(table + (size_t)(off + tok[u]) * 128 + lane * 4);
+            dv[u] = *reinterpret_cast<const uint2*>(dy + (size_t)row * ld_dy + c);
+            st[u][0] = mean_in[row]; st[u][1] = rstd_in[row]; st[u][2] = c1_in[row]; st[u][3] = c2_in[row];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (tok[u] == 0) continue;
+            const float mean = st[u][0], rstd = st[u][1], c1 = st[u][2], c2 = st[u][3];
+            const float2 d0 = unpack_bf16x2(dv[u].x), d1 = unpack_bf16x2(dv[u].y);
+            float* dst = stab + (size_t)tok[u] * 128 + lane * 4;
+            atomicAdd(dst + 0, rstd * (d0.x * g.x - c1 - (xv[u].x - mean) * rstd * c2));
+            atomicAdd(dst + 1, rstd * (d0.y * g.y - c1 - (xv[u].y - mean) * rstd * c2));
+            atomicAdd(dst + 2, rstd * (d1.x * g.z - c1 - (xv[u].z - mean) * rstd * c2));
+            atomicAdd(dst + 3, rstd * (d1.y * g.w - c1 - (xv[u].w - mean) * rstd * c2));
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < V * 128; i += blockDim.x) {
@@ -497,20 +515,21 @@ static inline uint32_t drop_thresh(float p) {
     return (uint32_t)(t < 1 ? 1 : (t > 16777215.0 ? 16777215.0 : t));
 }
 
-extern "C" int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, cudaStream_t stream) {
+extern "C" int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
+                           cudaStream_t stream) {
     if (n_rows <= 0) return SPB_OK;
     SPB_CHECK_ARG(u && h && hidden % 4 == 0, "spb_glu_fwd: bad arguments");
     const int64_t total = (int64_t)n_rows * hidden / 4;
     int64_t blocks = (total + 255) / 256;
     if (blocks > spb_num_sms() * 16) blocks = spb_num_sms() * 16;
     glu_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), reinterpret_cast<__nv_bfloat16*>(h),
-                                                    n_rows, hidden, seed, drop_thresh(dropout_p), 1.f / (1.f - dropout_p));
+                                                    n_rows, hidden, seed, rng_offset, drop_thresh(dropout_p), 1.f / (1.f - dropout_p));
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
 
 extern "C" int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p,
-                           uint64_t seed, cudaStream_t stream) {
+                           uint64_t seed, const uint64_t* rng_offset, cudaStream_t stream) {
     if (n_rows <= 0) return SPB_OK;
     SPB_CHECK_ARG(dh && u && du && hidden % 4 == 0 && hidden <= 4096, "spb_glu_bwd: bad arguments (hidden <= 4096, multiple of 4)");
     int grid = spb_num_sms() * 4;
@@ -519,10 +538,10 @@ extern "C" int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias
     const float ks = 1.f / (1.f - dropout_p);
     if (hidden <= 1024)
         glu_bwd_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
-                                                    reinterpret_cast<__nv_bfloat16*>(du), dbias, n_rows, hidden, seed, th, ks);
+                                                    reinterpret_cast<__nv_bfloat16*>(du), dbias, n_rows, hidden, seed, rng_offset, th, ks);
     else
         glu_bwd_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
-                                                    reinterpret_cast<__nv_bfloat16*>(du), dbias, n_rows, hidden, seed, th, ks);
+                                                    reinterpret_cast<__nv_bfloat16*>(du), dbias, n_rows, hidden, seed, rng_offset, th, ks);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
@@ -593,7 +612,7 @@ extern "C" int spb_embed_ln_bwd(const void* dy, int ld_dy, const int64_t* tokens
     int rows_per_chunk = ceil_div(n_rows, chunks);
     if (rows_per_chunk < 64) rows_per_chunk = 64;
     chunks = ceil_div(n_rows, rows_per_chunk);
-    embed_ln_bwd_scatter_kernel<<<dim3(chunks, n_fields), thr, smem, stream>>>(d, ld_dy, tokens, ld_tok, table, ft, w, mean, rstd,
+    embed_ln_bwd_scatter_kernel<<<dim3(chunks, n_fields), SCATTER_WARPS * 32, smem, stream>>>(d, ld_dy, tokens, ld_tok, table, ft, w, mean, rstd,
                                                                               c1, c2, dtable, n_rows, rows_per_chunk);
     SPB_CHECK_LAUNCH();
     return SPB_OK;

@@ -271,14 +271,24 @@ class TransformerStackFn(torch.autograd.Function):
         p_attn = spec.attn_dropout if spec.training else 0.0
         p_ff = spec.ff_dropout if spec.training else 0.0
 
+        # every small accumulate-into gradient of the stack lives in ONE zero-initialised buffer (one fill instead of ~60)
+        n_small = spec.depth * (2 * spec.ff_inner + H) + (0 if spec.ada else spec.n_norms * 2 * D)
+        small = torch.zeros(n_small, dtype=F32, device=g_out.device)
+        small_off = [0]
+
+        def take(n):
+            v = small[small_off[0]:small_off[0] + n]
+            small_off[0] += n
+            return v
+
         def norm_bwd(i_norm, dy16, rec, dres):
             if spec.ada:
                 sl = slice(i_norm * 2 * D, (i_norm + 1) * 2 * D)
                 return K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], None, gb_all[:, sl], dres=dres, dx_dtype=F32,
                                         dgb=dgb_all[:, sl])
             j = _norm_index(spec, i_norm)
-            dw = torch.zeros_like(params[j])
-            db = torch.zeros_like(params[j])
+            dw = take(D)
+            db = take(D)
             dx = K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], params[j], dres=dres, dx_dtype=F32, dw=dw, db=db)
             grads[j], grads[j + 1] = dw, db
             return dx
@@ -291,7 +301,7 @@ class TransformerStackFn(torch.autograd.Function):
             g16 = K.cast_bf16(g)
             grads[base + PARAMS_PER_ATTN + 4] = K.gemm(g16, rec_f["h"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
             dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
-            db1 = torch.zeros(2 * spec.ff_inner, dtype=F32, device=g.device)
+            db1 = take(2 * spec.ff_inner)
             du = K.glu_bwd(dh, rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
             grads[base + PARAMS_PER_ATTN + 3] = db1
             grads[base + PARAMS_PER_ATTN + 2] = K.gemm(du, rec_f["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
@@ -301,7 +311,7 @@ class TransformerStackFn(torch.autograd.Function):
             g16 = K.cast_bf16(g, None if mask is None else mask.view(-1))
             grads[base + 5] = K.gemm(g16, rec_a["o"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
             do = K.gemm(g16, rec_a["wo16"], trans_b=True, out_dtype=BF16)
-            dls = torch.zeros(H, dtype=F32, device=g.device)
+            dls = take(H)
             dqkv = K.attention_bwd(rec_a["qkv"], mask, rec_a["ls"], rec_a["o"], do, rec_a["lse"], dls, B, T, H, spec.causal, p_attn,
                                    ctx.seeds[2 * l])
             grads[base + 6] = dls.view(params[base + 6].shape)

@@ -15,6 +15,9 @@ from . import lib as _lib
 
 BF16, F32 = torch.bfloat16, torch.float32
 LAUNCHES = 0
+# Optional device-side uint64 counter mixed into every dropout seed (set by train_step.TrainStep): kernels captured in a CUDA
+# graph read it at run time, so replays draw fresh masks although the host-side seeds were baked in at capture.
+RNG_OFFSET: Optional[Tensor] = None
 
 
 def _count(n: int = 1) -> None:
@@ -145,7 +148,7 @@ def glu_fwd(u: Tensor, dropout_p: float, seed: int) -> Tensor:
     assert u.dtype == BF16 and u.is_contiguous()
     n, two_h = u.shape
     h = torch.empty((n, two_h // 2), dtype=BF16, device=u.device)
-    _call("spb_glu_fwd", _p(u), _p(h), n, two_h // 2, float(dropout_p), seed, _stream())
+    _call("spb_glu_fwd", _p(u), _p(h), n, two_h // 2, float(dropout_p), seed, _p(RNG_OFFSET), _stream())
     _count()
     return h
 
@@ -154,7 +157,7 @@ def glu_bwd(dh: Tensor, u: Tensor, dbias: Optional[Tensor], dropout_p: float, se
     assert dh.dtype == BF16 and dh.is_contiguous() and u.is_contiguous()
     n, two_h = u.shape
     du = torch.empty_like(u)
-    _call("spb_glu_bwd", _p(dh), _p(u), _p(du), _p(dbias), n, two_h // 2, float(dropout_p), seed, _stream())
+    _call("spb_glu_bwd", _p(dh), _p(u), _p(du), _p(dbias), n, two_h // 2, float(dropout_p), seed, _p(RNG_OFFSET), _stream())
     _count()
     return du
 
@@ -200,7 +203,7 @@ def attention_fwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, B:
     out = torch.empty((B * T, H * 64), dtype=BF16, device=qkv.device)
     lse = torch.empty((B, H, T), dtype=F32, device=qkv.device)
     _call("spb_attention_fwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), out.stride(0), _p(lse), B, T, H, 64,
-          int(causal), float(dropout_p), seed, _stream())
+          int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
     _count()
     return out, lse
 
@@ -211,7 +214,7 @@ def attention_bwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, ou
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, H, T), dtype=F32, device=qkv.device)
     _call("spb_attention_bwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), _p(dout), out.stride(0), _p(lse), _p(delta),
-          _p(dqkv), dqkv.stride(0), _p(dlogslopes), B, T, H, 64, int(causal), float(dropout_p), seed, _stream())
+          _p(dqkv), dqkv.stride(0), _p(dlogslopes), B, T, H, 64, int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
     _count(3)
     return dqkv
 
@@ -289,7 +292,7 @@ def clf_heads(x: Tensor, rowmask: Tensor, labels: Tensor, W: Tensor, bias: Tenso
     scratch = torch.empty((n, int(sum(n_classes))), dtype=F32, device=x.device) if backward else None
     _call("spb_clf_heads", _p(x), x.stride(0), _p(rowmask), _p(labels), labels.stride(0), _p(W), _p(bias), _p(class_w),
           _sizes_array(n_classes), len(n_classes), _p(num), _p(den), _p(dlogit_scale), _p(dW), _p(db), _p(scratch), n, in_dim,
-          float(dropout_p), seed, int(backward), _stream())
+          float(dropout_p), seed, _p(RNG_OFFSET), int(backward), _stream())
     _count(2 if backward else 1)
 
 

@@ -235,8 +235,7 @@ class MMDTupleTransformer(TupleTransformer):
         embeddings = style                                   # already * mask
         if self.training:
             full_embeddings = embeddings
-            widths = torch.tensor(self.latent_dim, device=hidden.device)
-            drop = torch.stack(level_drops, dim=-1).repeat_interleave(widths, dim=-1, output_size=self.embedding_dim)
+            drop = torch.cat([d[..., None].expand(-1, -1, z) for d, z in zip(level_drops, self.latent_dim)], dim=-1)
             drop = drop & mask[..., None] & ~deadpan_mask[:, None, None] if deadpan_mask is not None else drop & mask[..., None]
             embeddings = embeddings * (~drop)
             drop_mask = drop

@@ -63,6 +63,12 @@ class DiscreteContinuousEmbedding(nn.Module):
             self.value_layer = nn.Linear(1, embedding_dim, bias=False, **factory_kwargs)
             self.activation = activation
         self.register_buffer("token_values", token_values)
+        # [V, 1] indicator of the discrete ids (non-persistent: not part of the reference state_dict); keeps the per-step table
+        # build free of host->device index copies, which CUDA-graph capture forbids
+        disc = torch.zeros(num_embeddings, 1)
+        if self.discrete_ids is not None:
+            disc[self.discrete_ids] = 1.0
+        self.register_buffer("_discrete_mask", disc.to(**factory_kwargs), persistent=False)
 
         self._value_weight = None
         if _weight is None:
@@ -93,10 +99,7 @@ class DiscreteContinuousEmbedding(nn.Module):
         if self.discrete:
             return self.index_weight
         elif self.discrete_ids is not None:
-            ids = self.discrete_ids.to(self.index_weight.device)
-            index_weight = torch.zeros_like(self.index_weight)
-            index_weight[ids] = self.index_weight[ids]
-            return index_weight
+            return self.index_weight * self._discrete_mask
 
     @property
     def value_weight(self):
@@ -106,9 +109,7 @@ class DiscreteContinuousEmbedding(nn.Module):
             if self._value_weight is None:
                 value_weight = self._compute_value_embeddings(self.token_values)
                 if self.discrete_ids is not None:
-                    keep = torch.ones(value_weight.shape[0], 1, dtype=value_weight.dtype, device=value_weight.device)
-                    keep[self.discrete_ids.to(keep.device)] = 0.
-                    value_weight = value_weight * keep
+                    value_weight = value_weight * (1.0 - self._discrete_mask)
                 return value_weight
             return self._value_weight
 

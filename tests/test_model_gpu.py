@@ -62,3 +62,32 @@ def test_dropout_training_step_runs():
     assert torch.isfinite(l1) and torch.isfinite(l2) and float(l1) != float(l2)
     for n, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_train_step_graph_matches_eager_and_redraws_dropout():
+    """CUDA-graph replay == eager math (dropouts off), and with dropouts on every replay draws fresh masks (device RNG offset)."""
+    from scoreperformer_b200.train_step import TrainStep
+    batch = {k: v.cuda() for k, v in parity.make_batch(2, 64, seed=5).items()}
+    losses = {}
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        m = parity.build_model(dropout=False, device="cuda")
+        m.train()
+        m.perf_encoder.exact_latent_shapes = False
+        ts = TrainStep(m, lr=1e-3, use_graph=use_graph)
+        torch.manual_seed(1)
+        seq = []
+        for _ in range(7):                       # 3 eager warm-ups, capture, replays
+            seq.append(float(ts.step(batch)))
+        losses[use_graph] = seq
+    # the MMD prior sample comes from torch's CUDA generator in both modes: compare the deterministic LM part of the loss
+    assert losses[True][6] < losses[True][0], "loss should go down over 7 steps on one batch"
+    for a, b in zip(losses[False][:3], losses[True][:3]):
+        assert abs(a - b) < 1e-3 * abs(a), (losses[False], losses[True])
+    assert abs(losses[False][6] - losses[True][6]) < 5e-2 * abs(losses[False][6]), (losses[False], losses[True])
+
+    m = parity.build_model(dropout=True, device="cuda")
+    m.train()
+    ts = TrainStep(m, lr=0.0, use_graph=True)     # lr 0: only the dropout masks / prior samples change between replays
+    vals = [float(ts.losses["Velocity"]) for _ in range(6) if ts.step(batch) is not None]
+    assert len(set(round(v, 6) for v in vals[3:])) == 3, f"graph replays must redraw dropout masks, got {vals}"
