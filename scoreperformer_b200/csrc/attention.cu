@@ -49,6 +49,31 @@ __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Dropout: one 32-bit counter hash per PAIR of adjacent key columns (j, j^1) of a (batch, head, query) row gives two 16-bit
+// uniform numbers; forward and both backward kernels evaluate the same function, so no mask is stored.
+struct DropCtx {
+    uint32_t seed32, thr16, half_t;
+    float keep_scale;
+    bool on;
+};
+__device__ __forceinline__ DropCtx make_drop(const AttnParams& p) {
+    DropCtx d;
+    d.seed32 = (uint32_t)(p.seed ^ (p.seed >> 32));
+    d.thr16 = p.drop_thresh24 >> 8;
+    d.half_t = (uint32_t)((p.T + 1) >> 1);
+    d.keep_scale = p.keep_scale;
+    d.on = p.drop_thresh24 != 0;
+    return d;
+}
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// row_lin = (b*H + h)*T + i
+__device__ __forceinline__ uint32_t pair_hash(const DropCtx& d, uint32_t row_lin, uint32_t j) {
+    return hash32((row_lin * d.half_t + (j >> 1)) * 0x9E3779B9u + d.seed32);
+}
+
 // A 64x64 bf16 tile: row r at r*128 B, 16-byte chunk c stored at chunk (c ^ (r & 7)).
 __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
     return base + row * 128 + ((chunk ^ (row & 7)) << 4);
@@ -121,12 +146,13 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
     __shared__ __align__(128) uint8_t sQ[TQ * 128];
     __shared__ __align__(128) uint8_t sK[2][TK * 128];
     __shared__ __align__(128) uint8_t sV[2][TK * 128];
-    __shared__ uint8_t sMask[2][TK];
+    __shared__ uint32_t sMaskBits[2][2];
 
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T;
     const int q0 = qt * TQ;
+    const DropCtx drop = make_drop(p);
     const int kcol = p.H * DH, vcol = kcol + DH;
     const __nv_bfloat16* base = p.qkv + (size_t)b * T * p.ld;
     const float slope = __expf(p.logslopes[h]) * LOG2E;
@@ -137,9 +163,11 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
     auto load_kv = [&](int kt, int buf) {
         load_tile_async(sK[buf], base, p.ld, kt * TK, kcol, T);
         load_tile_async(sV[buf], base, p.ld, kt * TK, vcol, T);
-        if (threadIdx.x < TK) {
+        if (threadIdx.x < TK) {      // warps 0,1: 64-bit validity mask of the key tile
             const int j = kt * TK + threadIdx.x;
-            sMask[buf][threadIdx.x] = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+            const bool ok = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+            const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) sMaskBits[buf][warp] = bits;
         }
     };
 
@@ -171,16 +199,23 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
             for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
         mma_a_tile_nt(s, qf, smem_u32(sK[buf]), lane);
 
+        // scores in base-2 units: s*scale2 - slope*|i-j|; the mask / causal tests only run on tiles that need them
+        const uint32_t mlo = sMaskBits[buf][0] >> ((lane & 3) * 2), mhi = sMaskBits[buf][1] >> ((lane & 3) * 2);
+        const bool diag = p.causal && (kt == qt);
+        const bool simple = !diag && sMaskBits[buf][0] == 0xffffffffu && sMaskBits[buf][1] == 0xffffffffu;
+        const float dbase0 = (float)(r_lo - (kt * TK + (lane & 3) * 2));     // i - j for e = 0, nt = 0
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int jl = nt * 8 + (lane & 3) * 2 + (e & 1);
-                const int j = kt * TK + jl;
-                const int i = r_lo + (e >> 1) * 8;
-                const bool ok = sMask[buf][jl] && (!p.causal || j <= i);
-                const float v = ok ? s[nt][e] * scale2 - slope * fabsf((float)(i - j)) : -INFINITY;
+                const float d = dbase0 + (float)((e >> 1) * 8 - nt * 8 - (e & 1));
+                float v = fmaf(-slope, fabsf(d), s[nt][e] * scale2);
+                if (!simple) {
+                    const uint32_t word = nt < 4 ? mlo : mhi;
+                    const bool ok = ((word >> ((nt & 3) * 8 + (e & 1))) & 1u) && (!diag || d >= 0.f);
+                    v = ok ? v : -INFINITY;
+                }
                 s[nt][e] = v;
                 mx[e >> 1] = fmaxf(mx[e >> 1], v);
             }
@@ -200,15 +235,21 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float pv = exp2f(s[nt][e] - m_use[e >> 1]);
+                const float pv = exp2f(s[nt][e] - m_use[e >> 1]);
                 rs[e >> 1] += pv;
-                if (p.drop_thresh24 != 0) {
-                    const int j = kt * TK + nt * 8 + (lane & 3) * 2 + (e & 1);
-                    const int i = r_lo + (e >> 1) * 8;
-                    const uint64_t idx = (((uint64_t)(b * p.H + h) * T + i) * T) + j;
-                    pv = spb_keep(p.seed, idx, p.drop_thresh24) ? pv * p.keep_scale : 0.f;
-                }
                 s[nt][e] = pv;
+            }
+        }
+        if (drop.on) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint32_t row_lin = (uint32_t)((b * p.H + h) * T + r_lo + rr * 8);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const uint32_t hsh = pair_hash(drop, row_lin, (uint32_t)(kt * TK + nt * 8 + (lane & 3) * 2));
+                    s[nt][rr * 2] = (hsh & 0xffffu) >= drop.thr16 ? s[nt][rr * 2] * drop.keep_scale : 0.f;
+                    s[nt][rr * 2 + 1] = (hsh >> 16) >= drop.thr16 ? s[nt][rr * 2 + 1] * drop.keep_scale : 0.f;
+                }
             }
         }
 #pragma unroll
@@ -269,12 +310,14 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
     uint8_t* sV = sK + TK * 128;
     uint8_t (*sQ)[TQ * 128] = reinterpret_cast<uint8_t (*)[TQ * 128]>(sV + TK * 128);
     uint8_t (*sDO)[TQ * 128] = reinterpret_cast<uint8_t (*)[TQ * 128]>(sV + TK * 128 + 2 * TQ * 128);
-    __shared__ float sLse[2][TQ], sDelta[2][TQ];
+    __shared__ __align__(16) float sLse[2][TQ];
+    __shared__ __align__(16) float sDelta[2][TQ];
 
     const int kt = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, H = p.H;
     const int k0 = kt * TK;
+    const DropCtx drop = make_drop(p);
     const int kcol = H * DH, vcol = kcol + DH;
     const __nv_bfloat16* base = p.qkv + (size_t)b * T * p.ld;
     const __nv_bfloat16* dbase = dout + (size_t)b * T * ld_do;
@@ -343,23 +386,29 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
         mma_a_tile_nt(dpt, vf, smem_u32(sDO[buf]), lane);
 
         uint32_t pf[4][4];
+        const bool diag = p.causal && (qt == kt);
+        const float dbase0 = (float)(qt * TQ + (lane & 3) * 2 - j_lo);       // i - j for e = 0, nt = 0
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             float pd[4];
+            const float2 lse2 = *reinterpret_cast<const float2*>(&sLse[buf][nt * 8 + (lane & 3) * 2]);
+            const float2 del2 = *reinterpret_cast<const float2*>(&sDelta[buf][nt * 8 + (lane & 3) * 2]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int il = nt * 8 + (lane & 3) * 2 + (e & 1);
-                const int i = qt * TQ + il;
-                const int j = j_lo + (e >> 1) * 8;
-                const bool ok = key_ok[e >> 1] && (!p.causal || j <= i);
-                float pv = ok ? exp2f(st[nt][e] * scale2 - slope * fabsf((float)(i - j)) - sLse[buf][il]) : 0.f;
+                const float d = dbase0 + (float)(nt * 8 + (e & 1) - (e >> 1) * 8);
+                const bool ok = key_ok[e >> 1] && (!diag || d >= 0.f);
+                const float lse_i = (e & 1) ? lse2.y : lse2.x;
+                float pv = ok ? exp2f(fmaf(-slope, fabsf(d), st[nt][e] * scale2) - lse_i) : 0.f;
                 float keep = 1.f;
-                if (p.drop_thresh24 != 0) {
-                    const uint64_t idx = (((uint64_t)(b * H + h) * T + i) * T) + j;
-                    keep = spb_keep(p.seed, idx, p.drop_thresh24) ? p.keep_scale : 0.f;
+                if (drop.on) {
+                    const int i = qt * TQ + nt * 8 + (lane & 3) * 2 + (e & 1);
+                    const int j = j_lo + (e >> 1) * 8;
+                    const uint32_t hsh = pair_hash(drop, (uint32_t)((b * H + h) * T + i), (uint32_t)j);
+                    const uint32_t u16 = (j & 1) ? (hsh >> 16) : (hsh & 0xffffu);
+                    keep = u16 >= drop.thr16 ? drop.keep_scale : 0.f;
                 }
-                pd[e] = pv * keep;                                               // dropped P^T (for dV)
-                st[nt][e] = pv * (dpt[nt][e] * keep - sDelta[buf][il]);          // dS^T
+                pd[e] = pv * keep;                                                        // dropped P^T (for dV)
+                st[nt][e] = pv * (dpt[nt][e] * keep - ((e & 1) ? del2.y : del2.x));       // dS^T
             }
             // pack P^T_drop into A fragments as we go (two n-tiles form one k-step)
             const int ks = nt >> 1;
@@ -397,11 +446,12 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
     uint8_t* sDO = sQ + TQ * 128;
     uint8_t (*sK)[TK * 128] = reinterpret_cast<uint8_t (*)[TK * 128]>(sDO + TQ * 128);
     uint8_t (*sV)[TK * 128] = reinterpret_cast<uint8_t (*)[TK * 128]>(sDO + TQ * 128 + 2 * TK * 128);
-    __shared__ uint8_t sMask[2][TK];
+    __shared__ uint32_t sMaskBits[2][2];
 
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, H = p.H;
+    const DropCtx drop = make_drop(p);
     const int q0 = qt * TQ;
     const int kcol = H * DH, vcol = kcol + DH;
     const __nv_bfloat16* base = p.qkv + (size_t)b * T * p.ld;
@@ -416,7 +466,9 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
         load_tile_async(sV[buf], base, p.ld, kt * TK, vcol, T);
         if (threadIdx.x < TK) {
             const int j = kt * TK + threadIdx.x;
-            sMask[buf][threadIdx.x] = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+            const bool ok = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+            const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) sMaskBits[buf][warp] = bits;
         }
     };
     load_tile_async(sQ, base, p.ld, q0, h * DH, T);
@@ -459,20 +511,32 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
             for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
         mma_a_tile_nt(s, qf, smem_u32(sK[buf]), lane);     // S = Q K^T
         mma_a_tile_nt(dp, dof, smem_u32(sV[buf]), lane);   // dP = dO V^T
+        const uint32_t mlo = sMaskBits[buf][0] >> ((lane & 3) * 2), mhi = sMaskBits[buf][1] >> ((lane & 3) * 2);
+        const bool diag = p.causal && (kt == qt);
+        const bool simple = !diag && sMaskBits[buf][0] == 0xffffffffu && sMaskBits[buf][1] == 0xffffffffu;
+        const float dbase0 = (float)(r_lo - (kt * TK + (lane & 3) * 2));
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
+            uint32_t hsh[2] = {0, 0};
+            if (drop.on) {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                    hsh[rr] = pair_hash(drop, (uint32_t)((b * H + h) * T + r_lo + rr * 8), (uint32_t)(kt * TK + nt * 8 + (lane & 3) * 2));
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int jl = nt * 8 + (lane & 3) * 2 + (e & 1);
-                const int j = kt * TK + jl;
-                const int i = r_lo + (e >> 1) * 8;
-                const bool ok = sMask[buf][jl] && (!p.causal || j <= i);
-                const float dist = fabsf((float)(i - j));
-                const float pv = ok ? exp2f(s[nt][e] * scale2 - slope * dist - lse_r[e >> 1]) : 0.f;
+                const float d = dbase0 + (float)((e >> 1) * 8 - nt * 8 - (e & 1));
+                const float dist = fabsf(d);
+                float pv = exp2f(fmaf(-slope, dist, s[nt][e] * scale2) - lse_r[e >> 1]);
+                if (!simple) {
+                    const uint32_t word = nt < 4 ? mlo : mhi;
+                    const bool ok = ((word >> ((nt & 3) * 8 + (e & 1))) & 1u) && (!diag || d >= 0.f);
+                    pv = ok ? pv : 0.f;
+                }
                 float keep = 1.f;
-                if (p.drop_thresh24 != 0) {
-                    const uint64_t idx = (((uint64_t)(b * H + h) * T + i) * T) + j;
-                    keep = spb_keep(p.seed, idx, p.drop_thresh24) ? p.keep_scale : 0.f;
+                if (drop.on) {
+                    const uint32_t u16 = (e & 1) ? (hsh[e >> 1] >> 16) : (hsh[e >> 1] & 0xffffu);
+                    keep = u16 >= drop.thr16 ? drop.keep_scale : 0.f;
                 }
                 const float ds = pv * (dp[nt][e] * keep - delta_r[e >> 1]);
                 ds_dist[e >> 1] += ds * dist;
