@@ -14,19 +14,23 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;       // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                                  // two warps per TMEM lane quarter, one 64-column chunk each
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int EPI_SST = 68;                                   // padded row stride (floats) of the epilogue staging tile
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_SST * 4;       // one 32 x 64 fp32 chunk per epilogue warp
 
 struct GemmParams {
     int M, N, K;
-    int kb_per_split;      // k-blocks handled by one blockIdx.z
+    int kb_per_split;      // k-blocks handled by one split
+    int splits;
     void* C;
     int ldc;
     int c_fp32;            // 1: fp32 output, 0: bf16
@@ -39,30 +43,38 @@ struct GemmParams {
 };
 
 template <int BN>
+__host__ __device__ constexpr int gemm_stages() { return BN == 256 ? 3 : (BN == 128 ? 4 : 6); }
+template <int BN>
 constexpr int gemm_smem_bytes() {
-    return STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 /*align slack*/ + 128 /*barriers*/;
+    return gemm_stages<BN>() * (A_STAGE_BYTES + BN * BK * 2) + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
+// Persistent, warp-specialised GEMM: one CTA per SM walks the tile list (n fastest, so co-running CTAs share the A panel in
+// L2).  The TMA producer and the MMA issuer run ahead across tile boundaries; the accumulator is double-buffered in TMEM
+// (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
     constexpr int B_STAGE_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int STAGES = gemm_stages<BN>();
+    constexpr int TMEM_COLS = 2 * BN;            // double-buffered accumulator (BN = 256 uses all 512 columns)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    float* epi_smem = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * BM;
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_m = (p.M + BM - 1) / BM;
+    const int tiles_mn = tiles_m * tiles_n;
+    const int total_tiles = tiles_mn * p.splits;
     const int total_kb = (p.K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-    const int num_kb = kb1 - kb0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -71,10 +83,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], EPI_WARPS);   // one arrive per epilogue warp
+        }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -84,24 +99,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&empty_bar[s], phase ^ 1);
-                uint8_t* sA = smem + s * STAGE_BYTES;
-                uint8_t* sB = sA + A_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                if (A_MN) {
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int split = t / tiles_mn, rem = t % tiles_mn;
+                const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * BN;
+                const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[s], phase ^ 1);
+                    uint8_t* sA = smem + s * STAGE_BYTES;
+                    uint8_t* sB = sA + A_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (A_MN) {
 #pragma unroll
-                    for (int h = 0; h < BM / 64; ++h) tma_load_2d(sA + h * (BK * 128), &tmA, &full_bar[s], m0 + h * 64, kb * BK);
-                } else {
-                    tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
-                }
-                if (B_MN) {
+                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(sA + h * (BK * 128), &tmA, &full_bar[s], m0 + h * 64, kb * BK);
+                    } else {
+                        tma_load_2d(sA, &tmA, &full_bar[s], kb * BK, m0);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(sB + h * (BK * 128), &tmB, &full_bar[s], n0 + h * 64, kb * BK);
-                } else {
-                    tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                        for (int h = 0; h < BN / 64; ++h) tma_load_2d(sB + h * (BK * 128), &tmB, &full_bar[s], n0 + h * 64, kb * BK);
+                    } else {
+                        tma_load_2d(sB, &tmB, &full_bar[s], kb * BK, n0);
+                    }
+                    if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
-                if (++s == STAGES) { s = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -112,114 +132,142 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
             constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;   // bytes per UMMA_K step
             constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
-            int s = 0;
-            uint32_t phase = 0;
-            for (int i = 0; i < num_kb; ++i) {
-                mbar_wait(&full_bar[s], phase);
+            int s = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int split = t / tiles_mn;
+                const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int i = 0; i < kb1 - kb0; ++i) {
+                    mbar_wait(&full_bar[s], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t da = umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
-                    const uint64_t db = umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = umma_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+                        const uint64_t db = umma_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+                        umma_bf16(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[s]);
-                if (++s == STAGES) { s = 0; phase ^= 1; }
+                umma_commit(&acc_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            umma_commit(accum_bar);
         }
     } else {
-        // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+        // ---------------- epilogue: warps 2..9; warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a lane
+        // quarter split the tile's 64-column chunks between them
         const int q = warp & 3;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        const int chunk_first = (warp - 2) >> 2;                 // 0 or 1
+        constexpr int CHUNK_STEP = EPI_WARPS / 4;                // 2
         // Each warp drains its 32 accumulator rows 64 columns at a time: TMEM -> registers -> padded smem (row stride 68
         // floats keeps float4 accesses conflict-free) -> 4 rows x 8 lanes x 8 columns per pass, so every global access
         // is a 16/32-byte vector and a warp instruction covers four full 128/256-byte row segments.
-        constexpr int SST = 68;
-        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * SST);
-        const int row_base = m0 + q * 32;
+        constexpr int SST = EPI_SST;
+        float* stage = epi_smem + (warp - 2) * (32 * SST);
         float* Cf = reinterpret_cast<float*>(p.C);
         __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
         const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 1.f;
         const int sub_row = lane >> 3;          // 0..3
         const int sub_col = (lane & 7) * 8;     // 0..56
         const bool vec_ok = (p.ldc % 8 == 0) && (p.residual == nullptr || p.ldr % 4 == 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int rem = t % tiles_mn;
+            const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * BN;
+            const int row_base = m0 + q * 32;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            bool released = false;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-            const int col0 = n0 + c * 64;
-            if (col0 >= p.N) break;
-            {
-                uint32_t v[32];
+            for (int c = chunk_first; c < BN / 64 || !released; c += CHUNK_STEP) {
+                const int col0 = n0 + c * 64;
+                const bool live = c < BN / 64 && col0 < p.N;
+                if (live) {
+                    uint32_t v[32];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + half * 32), v);
-                    tmem_ld_wait();
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(c * 64 + half * 32), v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(stage + lane * SST + half * 32 + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(stage + lane * SST + half * 32 + j) =
+                                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }
                 }
-            }
-            __syncwarp();
-            const int col = col0 + sub_col;
-            float bias[8];
+                if (!released && (c + CHUNK_STEP >= BN / 64 || n0 + (c + CHUNK_STEP) * 64 >= p.N)) {
+                    // every accumulator value this warp needs is out of TMEM: hand the buffer back to the MMA warp
+                    released = true;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                }
+                if (!live) break;
+                __syncwarp();
+                const int col = col0 + sub_col;
+                float bias[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bias[j] = (p.bias != nullptr && col + j < p.N) ? __ldg(p.bias + col + j) : 0.f;
-            const bool full = vec_ok && (col + 8 <= p.N);
+                for (int j = 0; j < 8; ++j) bias[j] = (p.bias != nullptr && col + j < p.N) ? __ldg(p.bias + col + j) : 0.f;
+                const bool full = vec_ok && (col + 8 <= p.N);
 #pragma unroll 2
-            for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + sub_row;
-                const int row = row_base + r;
-                if (row >= p.M || col >= p.N) continue;
-                const float4 a0 = *reinterpret_cast<const float4*>(stage + r * SST + sub_col);
-                const float4 a1 = *reinterpret_cast<const float4*>(stage + r * SST + sub_col + 4);
-                float val[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const bool keep = p.rowmask == nullptr || p.rowmask[row] != 0;
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + sub_row;
+                    const int row = row_base + r;
+                    if (row >= p.M || col >= p.N) continue;
+                    const float4 a0 = *reinterpret_cast<const float4*>(stage + r * SST + sub_col);
+                    const float4 a1 = *reinterpret_cast<const float4*>(stage + r * SST + sub_col + 4);
+                    float val[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const bool keep = p.rowmask == nullptr || p.rowmask[row] != 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) val[j] = keep ? val[j] * alpha + bias[j] : 0.f;
-                const size_t off = (size_t)row * p.ldc + col;
-                if (full) {
-                    if (p.residual != nullptr) {
-                        const float4 r0 = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col);
-                        const float4 r1 = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col + 4);
-                        val[0] += r0.x; val[1] += r0.y; val[2] += r0.z; val[3] += r0.w;
-                        val[4] += r1.x; val[5] += r1.y; val[6] += r1.z; val[7] += r1.w;
-                    }
-                    if (p.atomic) {   // split-K / accumulate: two 16-byte vector reductions per lane
-                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(Cf + off), "f"(val[0]), "f"(val[1]), "f"(val[2]), "f"(val[3]) : "memory");
-                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(Cf + off + 4), "f"(val[4]), "f"(val[5]), "f"(val[6]), "f"(val[7]) : "memory");
-                    } else if (p.c_fp32) {
-                        *reinterpret_cast<float4*>(Cf + off) = make_float4(val[0], val[1], val[2], val[3]);
-                        *reinterpret_cast<float4*>(Cf + off + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                    for (int j = 0; j < 8; ++j) val[j] = keep ? val[j] * alpha + bias[j] : 0.f;
+                    const size_t off = (size_t)row * p.ldc + col;
+                    if (full) {
+                        if (p.residual != nullptr) {
+                            const float4 r0 = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col);
+                            const float4 r1 = *reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col + 4);
+                            val[0] += r0.x; val[1] += r0.y; val[2] += r0.z; val[3] += r0.w;
+                            val[4] += r1.x; val[5] += r1.y; val[6] += r1.z; val[7] += r1.w;
+                        }
+                        if (p.atomic) {   // split-K / accumulate: two 16-byte vector reductions per lane
+                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(Cf + off), "f"(val[0]), "f"(val[1]), "f"(val[2]), "f"(val[3]) : "memory");
+                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(Cf + off + 4), "f"(val[4]), "f"(val[5]), "f"(val[6]), "f"(val[7]) : "memory");
+                        } else if (p.c_fp32) {
+                            *reinterpret_cast<float4*>(Cf + off) = make_float4(val[0], val[1], val[2], val[3]);
+                            *reinterpret_cast<float4*>(Cf + off + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                        } else {
+                            uint4 o;
+                            o.x = pack_bf16x2(val[0], val[1]); o.y = pack_bf16x2(val[2], val[3]);
+                            o.z = pack_bf16x2(val[4], val[5]); o.w = pack_bf16x2(val[6], val[7]);
+                            *reinterpret_cast<uint4*>(Cb + off) = o;
+                        }
                     } else {
-                        uint4 o;
-                        o.x = pack_bf16x2(val[0], val[1]); o.y = pack_bf16x2(val[2], val[3]);
-                        o.z = pack_bf16x2(val[4], val[5]); o.w = pack_bf16x2(val[6], val[7]);
-                        *reinterpret_cast<uint4*>(Cb + off) = o;
-                    }
-                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (col + j < p.N) {
-                            float vj = val[j];
-                            if (p.residual != nullptr) vj += p.residual[(size_t)row * p.ldr + col + j];
-                            if (p.atomic) atomicAdd(Cf + off + j, vj);
-                            else if (p.c_fp32) Cf[off + j] = vj;
-                            else Cb[off + j] = __float2bfloat16_rn(vj);
+                        for (int j = 0; j < 8; ++j) {
+                            if (col + j < p.N) {
+                                float vj = val[j];
+                                if (p.residual != nullptr) vj += p.residual[(size_t)row * p.ldr + col + j];
+                                if (p.atomic) atomicAdd(Cf + off + j, vj);
+                                else if (p.c_fp32) Cf[off + j] = vj;
+                                else Cb[off + j] = __float2bfloat16_rn(vj);
+                            }
                         }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<BN>(tmem_base);
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -246,7 +294,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
         SPB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN>()));
         configured = true;
     }
-    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), splits);
+    const int total_tiles = ceil_div(p.N, BN) * ceil_div(p.M, BM) * splits;
+    const int grid = total_tiles < spb_num_sms() ? total_tiles : spb_num_sms();
     kern<<<grid, GEMM_THREADS, gemm_smem_bytes<BN>(), stream>>>(tmA, tmB, p);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -290,7 +339,11 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
                   ldb);
     SPB_CHECK_ARG(!(accumulate || split_k > 1) || c_fp32, "spb_gemm_bf16: split-K / accumulate need an fp32 C");
 
-    const int BN = (N <= 64) ? 64 : 128;
+    int BN = (N <= 64) ? 64 : 128;
+    // wide tiles cut the L2->SM operand traffic (the binding resource for these skinny-K GEMMs) once K is deep enough to
+    // amortise the 3-stage ring; SPB_GEMM_BN overrides for experiments
+    if (N % 256 == 0 && K >= 512 && M >= 8 * BM) BN = 256;
+    if (const char* e = getenv("SPB_GEMM_BN")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) BN = v; }
     const int total_kb = ceil_div(K, BK);
     int splits = 1;
     if (split_k > 1) splits = split_k;
@@ -315,6 +368,7 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.kb_per_split = kb_per_split;
+    p.splits = splits;
     p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
     p.atomic = (splits > 1 || accumulate) ? 1 : 0;
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.rowmask = rowmask; p.alpha = alpha;
@@ -330,6 +384,7 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
     if (trans_b) return launch_gemm<BN_, false, true>(tmA, tmB, p, splits, stream);               \
     return launch_gemm<BN_, false, false>(tmA, tmB, p, splits, stream);
     if (BN == 64) { SPB_DISPATCH(64) }
+    if (BN == 256) { SPB_DISPATCH(256) }
     SPB_DISPATCH(128)
 #undef SPB_DISPATCH
 }
