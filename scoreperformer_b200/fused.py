@@ -17,6 +17,74 @@ from . import kernels as K
 
 BF16, F32 = torch.bfloat16, torch.float32
 
+# ----------------------------------------------------------------------------- step-level plumbing (set by train_step.TrainStep)
+# DIRECT_GRAD: weight-gradient kernels accumulate straight into `param.grad` (a view of the flat gradient buffer) and the
+#   autograd node returns None for that input -- no temporary, no AccumulateGrad add kernel.
+# SHADOW_ACTIVE: parameters carry `_spb_shadow`, a bf16 view of the flat weight shadow that ONE cast kernel refreshed at the
+#   start of this step.  Both flags are only True inside TrainStep's forward/backward, so stale shadows are never read.
+DIRECT_GRAD = False
+SHADOW_ACTIVE = False
+
+
+def _shadow(param: Tensor) -> Optional[Tensor]:
+    return getattr(param, "_spb_shadow", None) if SHADOW_ACTIVE else None
+
+
+def w16(param: Tensor) -> Tensor:
+    """bf16 copy of a weight: the per-step shadow when active, else a fresh cast."""
+    t = _shadow(param)
+    return t if t is not None else K.cast_bf16(param.detach().contiguous())
+
+
+def w16_cat(params: Sequence[Tensor]) -> Tensor:
+    """bf16 copy of the row-concatenation of weights; free when their shadows are adjacent in the flat buffer."""
+    shadows = [_shadow(p) for p in params]
+    if all(t is not None for t in shadows):
+        ok = all(shadows[i].data_ptr() + shadows[i].numel() * 2 == shadows[i + 1].data_ptr() for i in range(len(shadows) - 1))
+        if ok:
+            rows = sum(t.shape[0] for t in shadows)
+            return torch.as_strided(shadows[0], (rows, shadows[0].shape[1]), (shadows[0].shape[1], 1))
+        return torch.cat(shadows, dim=0)
+    return K.cast_bf16(torch.cat([p.detach() for p in params], dim=0))
+
+
+def direct_grad(param: Tensor) -> Optional[Tensor]:
+    if not DIRECT_GRAD:
+        return None
+    g = param.grad
+    if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != param.shape:
+        return None
+    return g
+
+
+def direct_grad_cat(params: Sequence[Tensor]) -> Optional[Tensor]:
+    """One [sum rows, cols] view over adjacent gradient slots (to_q | to_k | to_v), or None."""
+    gs = [direct_grad(p) for p in params]
+    if any(g is None for g in gs):
+        return None
+    if not all(gs[i].data_ptr() + gs[i].numel() * 4 == gs[i + 1].data_ptr() for i in range(len(gs) - 1)):
+        return None
+    rows = sum(g.shape[0] for g in gs)
+    return torch.as_strided(gs[0], (rows, gs[0].shape[1]), (gs[0].shape[1], 1))
+
+
+def wgrad(param: Tensor, a: Tensor, b: Tensor, alpha: Optional[Tensor] = None) -> Optional[Tensor]:
+    """dW[M, N] = a^T b for a stored [K, M], b stored [K, N]: accumulated into param.grad (returns None) or returned."""
+    g = direct_grad(param)
+    if g is not None:
+        K.gemm(a, b, trans_a=True, trans_b=True, out=g, split_k=0, accumulate=True, alpha=alpha)
+        return None
+    return K.gemm(a, b, trans_a=True, trans_b=True, out_dtype=F32, split_k=0, alpha=alpha)
+
+
+def vgrad(param: Tensor) -> Tuple[Tensor, bool]:
+    """Accumulate-into buffer for a vector gradient: (param.grad.view(-1), True) in direct mode, else (zeros, False)."""
+    g = direct_grad(param)
+    if g is not None:
+        return g.view(-1), True
+    return torch.zeros(param.numel(), dtype=F32, device=param.device), False
+
+
 
 # ----------------------------------------------------------------------------- generic Linear
 class LinearFn(torch.autograd.Function):
@@ -28,29 +96,28 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, out_fp32: bool, w_is_kn: bool):
         x16 = K.cast_bf16(x.contiguous()) if x.dtype == F32 else x
-        w16 = K.cast_bf16(weight.contiguous())
-        y = K.gemm(x16, w16, trans_b=w_is_kn, bias=bias, out_dtype=F32 if out_fp32 else BF16)
-        ctx.saved = (x16, w16)
+        w_16 = w16(weight)
+        y = K.gemm(x16, w_16, trans_b=w_is_kn, bias=bias, out_dtype=F32 if out_fp32 else BF16)
+        ctx.saved = (x16, w_16, weight, bias)
         ctx.meta = (x.dtype, w_is_kn, bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x16, w16 = ctx.saved
+        x16, w_16, weight, bias = ctx.saved
         x_dtype, w_is_kn, has_bias = ctx.meta
         dy = dy.contiguous()
         dy16 = K.cast_bf16(dy) if dy.dtype == F32 else dy
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dx[n, in] = dy[n, out] @ W[out, in]   (B operand must be [in, out]-indexed: MN-major unless stored [in, out])
-            dx = K.gemm(dy16, w16, trans_b=not w_is_kn, out_dtype=x_dtype)
+            dx = K.gemm(dy16, w_16, trans_b=not w_is_kn, out_dtype=x_dtype)
         if ctx.needs_input_grad[1]:
-            if w_is_kn:   # dW[in, out] = x^T dy
-                dw = K.gemm(x16, dy16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
-            else:         # dW[out, in] = dy^T x
-                dw = K.gemm(dy16, x16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            dw = wgrad(weight, x16, dy16) if w_is_kn else wgrad(weight, dy16, x16)     # [in,out] = x^T dy  |  [out,in] = dy^T x
         if has_bias and ctx.needs_input_grad[2]:
-            db = K.colsum(dy16)
+            buf, direct = vgrad(bias)
+            K.colsum(dy16, out=buf)
+            db = None if direct else buf
         return dx, dw, db, None, None
 
 
@@ -68,20 +135,20 @@ class LayerNormFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, out_fp32: bool, eps: float):
         x = x.contiguous()
         y, mean, rstd = K.layer_norm_fwd(x, weight, bias, out_dtype=F32 if out_fp32 else BF16, eps=eps)
-        ctx.saved = (x, mean, rstd, weight)
+        ctx.saved = (x, mean, rstd, weight, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, rstd, weight = ctx.saved
+        x, mean, rstd, weight, bias = ctx.saved
         dy = dy.contiguous()
         dy16 = K.cast_bf16(dy) if dy.dtype == F32 else dy
-        dw = torch.zeros_like(weight)
-        db = torch.zeros_like(weight)
+        dw, d1 = vgrad(weight)
+        db, d2 = vgrad(bias)
         dx = K.layer_norm_bwd(dy16, x, mean, rstd, weight, dx_dtype=BF16, dw=dw, db=db)
         if x.dtype == F32:
             dx = dx.float()
-        return dx, dw, db, None, None
+        return dx, None if d1 else dw, None if d2 else db, None, None
 
 
 def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, out_fp32: bool = False, eps: float = 1e-5) -> Tensor:
@@ -96,25 +163,26 @@ class TupleEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tokens, table, ln_w, ln_b, proj_w, proj_b, sizes: Tuple[int, ...]):
         x16, mean, rstd = K.embed_ln_fwd(tokens, table.contiguous(), sizes, ln_w, ln_b)
-        w16 = K.cast_bf16(proj_w.contiguous())
-        y = K.gemm(x16, w16, bias=proj_b, out_dtype=BF16)
-        ctx.saved = (tokens, table, ln_w, mean, rstd, x16, w16)
+        w_16 = w16(proj_w)
+        y = K.gemm(x16, w_16, bias=proj_b, out_dtype=BF16)
+        ctx.saved = (tokens, table, ln_w, ln_b, proj_w, proj_b, mean, rstd, x16, w_16)
         ctx.sizes = sizes
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        tokens, table, ln_w, mean, rstd, x16, w16 = ctx.saved
+        tokens, table, ln_w, ln_b, proj_w, proj_b, mean, rstd, x16, w_16 = ctx.saved
         dy16 = dy if dy.stride(-1) == 1 else dy.contiguous()
         assert dy16.dtype == BF16
-        dproj_w = K.gemm(dy16, x16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
-        dproj_b = K.colsum(dy16)
-        dx16 = K.gemm(dy16, w16, trans_b=True, out_dtype=BF16)
+        dproj_w = wgrad(proj_w, dy16, x16)
+        dpb, d0 = vgrad(proj_b)
+        K.colsum(dy16, out=dpb)
+        dx16 = K.gemm(dy16, w_16, trans_b=True, out_dtype=BF16)
         dtable = torch.zeros_like(table)
-        dln_w = torch.zeros_like(ln_w)
-        dln_b = torch.zeros_like(ln_w)
+        dln_w, d1 = vgrad(ln_w)
+        dln_b, d2 = vgrad(ln_b)
         K.embed_ln_bwd(dx16, tokens, table, ctx.sizes, ln_w, mean, rstd, dtable, dln_w, dln_b)
-        return None, dtable, dln_w, dln_b, dproj_w, dproj_b, None
+        return None, dtable, None if d1 else dln_w, None if d2 else dln_b, dproj_w, None if d0 else dpb, None
 
 
 # ----------------------------------------------------------------------------- stand-alone attention core / GLU
@@ -201,7 +269,7 @@ class TransformerStackFn(torch.autograd.Function):
             norm_w = [params[_norm_index(spec, i)] for i in range(spec.n_norms)]
             norm_b = [params[_norm_index(spec, i) + 1] for i in range(spec.n_norms)]
             style16 = K.cast_bf16(style.contiguous().view(N, -1))
-            w_ada16 = K.cast_bf16(torch.cat(norm_w, dim=0))
+            w_ada16 = w16_cat(norm_w)
             gb_all = K.gemm(style16, w_ada16, bias=torch.cat(norm_b, dim=0), out_dtype=BF16)   # [N, n_norms * 2D]
 
         def norm_fwd(i_norm, xin, out_dtype=BF16):
@@ -226,11 +294,11 @@ class TransformerStackFn(torch.autograd.Function):
                 hiddens[l].copy_(cur)
             to_q, to_k, to_v, to_out, logslopes = params[base + 2:base + 7]
             xn, mean, rstd = norm_fwd(2 * l, cur)
-            wqkv16 = K.cast_bf16(torch.cat([to_q, to_k, to_v], dim=0))
+            wqkv16 = w16_cat([to_q, to_k, to_v])
             qkv = K.gemm(xn, wqkv16, out_dtype=BF16)
             ls = logslopes.detach().reshape(-1).contiguous()
             o, lse = K.attention_fwd(qkv, mask, ls, B, T, H, spec.causal, p_attn, seeds[2 * l])
-            wo16 = K.cast_bf16(to_out.contiguous())
+            wo16 = w16(to_out)
             nxt = K.gemm(o, wo16, residual=cur, rowmask=None if mask is None else mask.view(-1), out_dtype=F32)
             if spec.return_hiddens:
                 kvs[l].copy_(qkv[:, H * dh:])
@@ -239,10 +307,10 @@ class TransformerStackFn(torch.autograd.Function):
             # ---- feed-forward sub-layer
             proj_w, proj_b, out_w = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
             xn, mean, rstd = norm_fwd(2 * l + 1, cur)
-            w1_16 = K.cast_bf16(proj_w.contiguous())
+            w1_16 = w16(proj_w)
             u = K.gemm(xn, w1_16, bias=proj_b, out_dtype=BF16)
             h = K.glu_fwd(u, p_ff, seeds[2 * l + 1])
-            w2_16 = K.cast_bf16(out_w.contiguous())
+            w2_16 = w16(out_w)
             nxt = K.gemm(h, w2_16, residual=cur, out_dtype=F32)
             rec_f = dict(x=cur, mean=mean, rstd=rstd, xn=xn, w1_16=w1_16, u=u, h=h, w2_16=w2_16) if keep else None
             cur = nxt
@@ -271,15 +339,22 @@ class TransformerStackFn(torch.autograd.Function):
         p_attn = spec.attn_dropout if spec.training else 0.0
         p_ff = spec.ff_dropout if spec.training else 0.0
 
-        # every small accumulate-into gradient of the stack lives in ONE zero-initialised buffer (one fill instead of ~60)
+        # small accumulate-into gradients: straight into param.grad in direct mode, else ONE zero-initialised buffer (one fill)
         n_small = spec.depth * (2 * spec.ff_inner + H) + (0 if spec.ada else spec.n_norms * 2 * D)
-        small = torch.zeros(n_small, dtype=F32, device=g_out.device)
+        small = None
         small_off = [0]
 
-        def take(n):
+        def take(param):
+            nonlocal small
+            g_direct = direct_grad(param)
+            if g_direct is not None:
+                return g_direct.view(-1), True
+            if small is None:
+                small = torch.zeros(n_small, dtype=F32, device=g_out.device)
+            n = param.numel()
             v = small[small_off[0]:small_off[0] + n]
             small_off[0] += n
-            return v
+            return v, False
 
         def norm_bwd(i_norm, dy16, rec, dres):
             if spec.ada:
@@ -287,10 +362,10 @@ class TransformerStackFn(torch.autograd.Function):
                 return K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], None, gb_all[:, sl], dres=dres, dx_dtype=F32,
                                         dgb=dgb_all[:, sl])
             j = _norm_index(spec, i_norm)
-            dw = take(D)
-            db = take(D)
+            dw, d1 = take(params[j])
+            db, d2 = take(params[j + 1])
             dx = K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], params[j], dres=dres, dx_dtype=F32, dw=dw, db=db)
-            grads[j], grads[j + 1] = dw, db
+            grads[j], grads[j + 1] = (None if d1 else dw), (None if d2 else db)
             return dx
 
         g = norm_bwd(2 * spec.depth, K.cast_bf16(g_out.contiguous().view(N, D)), ctx.final, None)
@@ -298,26 +373,32 @@ class TransformerStackFn(torch.autograd.Function):
             base = l * (PARAMS_PER_ATTN + PARAMS_PER_FF)
             rec_a, rec_f = ctx.layers[l]
             # ---- feed-forward backward:  x_out = x + W2 glu(W1 LN(x) + b1)
+            p_w1, p_b1, p_w2 = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
             g16 = K.cast_bf16(g)
-            grads[base + PARAMS_PER_ATTN + 4] = K.gemm(g16, rec_f["h"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            grads[base + PARAMS_PER_ATTN + 4] = wgrad(p_w2, g16, rec_f["h"])
             dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
-            db1 = take(2 * spec.ff_inner)
+            db1, d_b1 = take(p_b1)
             du = K.glu_bwd(dh, rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
-            grads[base + PARAMS_PER_ATTN + 3] = db1
-            grads[base + PARAMS_PER_ATTN + 2] = K.gemm(du, rec_f["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            grads[base + PARAMS_PER_ATTN + 3] = None if d_b1 else db1
+            grads[base + PARAMS_PER_ATTN + 2] = wgrad(p_w1, du, rec_f["xn"])
             dxn = K.gemm(du, rec_f["w1_16"], trans_b=True, out_dtype=BF16)
             g = norm_bwd(2 * l + 1, dxn, rec_f, g)
             # ---- attention backward:  x_out = x + mask * Wo attn(Wqkv LN(x))
+            p_q, p_k, p_v, p_o, p_ls = params[base + 2:base + 7]
             g16 = K.cast_bf16(g, None if mask is None else mask.view(-1))
-            grads[base + 5] = K.gemm(g16, rec_a["o"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+            grads[base + 5] = wgrad(p_o, g16, rec_a["o"])
             do = K.gemm(g16, rec_a["wo16"], trans_b=True, out_dtype=BF16)
-            dls = take(H)
+            dls, d_ls = take(p_ls)
             dqkv = K.attention_bwd(rec_a["qkv"], mask, rec_a["ls"], rec_a["o"], do, rec_a["lse"], dls, B, T, H, spec.causal, p_attn,
                                    ctx.seeds[2 * l])
-            grads[base + 6] = dls.view(params[base + 6].shape)
-            dwqkv = K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
-            hq = H * spec.dim_head
-            grads[base + 2], grads[base + 3], grads[base + 4] = dwqkv[:hq], dwqkv[hq:hq + spec.dim_head], dwqkv[hq + spec.dim_head:]
+            grads[base + 6] = None if d_ls else dls.view(p_ls.shape)
+            g_qkv = direct_grad_cat([p_q, p_k, p_v])
+            if g_qkv is not None:
+                K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out=g_qkv, split_k=0, accumulate=True)
+            else:
+                dwqkv = K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+                hq = H * spec.dim_head
+                grads[base + 2], grads[base + 3], grads[base + 4] = dwqkv[:hq], dwqkv[hq:hq + spec.dim_head], dwqkv[hq + spec.dim_head:]
             dxn = K.gemm(dqkv, rec_a["wqkv16"], trans_b=True, out_dtype=BF16)
             g = norm_bwd(2 * l, dxn, rec_a, g)
         d_style = None
@@ -364,6 +445,7 @@ class LatentLevelsFn(torch.autograd.Function):
             saved.append((seg, S, z, col, W, pooled, counts, lmask))
             col += z
         ctx.saved = saved
+        ctx.wb = wb
         ctx.mask = mask
         ctx.shape = (B, T, D)
         ctx.mark_non_differentiable(*[o for o in outs[1::2]])
@@ -381,10 +463,12 @@ class LatentLevelsFn(torch.autograd.Function):
             seg, S, z, col, W, pooled, counts, lmask = ctx.saved[lvl]
             d_lat = d_outs[2 * lvl]
             d_lat = None if d_lat is None else d_lat.contiguous()
-            dW = torch.zeros_like(W)
-            db = torch.zeros(z, dtype=F32, device=W.device)
+            p_w, p_b = ctx.wb[2 * lvl], ctx.wb[2 * lvl + 1]
+            g_w = direct_grad(p_w)
+            dW = g_w if g_w is not None else torch.zeros_like(W)
+            db, d_b = vgrad(p_b)
             K.latent_level_bwd(d_style, col, d_lat, ctx.mask, seg, W, pooled, counts, lmask, d_hidden, dW, db, S, z)
-            grads_wb[2 * lvl], grads_wb[2 * lvl + 1] = dW, db
+            grads_wb[2 * lvl], grads_wb[2 * lvl + 1] = (None if g_w is not None else dW), (None if d_b else db)
         return (d_hidden, None, None, None, None) + tuple(grads_wb)
 
 
@@ -418,7 +502,7 @@ class TiedHeadCEFn(torch.autograd.Function):
         n = hidden.shape[0]
         dev = hidden.device
         h16 = K.cast_bf16(hidden.contiguous()) if hidden.dtype == F32 else hidden.contiguous()
-        wp16 = K.cast_bf16(proj_w.contiguous())                    # [dim, F*emb]
+        wp16 = w16(proj_w)                                          # [dim, F*emb]
         e_raw = K.gemm(h16, wp16, trans_b=True, out_dtype=BF16)     # [n, F*emb]
         e, mean, rstd = K.layer_norm_fwd(e_raw, ln_w, ln_b, out_dtype=BF16)
         table16 = K.cast_bf16(table.contiguous())
@@ -441,6 +525,7 @@ class TiedHeadCEFn(torch.autograd.Function):
         n_active = active.sum().clamp(min=1)
         loss = (per_field * active).sum() / n_active
         ctx.saved = (h16, wp16, e_raw, e, mean, rstd, ln_w, table16, dlogits, count, active, n_active)
+        ctx.params = (proj_w, ln_w, ln_b)
         ctx.meta = (sizes, fields, emb, offs, hidden.dtype)
         ctx.mark_non_differentiable(per_field, count)
         return loss, per_field, count
@@ -459,11 +544,14 @@ class TiedHeadCEFn(torch.autograd.Function):
             K.gemm(a, table16[offs[f]:offs[f] + V], trans_b=True, out=de[:, f * emb:(f + 1) * emb], alpha=coef[f:f + 1])
             K.gemm(a, e[:, f * emb:(f + 1) * emb], trans_a=True, trans_b=True, out=dtable[offs[f]:offs[f] + V], split_k=0,
                    alpha=coef[f:f + 1])
-        dln_w, dln_b = torch.zeros_like(ln_w), torch.zeros_like(ln_w)
+        p_proj, p_lnw, p_lnb = ctx.params
+        dln_w, d1 = vgrad(p_lnw)
+        dln_b, d2 = vgrad(p_lnb)
         de_raw = K.layer_norm_bwd(de, e_raw, mean, rstd, ln_w, dx_dtype=BF16, dw=dln_w, db=dln_b)
-        dproj = K.gemm(h16, de_raw, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)     # [dim, F*emb]
-        dh = K.gemm(de_raw, wp16, out_dtype=h_dtype)                                           # [n, dim]
-        return dh, dproj, dln_w, dln_b, dtable, None, None, None, None, None
+        dproj = wgrad(p_proj, h16, de_raw) if p_proj.dim() == 2 and p_proj.is_contiguous() else \
+            K.gemm(h16, de_raw, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)             # [dim, F*emb]
+        dh = K.gemm(de_raw, wp16, out_dtype=h_dtype)                                               # [n, dim]
+        return dh, dproj, None if d1 else dln_w, None if d2 else dln_b, dtable, None, None, None, None, None
 
 
 def tied_head_logits(hidden: Tensor, proj_w: Tensor, ln_w: Tensor, ln_b: Tensor, table: Tensor, sizes: Sequence[int],

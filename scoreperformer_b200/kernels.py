@@ -50,13 +50,14 @@ def seed_from_torch() -> int:
 
 
 # ----------------------------------------------------------------------------- elementwise helpers
-def cast_bf16(x: Tensor, rowmask: Optional[Tensor] = None) -> Tensor:
+def cast_bf16(x: Tensor, rowmask: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """fp32 -> bf16 copy; rows (last dim) where rowmask is False are zeroed."""
     _require_cuda(x)
     if x.dtype == BF16 and rowmask is None:
         return x
     assert x.dtype == F32 and x.is_contiguous(), (x.dtype, x.is_contiguous())
-    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
     row_len = x.shape[-1] if rowmask is not None else 0
     _call("spb_cast_f32_bf16", _p(x), _p(out), x.numel(), _p(rowmask), row_len, _stream())
     _count()

@@ -4,7 +4,8 @@ Mirrors what `Trainer.run_epoch` + `Optimizer.step` do per batch (experiments/tr
 backward, `clip_grad_norm_(2.0)`, AdamW(lr 2e-4, wd 1e-6), `zero_grad`) with two B200-first changes:
 
 * gradients live in ONE flat fp32 buffer (every `p.grad` is a view), so data parallelism is a single NCCL all-reduce of
-  46 MB over NVLink per step, and clipping / zeroing are single kernels;
+  46 MB over NVLink per step, and clipping / zeroing are single kernels; weight-gradient kernels accumulate straight into
+  that buffer (fused.DIRECT_GRAD) and ONE cast kernel per step refreshes a flat bf16 shadow of all weights (fused.SHADOW_ACTIVE);
 * forward + backward (the whole kernel sequence, ~1 000 launches) is captured once in a CUDA graph and replayed, because
   at ~15 ms per step the Python dispatch of the eager path (~19 ms) would otherwise be the bottleneck.  Dropout stays
   random across replays through a device-side counter mixed into the kernels' seeds (kernels.RNG_OFFSET).
@@ -17,7 +18,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from . import kernels as K
+from . import fused, kernels as K
 
 
 class TrainStep:
@@ -32,12 +33,21 @@ class TrainStep:
         dev = self.params[0].device
         if not dev.type == "cuda":
             raise RuntimeError("TrainStep needs a CUDA model: scoreperformer_b200 has no CPU fallback")
-        n = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
+        # parameters, gradients and the bf16 weight shadow are three flat buffers with identical layouts (offsets rounded to
+        # 8 elements so every bf16 view is 16-byte aligned for TMA)
+        offsets, n = [], 0
         for p in self.params:
+            offsets.append(n)
+            n += (p.numel() + 7) // 8 * 8
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_shadow = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        for p, off in zip(self.params, offsets):
+            view = self.flat_param[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            p._spb_shadow = self.flat_shadow[off:off + p.numel()].view_as(p)
         self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=True, capturable=True)
         if use_graph and getattr(model, "perf_encoder", None) is not None:
             model.perf_encoder.exact_latent_shapes = False      # static segment tables: the step must not sync with the host
@@ -54,8 +64,13 @@ class TrainStep:
     def _forward_backward(self, batch: Dict[str, Tensor]):
         self.rng_offset.add_(1)
         self.flat_grad.zero_()
-        out = self.model(**batch)
-        out.loss.backward()
+        K.cast_bf16(self.flat_param, out=self.flat_shadow)       # ONE cast kernel refreshes every bf16 weight of the step
+        fused.DIRECT_GRAD = fused.SHADOW_ACTIVE = True
+        try:
+            out = self.model(**batch)
+            out.loss.backward()
+        finally:
+            fused.DIRECT_GRAD = fused.SHADOW_ACTIVE = False
         return out
 
     def _update(self):
