@@ -51,10 +51,12 @@ int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, in
  * Replaces nn.LayerNorm and modules/layers.py:31-47. */
 int spb_layer_norm_fwd(const void* x, int x_fp32, int ldx, const float* w, const float* b, const void* gb, int ldgb, void* y, int y_fp32,
                        int ldy, float* mean, float* rstd, int n_rows, int dim, float eps, spb_stream_t stream);
-/* dx (= LN backward, + dres if given); dw/db ACCUMULATED (affine) or dgb written (adaptive). */
+/* dx (= LN backward, + dres if given); dw/db ACCUMULATED (affine) or dgb written (adaptive); optional dx16 = bf16 copy of dx with
+ * rows where dx16_rowmask is false zeroed (the operand of the next backward GEMM). */
 int spb_layer_norm_bwd(const void* dy, int lddy, const void* x, int x_fp32, int ldx, const float* mean, const float* rstd, const float* w,
                        const void* gb, int ldgb, const float* dres, int lddres, void* dx, int dx_fp32, int lddx, float* dw, float* db,
-                       void* dgb, int lddgb, int n_rows, int dim, spb_stream_t stream);
+                       void* dgb, int lddgb, void* dx16, int lddx16, const uint8_t* dx16_rowmask, int n_rows, int dim,
+                       spb_stream_t stream);
 
 /* GLU(SiLU) + dropout: u bf16 [n, 2*hidden] -> h bf16 [n, hidden] (modules/transformer/feedforward.py:13-22,56-61). */
 int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
@@ -78,6 +80,11 @@ int spb_embed_ln_bwd(const void* dy, int ld_dy, const int64_t* tokens, int ld_to
 int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, void* out, int ld_out, float* lse, int B,
                       int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
                       spb_stream_t stream);
+/* tcgen05/TMEM/TMA implementation of the same forward (4 heads x dim 64): 32 positions x 4 heads form the 128-row MMA tile, the
+ * softmax runs one row per thread out of TMEM.  mask_bits_scratch: uint32 [B, ceil(T/32)] (used when key_mask != NULL). */
+int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_mask, uint32_t* mask_bits_scratch, const float* logslopes, void* out,
+                         int ld_out, float* lse, int B, int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed,
+                         const uint64_t* rng_offset, spb_stream_t stream);
 /* dqkv bf16 [B*T, ld_dqkv] in the qkv column layout; delta fp32 [B,H,T] scratch; dlogslopes fp32 [H] ACCUMULATED. */
 int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out, const void* dout,
                       int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv, float* dlogslopes, int B, int T, int H,

@@ -138,6 +138,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -206,3 +213,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn_m
 // 2-D bf16 tensor map with 128-byte swizzle. `inner` is the contiguous dimension.
 int spb_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                           uint32_t box_inner, uint32_t box_outer);
+// 3-D bf16 tensor map [d2][d1][d0] (d0 contiguous) with 128-byte swizzle and a {box0, box1, 1} box; out-of-range rows read as zero.
+int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                          uint64_t stride2_bytes, uint32_t box0, uint32_t box1);

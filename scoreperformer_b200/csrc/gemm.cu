@@ -329,6 +329,29 @@ int spb_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, ui
     return SPB_OK;
 }
 
+int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                          uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) {
+        spb_set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+        return SPB_ERR_DRIVER;
+    }
+    SPB_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride1_bytes & 15) == 0 && (stride2_bytes & 15) == 0,
+                  "TMA 3-D map: base / strides must be 16-byte aligned");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        spb_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+        return SPB_ERR_DRIVER;
+    }
+    return SPB_OK;
+}
+
 // C-ABI entry point; see include/spb200.h for the contract.
 extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
                              int ldb, int ldc, const float* bias, const float* residual, int ldr, const uint8_t* rowmask,

@@ -99,7 +99,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const Tin* __restr
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ w,
               const __nv_bfloat16* __restrict__ gb, int ldgb, const float* __restrict__ dres, int lddres,
               Tdx* __restrict__ dx, int lddx, float* __restrict__ dw, float* __restrict__ db,
-              __nv_bfloat16* __restrict__ dgb, int lddgb, int n_rows) {
+              __nv_bfloat16* __restrict__ dgb, int lddgb, __nv_bfloat16* __restrict__ dx16, int lddx16,
+              const uint8_t* __restrict__ dx16_rowmask, int n_rows) {
     constexpr int D = 256 * G;
     __shared__ float red[ROW_WARPS][256];
     const int lane = threadIdx.x & 31;
@@ -153,6 +154,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const Tin* __restr
                 for (int j = 0; j < 8; ++j) o[j] += r[j];
             }
             Ld8<Tdx>::store(dx + (size_t)row * lddx + c, o);
+            if (dx16 != nullptr) {     // bf16 (optionally row-masked) copy for the next backward GEMM: saves a separate cast pass
+                if (dx16_rowmask != nullptr && !dx16_rowmask[row]) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+                }
+                Ld8<__nv_bfloat16>::store(dx16 + (size_t)row * lddx16 + c, o);
+            }
         }
     }
     if (!ADA && dw != nullptr) {
@@ -174,30 +182,26 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const Tin* __restr
 }
 
 // ------------------------------------------------------------------------------------------- GLU (SiLU)
-// u: [n, 2H] (value | gate) -> h[n, H] = value * silu(gate) * dropout_keep / (1-p)
+// u: [n, 2H] (value | gate) -> h[n, H] = value * silu(gate) * dropout_keep / (1-p);  8 elements (16 bytes) per thread
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, int n_rows, int H, uint64_t seed,
                const uint64_t* __restrict__ rng_offset, uint32_t drop_thresh24, float keep_scale) {
     if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
-    const int per_row = H / 4;
+    const int per_row = H / 8;
     const int64_t total = (int64_t)n_rows * per_row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / per_row);
-        const int c = (int)(i % per_row) * 4;
-        const uint2 xv = *reinterpret_cast<const uint2*>(u + (size_t)row * 2 * H + c);
-        const uint2 gv = *reinterpret_cast<const uint2*>(u + (size_t)row * 2 * H + H + c);
-        const float2 x0 = unpack_bf16x2(xv.x), x1 = unpack_bf16x2(xv.y), g0 = unpack_bf16x2(gv.x), g1 = unpack_bf16x2(gv.y);
-        float xs[4] = {x0.x, x0.y, x1.x, x1.y}, gs[4] = {g0.x, g0.y, g1.x, g1.y}, o[4];
+        const int c = (int)(i % per_row) * 8;
+        float xs[8], gs[8], o[8];
+        Ld8<__nv_bfloat16>::load(u + (size_t)row * 2 * H + c, xs);
+        Ld8<__nv_bfloat16>::load(u + (size_t)row * 2 * H + H + c, gs);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const float sig = 1.f / (1.f + __expf(-gs[j]));
             o[j] = xs[j] * gs[j] * sig;
             if (drop_thresh24 != 0) o[j] = spb_keep(seed, (uint64_t)row * H + c + j, drop_thresh24) ? o[j] * keep_scale : 0.f;
         }
-        uint2 ov;
-        ov.x = pack_bf16x2(o[0], o[1]);
-        ov.y = pack_bf16x2(o[2], o[3]);
-        *reinterpret_cast<uint2*>(h + (size_t)row * H + c) = ov;
+        Ld8<__nv_bfloat16>::store(h + (size_t)row * H + c, o);
     }
 }
 
@@ -478,8 +482,8 @@ extern "C" int spb_layer_norm_fwd(const void* x, int x_fp32, int ldx, const floa
 
 extern "C" int spb_layer_norm_bwd(const void* dy, int lddy, const void* x, int x_fp32, int ldx, const float* mean,
                                   const float* rstd, const float* w, const void* gb, int ldgb, const float* dres, int lddres,
-                                  void* dx, int dx_fp32, int lddx, float* dw, float* db, void* dgb, int lddgb, int n_rows,
-                                  int dim, cudaStream_t stream) {
+                                  void* dx, int dx_fp32, int lddx, float* dw, float* db, void* dgb, int lddgb, void* dx16,
+                                  int lddx16, const uint8_t* dx16_rowmask, int n_rows, int dim, cudaStream_t stream) {
     if (n_rows <= 0) return SPB_OK;
     SPB_CHECK_ARG(dy && x && dx && mean && rstd, "spb_layer_norm_bwd: null pointer");
     const bool ada = gb != nullptr;
@@ -493,7 +497,8 @@ extern "C" int spb_layer_norm_bwd(const void* dy, int lddy, const void* x, int x
 #define LN_BWD(G, TI, TD, A)                                                                                              \
     ln_bwd_kernel<G, TI, TD, A><<<grid, thr, 0, stream>>>(dyp, lddy, reinterpret_cast<const TI*>(x), ldx, mean, rstd, w, \
                                                           gbp, ldgb, dres, lddres, reinterpret_cast<TD*>(dx), lddx, dw,  \
-                                                          db, dgbp, lddgb, n_rows)
+                                                          db, dgbp, lddgb, reinterpret_cast<__nv_bfloat16*>(dx16), lddx16,  \
+                                                          dx16_rowmask, n_rows)
     if (dim == 256 && x_fp32 && dx_fp32 && !ada) LN_BWD(1, float, float, false);
     else if (dim == 256 && x_fp32 && dx_fp32 && ada) LN_BWD(1, float, float, true);
     else if (dim == 256 && x_fp32 && !dx_fp32 && !ada) LN_BWD(1, float, __nv_bfloat16, false);
@@ -518,8 +523,8 @@ static inline uint32_t drop_thresh(float p) {
 extern "C" int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
                            cudaStream_t stream) {
     if (n_rows <= 0) return SPB_OK;
-    SPB_CHECK_ARG(u && h && hidden % 4 == 0, "spb_glu_fwd: bad arguments");
-    const int64_t total = (int64_t)n_rows * hidden / 4;
+    SPB_CHECK_ARG(u && h && hidden % 8 == 0, "spb_glu_fwd: hidden must be a multiple of 8");
+    const int64_t total = (int64_t)n_rows * hidden / 8;
     int64_t blocks = (total + 255) / 256;
     if (blocks > spb_num_sms() * 16) blocks = spb_num_sms() * 16;
     glu_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), reinterpret_cast<__nv_bfloat16*>(h),

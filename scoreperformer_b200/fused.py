@@ -356,25 +356,33 @@ class TransformerStackFn(torch.autograd.Function):
             small_off[0] += n
             return v, False
 
+        rowmask = None if mask is None else mask.view(-1)
+
         def norm_bwd(i_norm, dy16, rec, dres):
+            """LN backward (+ residual gradient); also returns the bf16 copy of the result the NEXT backward GEMM consumes:
+            row-masked when that consumer is an attention sub-layer (its output was multiplied by the mask)."""
+            next_is_attn = (i_norm % 2 == 1)              # after a feed-forward norm comes the attention sub-layer of that layer
+            want16 = i_norm > 0
+            rm16 = rowmask if next_is_attn else None
             if spec.ada:
                 sl = slice(i_norm * 2 * D, (i_norm + 1) * 2 * D)
-                return K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], None, gb_all[:, sl], dres=dres, dx_dtype=F32,
-                                        dgb=dgb_all[:, sl])
+                res = K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], None, gb_all[:, sl], dres=dres, dx_dtype=F32,
+                                       dgb=dgb_all[:, sl], want_dx16=want16, dx16_rowmask=rm16)
+                return res if want16 else (res, None)
             j = _norm_index(spec, i_norm)
             dw, d1 = take(params[j])
             db, d2 = take(params[j + 1])
-            dx = K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], params[j], dres=dres, dx_dtype=F32, dw=dw, db=db)
+            res = K.layer_norm_bwd(dy16, rec["x"], rec["mean"], rec["rstd"], params[j], dres=dres, dx_dtype=F32, dw=dw, db=db,
+                                   want_dx16=want16, dx16_rowmask=rm16)
             grads[j], grads[j + 1] = (None if d1 else dw), (None if d2 else db)
-            return dx
+            return res if want16 else (res, None)
 
-        g = norm_bwd(2 * spec.depth, K.cast_bf16(g_out.contiguous().view(N, D)), ctx.final, None)
+        g, g16 = norm_bwd(2 * spec.depth, K.cast_bf16(g_out.contiguous().view(N, D)), ctx.final, None)
         for l in reversed(range(spec.depth)):
             base = l * (PARAMS_PER_ATTN + PARAMS_PER_FF)
             rec_a, rec_f = ctx.layers[l]
             # ---- feed-forward backward:  x_out = x + W2 glu(W1 LN(x) + b1)
             p_w1, p_b1, p_w2 = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
-            g16 = K.cast_bf16(g)
             grads[base + PARAMS_PER_ATTN + 4] = wgrad(p_w2, g16, rec_f["h"])
             dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
             db1, d_b1 = take(p_b1)
@@ -382,10 +390,9 @@ class TransformerStackFn(torch.autograd.Function):
             grads[base + PARAMS_PER_ATTN + 3] = None if d_b1 else db1
             grads[base + PARAMS_PER_ATTN + 2] = wgrad(p_w1, du, rec_f["xn"])
             dxn = K.gemm(du, rec_f["w1_16"], trans_b=True, out_dtype=BF16)
-            g = norm_bwd(2 * l + 1, dxn, rec_f, g)
+            g, g16 = norm_bwd(2 * l + 1, dxn, rec_f, g)
             # ---- attention backward:  x_out = x + mask * Wo attn(Wqkv LN(x))
             p_q, p_k, p_v, p_o, p_ls = params[base + 2:base + 7]
-            g16 = K.cast_bf16(g, None if mask is None else mask.view(-1))
             grads[base + 5] = wgrad(p_o, g16, rec_a["o"])
             do = K.gemm(g16, rec_a["wo16"], trans_b=True, out_dtype=BF16)
             dls, d_ls = take(p_ls)
@@ -400,7 +407,7 @@ class TransformerStackFn(torch.autograd.Function):
                 hq = H * spec.dim_head
                 grads[base + 2], grads[base + 3], grads[base + 4] = dwqkv[:hq], dwqkv[hq:hq + spec.dim_head], dwqkv[hq + spec.dim_head:]
             dxn = K.gemm(dqkv, rec_a["wqkv16"], trans_b=True, out_dtype=BF16)
-            g = norm_bwd(2 * l, dxn, rec_a, g)
+            g, g16 = norm_bwd(2 * l, dxn, rec_a, g)
         d_style = None
         if spec.ada:
             dw_ada = K.gemm(dgb_all, style16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)   # [n_norms*2D, S]

@@ -18,6 +18,9 @@ LAUNCHES = 0
 # Optional device-side uint64 counter mixed into every dropout seed (set by train_step.TrainStep): kernels captured in a CUDA
 # graph read it at run time, so replays draw fresh masks although the host-side seeds were baked in at capture.
 RNG_OFFSET: Optional[Tensor] = None
+# "tcgen05" (TMEM/TMA kernel, needs 4 heads) or "mma" (legacy mma.sync kernel); SPB_ATTN_FWD overrides.
+import os as _os
+ATTENTION_FWD_IMPL = _os.environ.get("SPB_ATTN_FWD", "mma")
 
 
 def _count(n: int = 1) -> None:
@@ -130,17 +133,21 @@ def layer_norm_fwd(x: Tensor, w: Optional[Tensor], b: Optional[Tensor], gb: Opti
 
 def layer_norm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, w: Optional[Tensor], gb: Optional[Tensor] = None,
                    dres: Optional[Tensor] = None, dx_dtype: torch.dtype = F32, dw: Optional[Tensor] = None,
-                   db: Optional[Tensor] = None, dgb: Optional[Tensor] = None) -> Tensor:
-    """Returns dx; dw/db (fp32 [dim]) are accumulated into, dgb (bf16 view [n, 2*dim]) is written."""
+                   db: Optional[Tensor] = None, dgb: Optional[Tensor] = None, want_dx16: bool = False,
+                   dx16_rowmask: Optional[Tensor] = None):
+    """Returns dx (or (dx, dx16) with want_dx16: a bf16, optionally row-masked copy); dw/db (fp32 [dim]) are accumulated into,
+    dgb (bf16 view [n, 2*dim]) is written."""
     _require_cuda(dy, x)
     assert dy.dtype == BF16 and dy.stride(1) == 1 and x.stride(1) == 1
     n, dim = x.shape
     dx = torch.empty((n, dim), dtype=dx_dtype, device=x.device)
+    dx16 = torch.empty((n, dim), dtype=BF16, device=x.device) if want_dx16 else None
     _call("spb_layer_norm_bwd", _p(dy), dy.stride(0), _p(x), int(x.dtype == F32), x.stride(0), _p(mean), _p(rstd), _p(w), _p(gb),
           gb.stride(0) if gb is not None else 0, _p(dres), dres.stride(0) if dres is not None else 0, _p(dx), int(dx.dtype == F32),
-          dx.stride(0), _p(dw), _p(db), _p(dgb), dgb.stride(0) if dgb is not None else 0, n, dim, _stream())
+          dx.stride(0), _p(dw), _p(db), _p(dgb), dgb.stride(0) if dgb is not None else 0, _p(dx16), dim if want_dx16 else 0,
+          _p(dx16_rowmask), n, dim, _stream())
     _count()
-    return dx
+    return (dx, dx16) if want_dx16 else dx
 
 
 # ----------------------------------------------------------------------------- GLU
@@ -203,6 +210,12 @@ def attention_fwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, B:
     assert qkv.dtype == BF16 and qkv.stride(1) == 1 and logslopes.dtype == F32
     out = torch.empty((B * T, H * 64), dtype=BF16, device=qkv.device)
     lse = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+    if H == 4 and ATTENTION_FWD_IMPL == "tcgen05":
+        bits = torch.empty((B, (T + 31) // 32), dtype=torch.int32, device=qkv.device) if key_mask is not None else None
+        _call("spb_attention_fwd_tc", _p(qkv), qkv.stride(0), _p(key_mask), _p(bits), _p(logslopes), _p(out), out.stride(0), _p(lse),
+              B, T, H, 64, int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
+        _count(2 if key_mask is not None else 1)
+        return out, lse
     _call("spb_attention_fwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), out.stride(0), _p(lse), B, T, H, 64,
           int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
     _count()
