@@ -262,6 +262,7 @@ def main():
         ts.use_graph = False
         for _ in range(3):                    # first eager passes only warm the allocator (the graph owns a private pool)
             records.clear()
+            torch.cuda._sleep(int(60e6))      # ~30 ms spin kernel: lets the CPU run ahead so event pairs see GPU time only
             ts.step(dev_batch)
             torch.cuda.synchronize()
         K.gemm = orig
