@@ -65,6 +65,13 @@ int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p,
 int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p, uint64_t seed,
                 const uint64_t* rng_offset, spb_stream_t stream);
 
+/* Computed per-field tables W_f = index rows {discrete ids} + MLP(token_values) (modules/transformer/embeddings.py:124-143,199-211),
+ * all fields in one launch.  ptrs is a HOST array of device pointers, 7 per field for the forward (index_weight [V,128], token_values
+ * [V], discrete mask [V] fp32 0/1, W0 [128], b0 [128], W1 [128,128], b1 [128]) and 12 per field for the backward (+ the five gradient
+ * buffers d_index_weight, dW0, db0, dW1, db1, all ACCUMULATED into). */
+int spb_table_build_fwd(const int* field_sizes, int n_fields, const void* const* ptrs, float* table, spb_stream_t stream);
+int spb_table_build_bwd(const int* field_sizes, int n_fields, const void* const* ptrs, const float* dtable, spb_stream_t stream);
+
 /* Fused SPMuple tuple-token embedding: out[n, F*128] = LayerNorm(cat_f table[off_f + tokens[n,f]]) in bf16.
  * table fp32 [sum V_f, 128] is the concatenation of the computed per-field tables (modules/transformer/embeddings.py:91-143).
  * Replaces models/scoreperformer/embeddings.py:121-143 (12 gathers + cat + LayerNorm). */

@@ -156,6 +156,46 @@ def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, out_fp32: bool = False, 
     return LayerNormFn.apply(x.reshape(-1, shape[-1]), weight, bias, out_fp32, eps).view(shape)
 
 
+# ----------------------------------------------------------------------------- computed per-field tables (a1)
+class TableBuildFn(torch.autograd.Function):
+    """table [sum V_f, 128] = cat_f ( index rows of the discrete ids | MLP(token_values_f) elsewhere ), one launch for all fields.
+
+    modules/transformer/embeddings.py:124-143 (token_weight + value_weight) with the dense value MLP of :199-211.
+    params: per field (index_weight, W0 [128,1], b0, W1 [128,128], b1); consts: per field (token_values [V,1], discrete mask [V,1])."""
+
+    @staticmethod
+    def forward(ctx, sizes: Tuple[int, ...], consts: Tuple[Tensor, ...], *params):
+        nf = len(sizes)
+        per_field = []
+        for f in range(nf):
+            iw, w0, b0, w1, b1 = params[5 * f:5 * f + 5]
+            per_field.append((iw.detach(), consts[2 * f], consts[2 * f + 1], w0.detach(), b0.detach(), w1.detach(), b1.detach()))
+        ctx.sizes, ctx.consts, ctx.params = sizes, consts, params
+        return K.table_build_fwd(sizes, per_field)
+
+    @staticmethod
+    def backward(ctx, dtable):
+        sizes, consts, params = ctx.sizes, ctx.consts, ctx.params
+        nf = len(sizes)
+        per_field, grads = [], []
+        for f in range(nf):
+            ps = params[5 * f:5 * f + 5]
+            bufs = []
+            for p_ in ps:
+                g = direct_grad(p_)
+                if g is not None:
+                    bufs.append(g)
+                    grads.append(None)
+                else:
+                    z = torch.zeros_like(p_)
+                    bufs.append(z)
+                    grads.append(z)
+            per_field.append((ps[0].detach(), consts[2 * f], consts[2 * f + 1], ps[1].detach(), ps[2].detach(), ps[3].detach(),
+                              ps[4].detach(), *bufs))
+        K.table_build_bwd(sizes, per_field, dtable.contiguous())
+        return (None, None) + tuple(grads)
+
+
 # ----------------------------------------------------------------------------- tuple-token embedding (a1/a2)
 class TupleEmbedFn(torch.autograd.Function):
     """project_emb(LayerNorm(cat_f table_f[tokens_f])) -> bf16 [n, dim]  (models/scoreperformer/embeddings.py:121-143)."""

@@ -170,6 +170,30 @@ def glu_bwd(dh: Tensor, u: Tensor, dbias: Optional[Tensor], dropout_p: float, se
     return du
 
 
+# ----------------------------------------------------------------------------- computed tables
+def _ptr_array(tensors: Sequence[Tensor]):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def table_build_fwd(sizes: Sequence[int], per_field: Sequence[Sequence[Tensor]]) -> Tensor:
+    """per_field[f] = (index_weight, token_values, discrete_mask, W0, b0, W1, b1) -> table fp32 [sum V, 128]."""
+    flat = [t for fld in per_field for t in fld]
+    _require_cuda(*flat)
+    assert all(t.dtype == F32 and t.is_contiguous() for t in flat)
+    table = torch.empty((int(sum(sizes)), 128), dtype=F32, device=flat[0].device)
+    _call("spb_table_build_fwd", _sizes_array(sizes), len(sizes), _ptr_array(flat), _p(table), _stream())
+    _count()
+    return table
+
+
+def table_build_bwd(sizes: Sequence[int], per_field: Sequence[Sequence[Tensor]], dtable: Tensor) -> None:
+    """per_field[f] = the 7 forward tensors + (d_index_weight, dW0, db0, dW1, db1), accumulated into."""
+    flat = [t for fld in per_field for t in fld]
+    assert all(t.dtype == F32 and t.is_contiguous() for t in flat) and dtable.dtype == F32 and dtable.is_contiguous()
+    _call("spb_table_build_bwd", _sizes_array(sizes), len(sizes), _ptr_array(flat), _p(dtable), _stream())
+    _count()
+
+
 # ----------------------------------------------------------------------------- tuple embedding
 def _sizes_array(sizes: Sequence[int]):
     return (ctypes.c_int * len(sizes))(*[int(s) for s in sizes])

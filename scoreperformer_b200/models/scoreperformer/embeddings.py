@@ -21,21 +21,40 @@ from ...modules.transformer import DiscreteContinuousEmbedding, DiscreteDenseCon
 TupleTokenEmbeddingsRegistry = type("_TupleTokenEmbeddingsRegistry", (Registry,), {})()
 
 
-def build_table(embs: nn.ModuleDict, cache: Optional[dict] = None) -> Tensor:
-    rows = []
+def _fused_table_ok(embs: nn.ModuleDict) -> bool:
     for emb in embs.values():
-        if cache is None:
-            rows.append(emb.weight)
-        else:
-            if id(emb) not in cache:
-                cache[id(emb)] = emb.weight
-            rows.append(cache[id(emb)])
+        if not isinstance(emb, DiscreteDenseContinuousEmbedding) or emb.embedding_dim != 128 or emb.discrete or not emb.continuous:
+            return False
+        if emb.discrete_ids is None or emb.token_values is None or len(emb.value_layer) != 2 or not emb.index_weight.is_cuda:
+            return False
+    return len(embs) <= 16
+
+
+def build_table(embs: nn.ModuleDict, cache: Optional[dict] = None) -> Tensor:
+    """Concatenated computed tables of the field modules.  The recipes' configuration (dense continuous embeddings, 128 wide)
+    is built by ONE fused kernel (fused.TableBuildFn); anything else falls back to the per-field module arithmetic."""
     key = ("cat",) + tuple(id(e) for e in embs.values())
     if cache is not None:
-        if key not in cache:
-            cache[key] = torch.cat(rows, dim=0)
-        return cache[key]
-    return torch.cat(rows, dim=0)
+        if key in cache:
+            return cache[key]
+        for other, tab in cache.items():        # tied score fields are a prefix of the performance fields: slice, don't rebuild
+            if isinstance(other, tuple) and other and other[0] == "cat" and len(other) > len(key) and other[:len(key)] == key:
+                rows = sum(int(e.num_embeddings) for e in embs.values())
+                cache[key] = tab[:rows]
+                return cache[key]
+    if _fused_table_ok(embs):
+        sizes = tuple(int(e.num_embeddings) for e in embs.values())
+        consts, params = [], []
+        for e in embs.values():
+            consts += [e.token_values, e._discrete_mask]
+            params += [e.index_weight, e.value_layer[0][0].weight, e.value_layer[0][0].bias, e.value_layer[1][0].weight,
+                       e.value_layer[1][0].bias]
+        table = fused.TableBuildFn.apply(sizes, tuple(consts), *params)
+    else:
+        table = torch.cat([e.weight for e in embs.values()], dim=0)
+    if cache is not None:
+        cache[key] = table
+    return table
 
 
 @dataclass

@@ -362,3 +362,34 @@ def test_clf_heads(k):
     k.clf_heads(x, rowmask, labels, W, b, cw, ncls, 0.0, 0, dlogit_scale=scale, dW=dW, db=db)
     assert rel_err(dW, Wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
     assert rel_err(k.clf_logits(x, W, b), x @ W.t() + b) < 1e-5
+
+
+def test_table_build_matches_module_arithmetic():
+    """Fused table kernel (forward + backward) against the per-field module arithmetic (the reference's token_weight + value MLP)."""
+    from scoreperformer_b200 import fused
+    from scoreperformer_b200.modules.transformer import DiscreteDenseContinuousEmbedding
+    torch.manual_seed(13)
+    sizes = [260, 16, 85]
+    embs = torch.nn.ModuleDict()
+    for i, v in enumerate(sizes):
+        tv = [0.0] * 4 + torch.linspace(0, 1, v - 4).tolist()
+        e = DiscreteDenseContinuousEmbedding(v, 128, discrete=False, continuous=True, discrete_ids=[0, 1, 2, 3], token_values=tv, padding_idx=0)
+        for p_ in e.parameters():
+            p_.data.normal_(0, 0.5)
+        embs[f"f{i}"] = e
+    embs = embs.cuda()
+    ref = torch.cat([e.weight for e in embs.values()], 0)
+    g = randn(sum(sizes), 128)
+    ref.backward(g)
+    ref_grads = [p_.grad.clone() for p_ in embs.parameters()]
+    for p_ in embs.parameters():
+        p_.grad = None
+    consts, params = [], []
+    for e in embs.values():
+        consts += [e.token_values, e._discrete_mask]
+        params += [e.index_weight, e.value_layer[0][0].weight, e.value_layer[0][0].bias, e.value_layer[1][0].weight, e.value_layer[1][0].bias]
+    out = fused.TableBuildFn.apply(tuple(sizes), tuple(consts), *params)
+    assert rel_err(out, ref) < 1e-5
+    out.backward(g)
+    for p_, want in zip(embs.parameters(), ref_grads):
+        assert rel_err(p_.grad, want) < 1e-4
