@@ -89,6 +89,21 @@ __device__ __forceinline__ bool spb_keep(uint64_t seed, uint64_t idx, uint32_t d
     return (spb_hash32(seed, idx) >> 8) >= drop_thresh24;
 }
 
+// Cheap form for the bandwidth-bound elementwise kernels: ONE 32-bit hash (8 integer instructions instead of three 64-bit
+// multiplies) decides two elements, 16 bits each; keep-probability resolution 2^-16.
+__device__ __forceinline__ uint32_t spb_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t spb_seed32(uint64_t seed) { return (uint32_t)(seed ^ (seed >> 32)); }
+__device__ __forceinline__ uint32_t spb_pair_hash(uint32_t seed32, uint32_t pair_idx) {
+    return spb_mix32((pair_idx * 0x9E3779B9u) ^ seed32);
+}
+// half = 0 / 1 selects the element of the pair; thr16 = drop_thresh24 >> 8
+__device__ __forceinline__ bool spb_keep16(uint32_t pair_hash, int half, uint32_t thr16) {
+    return ((pair_hash >> (16 * half)) & 0xFFFFu) >= thr16;
+}
+
 // ----------------------------------------------------------------------------- PTX: mbarrier / TMA / tcgen05
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

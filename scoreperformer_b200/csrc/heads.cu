@@ -114,8 +114,10 @@ clf_heads_kernel(const float* __restrict__ x, int ldx, const uint8_t* __restrict
             }
             float a0 = x0, a1 = x1;
             if (drop_thresh24 != 0) {
-                a0 = spb_keep(seed, ((uint64_t)row * CLF_MAX_HEADS + g) * 64 + lane, drop_thresh24) ? x0 * keep_scale : 0.f;
-                a1 = spb_keep(seed, ((uint64_t)row * CLF_MAX_HEADS + g) * 64 + lane + 32, drop_thresh24) ? x1 * keep_scale : 0.f;
+                // one hash per (row, head, lane): low half decides input dim `lane`, high half dim `lane + 32`
+                const uint32_t hsh = spb_pair_hash(spb_seed32(seed), ((uint32_t)row * CLF_MAX_HEADS + (uint32_t)g) * 32u + (uint32_t)lane);
+                a0 = spb_keep16(hsh, 0, drop_thresh24 >> 8) ? x0 * keep_scale : 0.f;
+                a1 = spb_keep16(hsh, 1, drop_thresh24 >> 8) ? x1 * keep_scale : 0.f;
             }
             // lane c (< C) keeps logit c
             float my_logit = -INFINITY;
@@ -168,8 +170,10 @@ clf_wgrad_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
             float v = 0.f;
             if (r < nr && k < in_dim) {
                 v = x[(size_t)(r0 + r) * ldx + k];
-                if (drop_thresh24 != 0)
-                    v = spb_keep(seed, ((uint64_t)(r0 + r) * CLF_MAX_HEADS + g) * 64 + k, drop_thresh24) ? v * keep_scale : 0.f;
+                if (drop_thresh24 != 0) {
+                    const uint32_t hsh = spb_pair_hash(spb_seed32(seed), ((uint32_t)(r0 + r) * CLF_MAX_HEADS + (uint32_t)g) * 32u + (uint32_t)(k & 31));
+                    v = spb_keep16(hsh, k >> 5, drop_thresh24 >> 8) ? v * keep_scale : 0.f;
+                }
             }
             sx[r][k] = v;
         }

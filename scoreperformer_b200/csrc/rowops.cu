@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, int n_rows, int H, uint64_t seed,
                const uint64_t* __restrict__ rng_offset, uint32_t drop_thresh24, float keep_scale) {
     if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
+    const uint32_t seed32 = spb_seed32(seed), thr16 = drop_thresh24 >> 8;
     const int per_row = H / 8;
     const int64_t total = (int64_t)n_rows * per_row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -195,11 +196,19 @@ glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ 
         float xs[8], gs[8], o[8];
         Ld8<__nv_bfloat16>::load(u + (size_t)row * 2 * H + c, xs);
         Ld8<__nv_bfloat16>::load(u + (size_t)row * 2 * H + H + c, gs);
+        const uint32_t pair0 = (uint32_t)row * (uint32_t)(H >> 1) + (uint32_t)(c >> 1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float sig = 1.f / (1.f + __expf(-gs[j]));
             o[j] = xs[j] * gs[j] * sig;
-            if (drop_thresh24 != 0) o[j] = spb_keep(seed, (uint64_t)row * H + c + j, drop_thresh24) ? o[j] * keep_scale : 0.f;
+        }
+        if (drop_thresh24 != 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const uint32_t hsh = spb_pair_hash(seed32, pair0 + (uint32_t)(j >> 1));
+                o[j] = spb_keep16(hsh, 0, thr16) ? o[j] * keep_scale : 0.f;
+                o[j + 1] = spb_keep16(hsh, 1, thr16) ? o[j + 1] * keep_scale : 0.f;
+            }
         }
         Ld8<__nv_bfloat16>::store(h + (size_t)row * H + c, o);
     }
@@ -213,6 +222,7 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __rest
                float* __restrict__ dbias, int n_rows, int H, uint64_t seed, const uint64_t* __restrict__ rng_offset,
                uint32_t drop_thresh24, float keep_scale) {
     if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
+    const uint32_t seed32 = spb_seed32(seed), thr16 = drop_thresh24 >> 8;
     float sx[MAXG][4], sg[MAXG][4];
 #pragma unroll
     for (int k = 0; k < MAXG; ++k)
@@ -231,10 +241,18 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __rest
                 const float2 g0 = unpack_bf16x2(gv.x), g1 = unpack_bf16x2(gv.y);
                 float ds[4] = {d0.x, d0.y, d1.x, d1.y}, xs[4] = {x0.x, x0.y, x1.x, x1.y}, gs[4] = {g0.x, g0.y, g1.x, g1.y};
                 float ox[4], og[4];
+                if (drop_thresh24 != 0) {      // same (seed, pair) hashes as the forward kernel
+                    const uint32_t pair0 = (uint32_t)row * (uint32_t)(H >> 1) + (uint32_t)(c >> 1);
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2) {
+                        const uint32_t hsh = spb_pair_hash(seed32, pair0 + (uint32_t)(j >> 1));
+                        ds[j] = spb_keep16(hsh, 0, thr16) ? ds[j] * keep_scale : 0.f;
+                        ds[j + 1] = spb_keep16(hsh, 1, thr16) ? ds[j + 1] * keep_scale : 0.f;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float d = ds[j];
-                    if (drop_thresh24 != 0) d = spb_keep(seed, (uint64_t)row * H + c + j, drop_thresh24) ? d * keep_scale : 0.f;
+                    const float d = ds[j];
                     const float sig = 1.f / (1.f + __expf(-gs[j]));
                     const float silu = gs[j] * sig;
                     ox[j] = d * silu;

@@ -11,16 +11,23 @@ dev = "cuda"
 
 
 def t(fn, iters=20):
+    """GPU time per launch: `iters` launches captured in one CUDA graph (no CPU launch floor), replayed 3 times."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3
+    return e0.elapsed_time(e1) / (3 * iters) * 1e3
 
 
 def case(name, m, n, k, ta=False, tb=False, out=BF, bias=False, residual=False, rowmask=False, split_k=1):
