@@ -311,6 +311,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool a_mn_m
 
 #endif  // __CUDACC__
 
+// ----------------------------------------------------------------------------- tuple-embedding field layout
+constexpr int MAX_FIELDS = 16;
+struct FieldTable {
+    int n_fields;
+    int offset[MAX_FIELDS];   // first row of field f in the concatenated table
+    int size[MAX_FIELDS];     // V_f
+};
+#ifdef __CUDACC__
+// tensor-core scatter of the table gradient (embed_scatter.cu)
+int spb_embed_scatter_mma(const __nv_bfloat16* dy, int ld_dy, const int64_t* tokens, int ld_tok, const float* table,
+                          const FieldTable& ft, const float* w, const float* mean, const float* rstd, const float* c1,
+                          const float* c2, float* dtable, int n_rows, cudaStream_t stream);
+#endif
+
 // ----------------------------------------------------------------------------- TMA descriptors (host)
 // 2-D bf16 tensor map with 128-byte swizzle. `inner` is the contiguous dimension.
 int spb_make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,

@@ -11,6 +11,8 @@
 // one fp32 atomic per column per CTA.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int ROW_WARPS = 8;
@@ -285,12 +287,6 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------- tuple embedding
-constexpr int MAX_FIELDS = 16;
-struct FieldTable {
-    int n_fields;
-    int offset[MAX_FIELDS];   // first row of field f in the concatenated table
-    int size[MAX_FIELDS];     // V_f
-};
 
 // out[n, F*128] = LayerNorm_{F*128}( cat_f table[offset_f + tokens[n, f]] ); one warp per tuple.
 template <int F>
@@ -339,7 +335,7 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ tokens, int ld_tok, const float*
 
 // Backward pass 1: per-tuple c1 = mean(dy*w), c2 = mean(dy*w*xhat); dw += dy*xhat, db += dy.
 template <int F>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
 embed_ln_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int ld_dy, const int64_t* __restrict__ tokens, int ld_tok,
                           const float* __restrict__ table, FieldTable ft, const float* __restrict__ w,
                           const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ c1_out,
@@ -622,6 +618,8 @@ extern "C" int spb_embed_ln_bwd(const void* dy, int ld_dy, const int64_t* tokens
         return SPB_ERR_ARG;
     }
     SPB_CHECK_LAUNCH();
+    if (getenv("SPB_EMBED_SCATTER_ATOMIC") == nullptr)
+        return spb_embed_scatter_mma(d, ld_dy, tokens, ld_tok, table, ft, w, mean, rstd, c1, c2, dtable, n_rows, stream);
     int max_v = 0;
     for (int f = 0; f < n_fields; ++f) max_v = field_sizes[f] > max_v ? field_sizes[f] : max_v;
     const size_t smem = (size_t)max_v * 128 * sizeof(float);

@@ -15,7 +15,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libspb200.so")
-SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "latents.cu", "heads.cu", "tables.cu"]
+SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "latents.cu", "heads.cu", "tables.cu"]
 
 _P, _I, _F, _L, _U64 = c_void_p, c_int, c_float, c_int64, c_uint64
 

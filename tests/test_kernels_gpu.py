@@ -172,7 +172,7 @@ def test_embed_ln(k, F_):
     ref.backward(dy.float())
     dtable, dw, db = torch.zeros_like(table), torch.zeros_like(w), torch.zeros_like(b)
     k.embed_ln_bwd(dy, tokens, table, sizes, w, mean, rstd, dtable, dw, db)
-    assert rel_err(dtable, tr.grad) < 1e-4
+    assert rel_err(dtable, tr.grad) < 4e-3        # dx is rounded to bf16 (like dy itself) before the tensor-core scatter
     assert rel_err(dw, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
 
 
