@@ -140,7 +140,7 @@ __device__ __forceinline__ void acc_to_frags(const float acc[8][4], uint32_t pf[
 
 // ------------------------------------------------------------------------------------------- forward
 // grid (ceil(T/64), H, B), 128 threads; warp w owns query rows [16w, 16w+16) of the tile.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float* __restrict__ lse_out) {
     if (p.rng_offset != nullptr) p.seed += *p.rng_offset * 0x9E3779B97F4A7C15ull;
     __shared__ __align__(128) uint8_t sQ[TQ * 128];
