@@ -123,6 +123,13 @@ int spb_mmd_fwd_bwd(const float* z_prior, const float* y, const uint8_t* w, int 
 int spb_ce_rows(const float* logits, int ld, const int64_t* labels, int ld_lab, int V, long long ignore_index, float* loss_sum,
                 float* count, void* dlogits, int ld_d, int* argmax_out, int n_rows, spb_stream_t stream);
 
+/* Tied head of one tuple field fused with its cross-entropy (embeddings.py:345-353 + wrappers.py:49-59): the [n, V] logits
+ * e_f . table_f^T stay in tensor memory; only loss_sum / count (ACCUMULATED), the optional bf16 gradient rows
+ * dlogits = softmax - onehot (zero for ignored labels; columns [V, ld_d) zeroed) and the optional argmax leave the SM.
+ * e bf16 [n, lde] (the field's 128 columns), table bf16 [V, ldt], V <= 256. */
+int spb_head_ce(const void* e, int lde, const void* table, int ldt, int V, const int64_t* labels, int ld_lab, long long ignore_index,
+                float* loss_sum, float* count, void* dlogits, int ld_d, int* argmax, int n_rows, spb_stream_t stream);
+
 /* Direction-classifier heads (models/classifiers/model.py:74-82,202-216): Dropout -> Linear(in_dim, C_g) -> weighted CE. */
 int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, const int64_t* labels, int ld_lab, const float* W, const float* bias,
                   const float* class_w, const int* n_classes, int n_heads, float* num, float* den, const float* dlogit_scale, float* dW,

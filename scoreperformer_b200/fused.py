@@ -563,9 +563,14 @@ class TiedHeadCEFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         for f in fields:
             V = sizes[f]
-            logits = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + V], out_dtype=F32)
             dl = torch.empty((n, (V + 7) // 8 * 8), dtype=BF16, device=dev) if need_grad else None
-            K.ce_rows(logits, labels[:, f], V, loss_sum[f:f + 1], count[f:f + 1], dl, None, ignore_index)
+            if emb == 128 and V <= 256:
+                # logits stay in tensor memory: GEMM + masked CE + gradient rows in one kernel
+                K.head_ce(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + V], labels[:, f], loss_sum[f:f + 1], count[f:f + 1],
+                          dl, None, ignore_index)
+            else:
+                logits = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + V], out_dtype=F32)
+                K.ce_rows(logits, labels[:, f], V, loss_sum[f:f + 1], count[f:f + 1], dl, None, ignore_index)
             dlogits[f] = dl
         active = count > 0
         per_field = loss_sum / count.clamp(min=1.0)

@@ -320,6 +320,21 @@ def ce_rows(logits: Tensor, labels: Tensor, V: int, loss_sum: Tensor, count: Ten
     _count()
 
 
+def head_ce(e_f: Tensor, table_f: Tensor, labels: Tensor, loss_sum: Tensor, count: Tensor, dlogits: Optional[Tensor] = None,
+            argmax: Optional[Tensor] = None, ignore_index: int = -100) -> None:
+    """Fused tied head + cross-entropy of one field: e_f bf16 [n, 128] (strided view allowed), table_f bf16 [V, 128],
+    labels int64 [n] (strided view allowed).  loss_sum / count fp32 scalars are accumulated into."""
+    _require_cuda(e_f, table_f)
+    assert e_f.dtype == BF16 and table_f.dtype == BF16 and e_f.shape[1] == 128 and table_f.shape[1] == 128
+    assert e_f.stride(1) == 1 and table_f.stride(1) == 1 and labels.dtype == torch.int64 and labels.dim() == 1
+    n, V = e_f.shape[0], table_f.shape[0]
+    if dlogits is not None:
+        assert dlogits.dtype == BF16 and dlogits.shape[0] == n and dlogits.stride(1) == 1
+    _call("spb_head_ce", _p(e_f), e_f.stride(0), _p(table_f), table_f.stride(0), V, _p(labels), labels.stride(0), ignore_index,
+          _p(loss_sum), _p(count), _p(dlogits), dlogits.stride(0) if dlogits is not None else 0, _p(argmax), n, _stream())
+    _count()
+
+
 def clf_heads(x: Tensor, rowmask: Tensor, labels: Tensor, W: Tensor, bias: Tensor, class_w: Tensor, n_classes: Sequence[int],
               dropout_p: float, seed: int, num: Optional[Tensor] = None, den: Optional[Tensor] = None,
               dlogit_scale: Optional[Tensor] = None, dW: Optional[Tensor] = None, db: Optional[Tensor] = None) -> None:

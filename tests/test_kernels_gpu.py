@@ -333,6 +333,38 @@ def test_ce_rows(k, V):
     assert torch.equal(am.long(), logits.argmax(-1))
 
 
+@pytest.mark.parametrize("V,n", [(132, 999), (125, 4096), (165, 130), (85, 777), (256, 300), (16, 64)])
+def test_head_ce_fused(k, V, n):
+    """Tied head + CE in one kernel (logits stay in TMEM) against torch: loss, count, gradient rows, argmax."""
+    torch.manual_seed(13)
+    e_all = randn(n, 3 * 128, dtype=BF16)                     # the field's 128 columns are a strided slice
+    e = e_all[:, 128:256]
+    table = (randn(V + 5, 128) * 0.3).to(BF16)[2:2 + V]     # row-offset slice of a bigger table
+    labels2 = torch.randint(0, V, (n, 2), device="cuda")
+    labels2[::3, 1] = -100
+    labels = labels2[:, 1]
+    logits = (e.float() @ table.float().t()).requires_grad_(True)
+    ref = F.cross_entropy(logits, labels, ignore_index=-100, reduction="sum")
+    ref.backward()
+    ls, cnt = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    vpad = (V + 7) // 8 * 8
+    dl = torch.full((n, vpad), 7.0, dtype=BF16, device="cuda")
+    am = torch.empty(n, dtype=torch.int32, device="cuda")
+    k.head_ce(e, table, labels, ls, cnt, dl, am)
+    assert abs(float(ls) - float(ref)) / abs(float(ref)) < 1e-4
+    assert int(cnt) == int((labels != -100).sum())
+    assert rel_err(dl[:, :V], logits.grad) < 1e-2
+    if vpad > V:
+        assert float(dl[:, V:].abs().max()) == 0
+    top2 = logits.detach().topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3                # argmax may differ only on near ties (fp32 accumulation order)
+    assert torch.equal(am.long()[clear], logits.detach().argmax(-1)[clear])
+    # loss only (inference / evaluation): no gradient buffer
+    ls2, cnt2 = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    k.head_ce(e, table, labels, ls2, cnt2)
+    assert abs(float(ls2) - float(ls)) <= 1e-6 * abs(float(ls))
+
+
 def test_clf_heads(k):
     torch.manual_seed(12)
     n, in_dim = 1500, 64
