@@ -130,6 +130,13 @@ int spb_ce_rows(const float* logits, int ld, const int64_t* labels, int ld_lab, 
 int spb_head_ce(const void* e, int lde, const void* table, int ldt, int V, const int64_t* labels, int ld_lab, long long ignore_index,
                 float* loss_sum, float* count, void* dlogits, int ld_d, int* argmax, int n_rows, spb_stream_t stream);
 
+/* Optimiser step on the flat buffers (experiments/optimizers.py:151-169): clip_grad_norm_(max_norm) + AdamW + bf16 shadow
+ * refresh in one pass.  grad_norm = device scalar ||g||_2 before grad_scale (null / max_norm <= 0: no clipping);
+ * step = device int64 with the 1-based step number. */
+int spb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* grad_norm, float grad_scale,
+                   float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, const int64_t* step,
+                   spb_stream_t stream);
+
 /* Direction-classifier heads (models/classifiers/model.py:74-82,202-216): Dropout -> Linear(in_dim, C_g) -> weighted CE. */
 int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, const int64_t* labels, int ld_lab, const float* W, const float* bias,
                   const float* class_w, const int* n_classes, int n_heads, float* num, float* den, const float* dlogit_scale, float* dW,

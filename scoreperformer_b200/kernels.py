@@ -335,6 +335,20 @@ def head_ce(e_f: Tensor, table_f: Tensor, labels: Tensor, loss_sum: Tensor, coun
     _count()
 
 
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, shadow: Optional[Tensor], grad_norm: Optional[Tensor], step: Tensor, *,
+               lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, max_norm: float = 0.0,
+               grad_scale: float = 1.0) -> None:
+    """Clip-by-global-norm + AdamW + bf16 shadow refresh over flat fp32 buffers (one launch for the whole model)."""
+    _require_cuda(p, g, m, v)
+    assert p.dtype == F32 and g.dtype == F32 and m.dtype == F32 and v.dtype == F32 and step.dtype == torch.int64
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or (shadow.dtype == BF16 and shadow.numel() == n))
+    _call("spb_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(shadow), n, _p(grad_norm), float(grad_scale), float(max_norm), float(lr),
+          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), _p(step), _stream())
+    _count()
+
+
 def clf_heads(x: Tensor, rowmask: Tensor, labels: Tensor, W: Tensor, bias: Tensor, class_w: Tensor, n_classes: Sequence[int],
               dropout_p: float, seed: int, num: Optional[Tensor] = None, den: Optional[Tensor] = None,
               dlogit_scale: Optional[Tensor] = None, dW: Optional[Tensor] = None, db: Optional[Tensor] = None) -> None:

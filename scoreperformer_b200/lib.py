@@ -15,7 +15,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libspb200.so")
-SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "latents.cu", "heads.cu", "head_ce.cu", "tables.cu"]
+SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "latents.cu", "heads.cu", "head_ce.cu", "tables.cu", "optim.cu"]
 
 _P, _I, _F, _L, _U64 = c_void_p, c_int, c_float, c_int64, c_uint64
 
@@ -40,6 +40,7 @@ SIGNATURES = {
     "spb_latent_level_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "spb_mmd_fwd_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "spb_head_ce": [_P, _I, _P, _I, _I, _P, _I, c_longlong, _P, _P, _P, _I, _P, _I, _P],
+    "spb_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "spb_ce_rows": [_P, _I, _P, _I, _I, c_longlong, _P, _P, _P, _I, _P, _I, _P],
     "spb_clf_heads": [_P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U64, _P, _I, _P],
     "spb_clf_logits": [_P, _I, _P, _P, _P, _I, _I, _I, _P],

@@ -3,9 +3,11 @@
 Mirrors what `Trainer.run_epoch` + `Optimizer.step` do per batch (experiments/trainer.py:449-452, optimizers.py:151-169:
 backward, `clip_grad_norm_(2.0)`, AdamW(lr 2e-4, wd 1e-6), `zero_grad`) with two B200-first changes:
 
-* gradients live in ONE flat fp32 buffer (every `p.grad` is a view), so data parallelism is a single NCCL all-reduce of
-  46 MB over NVLink per step, and clipping / zeroing are single kernels; weight-gradient kernels accumulate straight into
-  that buffer (fused.DIRECT_GRAD) and ONE cast kernel per step refreshes a flat bf16 shadow of all weights (fused.SHADOW_ACTIVE);
+* parameters, gradients, both AdamW moments and a bf16 weight shadow live in flat buffers (every `p.data` / `p.grad` is a
+  view), so data parallelism is a single NCCL all-reduce of 46 MB over NVLink per step and the optimiser is ONE kernel:
+  clip-by-global-norm + AdamW in one pass over memory (csrc/optim.cu); weight-gradient kernels accumulate
+  straight into the gradient buffer (fused.DIRECT_GRAD) and ONE cast kernel per step refreshes the bf16 shadow every
+  forward GEMM reads its weight from (fused.SHADOW_ACTIVE);
 * forward + backward (the whole kernel sequence, ~1 000 launches) is captured once in a CUDA graph and replayed, because
   at ~15 ms per step the Python dispatch of the eager path (~19 ms) would otherwise be the bottleneck.  Dropout stays
   random across replays through a device-side counter mixed into the kernels' seeds (kernels.RNG_OFFSET).
@@ -23,9 +25,10 @@ from . import fused, kernels as K
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, lr: float = 2e-4, weight_decay: float = 1e-6, grad_clip: Optional[float] = 2.0,
-                 use_graph: bool = True, process_group=None):
+                 use_graph: bool = True, process_group=None, betas=(0.9, 0.999), eps: float = 1e-8):
         self.model = model
         self.grad_clip = grad_clip
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, tuple(betas), eps
         self.use_graph = use_graph
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -48,7 +51,10 @@ class TrainStep:
             p.data = view
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             p._spb_shadow = self.flat_shadow[off:off + p.numel()].view_as(p)
-        self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=True, capturable=True)
+        self.offsets = offsets
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)        # AdamW exp_avg
+        self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)        # AdamW exp_avg_sq
+        self.opt_step = torch.zeros(1, dtype=torch.int64, device=dev)        # device-side step number (CUDA-graph safe)
         if use_graph and getattr(model, "perf_encoder", None) is not None:
             model.perf_encoder.exact_latent_shapes = False      # static segment tables: the step must not sync with the host
         self.rng_offset = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -76,11 +82,41 @@ class TrainStep:
     def _update(self):
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat_grad.mul_(1.0 / self.world)
-        if self.grad_clip is not None:
-            norm = torch.linalg.vector_norm(self.flat_grad)
-            self.flat_grad.mul_(torch.clamp(self.grad_clip / (norm + 1e-6), max=1.0))
-        self.optimizer.step()
+        norm = torch.linalg.vector_norm(self.flat_grad) if self.grad_clip is not None else None
+        self.opt_step.add_(1)
+        # averaging over ranks, clipping and AdamW: one pass over the flat buffers
+        K.adamw_step(self.flat_param, self.flat_grad, self.flat_m, self.flat_v, None, norm, self.opt_step, lr=self.lr,
+                     betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, max_norm=self.grad_clip or 0.0,
+                     grad_scale=1.0 / self.world)
+
+    def set_lr(self, lr: float):
+        """ExponentialLR etc. (experiments/optimizers.py:121-149): the rate is baked into a captured graph, so re-capture."""
+        if lr != self.lr:
+            self.lr = lr
+            self.graph = None
+
+    def optimizer_state_dict(self) -> dict:
+        """`torch.optim.AdamW.state_dict()`-shaped view of the flat moments, so reference checkpoints interoperate."""
+        state = {}
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            state[i] = {"step": self.opt_step.clone().float().squeeze(0),
+                        "exp_avg": self.flat_m[off:off + p.numel()].view_as(p).clone(),
+                        "exp_avg_sq": self.flat_v[off:off + p.numel()].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict):
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            self.flat_m[off:off + p.numel()].view_as(p).copy_(st["exp_avg"])
+            self.flat_v[off:off + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+            self.opt_step.fill_(int(st["step"]))
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+        self.graph = None
 
     def _capture(self, batch: Dict[str, Tensor]):
         self.static_batch = {k: v.clone() for k, v in batch.items()}

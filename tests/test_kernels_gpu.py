@@ -365,6 +365,33 @@ def test_head_ce_fused(k, V, n):
     assert abs(float(ls2) - float(ls)) <= 1e-6 * abs(float(ls))
 
 
+@pytest.mark.parametrize("world", [1, 4])
+def test_adamw_flat_matches_torch(k, world):
+    """csrc/optim.cu against clip_grad_norm_ + torch.optim.AdamW (the reference's Optimizer.step) over five steps."""
+    torch.manual_seed(14)
+    n = 40_008
+    p0 = randn(n) * 0.1
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=2e-3, weight_decay=1e-2, betas=(0.9, 0.99), eps=1e-8)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    shadow = torch.empty(n, dtype=BF16, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(5):
+        g = randn(n) * (10.0 if it % 2 == 0 else 1e-3)           # alternately clipped / not clipped
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 2.0)
+        opt.step()
+        g_sum = g * world                                       # what an all-reduce SUM over `world` ranks would hold
+        norm = torch.linalg.vector_norm(g_sum)
+        step.add_(1)
+        k.adamw_step(p, g_sum, m, v, shadow, norm, step, lr=2e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2, max_norm=2.0,
+                     grad_scale=1.0 / world)
+        assert rel_err(p, ref_p.data) < 2e-6, it
+        assert torch.equal(shadow, p.to(BF16))
+    st = opt.state[ref_p]
+    assert rel_err(m, st["exp_avg"]) < 1e-5 and rel_err(v, st["exp_avg_sq"]) < 1e-5
+
+
 def test_clf_heads(k):
     torch.manual_seed(12)
     n, in_dim = 1500, 64
