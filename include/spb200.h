@@ -98,10 +98,12 @@ int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const fl
                       int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset, spb_stream_t stream);
 
 /* KV-cached incremental decode (one new query per sequence): q bf16 [B, H*64]; kv cache bf16 rows of (k | v); the query sits at
- * position q_pos.  Replaces the cached path of attention.py:155-156 / transformer.py:161-186 without the per-step torch.cat. */
-int spb_attention_decode(const void* q, int ld_q, const void* kv, int ld_kv, long long kv_batch_stride, const uint8_t* key_mask,
+ * position q_pos.  Replaces the cached path of attention.py:155-156 / transformer.py:161-186 without the per-step torch.cat.
+ * pos_dev (optional): device int64 holding q_pos -- n_keys is then the cache capacity, which makes the launch replayable from a
+ * CUDA graph; append_kv: first copy columns [H*64, H*64+128) of every q row (the new k | v) into cache row q_pos. */
+int spb_attention_decode(const void* q, int ld_q, void* kv, int ld_kv, long long kv_batch_stride, const uint8_t* key_mask,
                          int mask_stride, const float* logslopes, void* out, int ld_out, int B, int H, int dim_head, int n_keys,
-                         int q_pos, spb_stream_t stream);
+                         int q_pos, const int64_t* pos_dev, int append_kv, spb_stream_t stream);
 
 /* One level of the hierarchical MMD-VAE style encoder (models/scoreperformer/mmd_transformer.py:304-368):
  * segmented mean over cat(hidden*mask, style[:, :w_style]) -> Linear -> latents_mask -> broadcast back into style[:, col0:col0+z].

@@ -653,11 +653,23 @@ constexpr int DEC_MAX_T = 4096;
 __global__ void attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ kv, int ld_kv,
                                    long long kv_batch_stride, const uint8_t* __restrict__ key_mask, int mask_stride,
                                    const float* __restrict__ logslopes, __nv_bfloat16* __restrict__ out, int ld_out, int n_keys,
-                                   int q_pos, float scale) {
-    extern __shared__ float sp[];                  // [H][n_keys]
+                                   int q_pos, float scale, const long long* __restrict__ pos_dev, int append_kv, int n_heads) {
+    extern __shared__ float sp[];                  // [H][capacity]
     const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* p = sp + (size_t)h * n_keys;
-    const __nv_bfloat16* kvb = kv + (size_t)b * kv_batch_stride;
+    const int cap = n_keys;
+    if (pos_dev != nullptr) {                      // position lives on the device: the launch is replayable from a CUDA graph
+        q_pos = (int)*pos_dev;
+        n_keys = min(cap, q_pos + 1);
+    }
+    float* p = sp + (size_t)h * cap;
+    __nv_bfloat16* kvb = const_cast<__nv_bfloat16*>(kv) + (size_t)b * kv_batch_stride;
+    if (append_kv) {
+        // the new position's (k | v) sit right after the H query heads of this row: append them to the cache first
+        if (threadIdx.x < 16)
+            reinterpret_cast<uint4*>(kvb + (size_t)q_pos * ld_kv)[threadIdx.x] =
+                reinterpret_cast<const uint4*>(q + (size_t)b * ld_q + n_heads * DH)[threadIdx.x];
+        __syncthreads();
+    }
     const float slope = __expf(logslopes[h]);
     float qv[DH];
     {
@@ -700,28 +712,55 @@ __global__ void attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ld_q
     sum = warp_sum(sum);
     __syncwarp();
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < n_keys; ++j) {
-        const float pj = p[j];
-        if (pj == 0.f) continue;
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kvb + (size_t)j * ld_kv + DH + lane * 2));
-        o0 += pj * v.x;
-        o1 += pj * v.y;
+    // P.V: 8 lanes cover the 64 value dims with 16-byte loads, the 4 lane groups walk 4 different keys, two keys per group in
+    // flight; the groups' partial sums meet through shuffles at the end.
+    const int grp = lane >> 3, sub = lane & 7;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    const __nv_bfloat16* vbase = kvb + DH + sub * 8;
+    int j = grp;
+    for (; j + 4 < n_keys; j += 8) {
+        const float p0 = p[j], p1 = p[j + 4];
+        const uint4 u0 = *reinterpret_cast<const uint4*>(vbase + (size_t)j * ld_kv);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(vbase + (size_t)(j + 4) * ld_kv);
+        const float2 a0 = unpack_bf16x2(u0.x), a1 = unpack_bf16x2(u0.y), a2 = unpack_bf16x2(u0.z), a3 = unpack_bf16x2(u0.w);
+        const float2 b0 = unpack_bf16x2(u1.x), b1 = unpack_bf16x2(u1.y), b2 = unpack_bf16x2(u1.z), b3 = unpack_bf16x2(u1.w);
+        o[0] += p0 * a0.x + p1 * b0.x; o[1] += p0 * a0.y + p1 * b0.y; o[2] += p0 * a1.x + p1 * b1.x; o[3] += p0 * a1.y + p1 * b1.y;
+        o[4] += p0 * a2.x + p1 * b2.x; o[5] += p0 * a2.y + p1 * b2.y; o[6] += p0 * a3.x + p1 * b3.x; o[7] += p0 * a3.y + p1 * b3.y;
     }
-    *reinterpret_cast<uint32_t*>(out + (size_t)b * ld_out + h * DH + lane * 2) = pack_bf16x2(o0 * inv, o1 * inv);
+    for (; j < n_keys; j += 4) {
+        const float p0 = p[j];
+        const uint4 u0 = *reinterpret_cast<const uint4*>(vbase + (size_t)j * ld_kv);
+        const float2 a0 = unpack_bf16x2(u0.x), a1 = unpack_bf16x2(u0.y), a2 = unpack_bf16x2(u0.z), a3 = unpack_bf16x2(u0.w);
+        o[0] += p0 * a0.x; o[1] += p0 * a0.y; o[2] += p0 * a1.x; o[3] += p0 * a1.y;
+        o[4] += p0 * a2.x; o[5] += p0 * a2.y; o[6] += p0 * a3.x; o[7] += p0 * a3.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+    }
+    if (grp == 0) {
+        const uint4 r = make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
+                                   pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
+        *reinterpret_cast<uint4*>(out + (size_t)b * ld_out + h * DH + sub * 8) = r;
+    }
 }
 }  // namespace
 
 // q bf16 [B, >= H*64] (row stride ld_q); kv bf16 cache [B][n_keys rows of (k | v) = 128 columns] (row stride ld_kv, batch stride in
 // elements); key_mask [B, mask_stride] or NULL; out bf16 [B, H*64].  The query sits at position q_pos (keys j <= q_pos attend).
-extern "C" int spb_attention_decode(const void* q, int ld_q, const void* kv, int ld_kv, long long kv_batch_stride, const uint8_t* key_mask,
+// pos_dev (optional): device int64 holding q_pos; n_keys is then the cache CAPACITY and keys j <= *pos_dev are used.
+// append_kv: copy columns [H*64, H*64+128) of each q row into cache row q_pos before attending (saves a separate copy).
+extern "C" int spb_attention_decode(const void* q, int ld_q, void* kv, int ld_kv, long long kv_batch_stride, const uint8_t* key_mask,
                                     int mask_stride, const float* logslopes, void* out, int ld_out, int B, int H, int dim_head,
-                                    int n_keys, int q_pos, cudaStream_t stream) {
+                                    int n_keys, int q_pos, const int64_t* pos_dev, int append_kv, cudaStream_t stream) {
     if (B <= 0 || n_keys <= 0) return SPB_OK;
     SPB_CHECK_ARG(q && kv && logslopes && out, "spb_attention_decode: null pointer");
     SPB_CHECK_ARG(dim_head == DH && H >= 1 && H <= 32, "spb_attention_decode: dim_head must be %d, 1..32 heads", DH);
     SPB_CHECK_ARG(n_keys <= DEC_MAX_T, "spb_attention_decode: at most %d cached keys", DEC_MAX_T);
-    SPB_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 2 == 0, "spb_attention_decode: unaligned leading dims");
+    SPB_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0, "spb_attention_decode: leading dims must be multiples of 8");
     const size_t smem = (size_t)H * n_keys * sizeof(float);
     static size_t configured = 48 * 1024;
     if (smem > configured) {
@@ -730,7 +769,8 @@ extern "C" int spb_attention_decode(const void* q, int ld_q, const void* kv, int
     }
     attn_decode_kernel<<<B, 32 * H, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), ld_q, reinterpret_cast<const __nv_bfloat16*>(kv),
                                                    ld_kv, kv_batch_stride, key_mask, mask_stride, logslopes,
-                                                   reinterpret_cast<__nv_bfloat16*>(out), ld_out, n_keys, q_pos, 1.f / sqrtf((float)dim_head));
+                                                   reinterpret_cast<__nv_bfloat16*>(out), ld_out, n_keys, q_pos, 1.f / sqrtf((float)dim_head),
+                                                   reinterpret_cast<const long long*>(pos_dev), append_kv, H);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -48,7 +48,7 @@ struct Ld8<__nv_bfloat16> {
 // ------------------------------------------------------------------------------------------- LayerNorm
 // D = 256 * G.  Lane l owns elements g*256 + l*8 + j (g < G, j < 8).
 template <int G, typename Tin, typename Tout, bool ADA>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, G >= 5 ? 2 : 1)
 ln_fwd_kernel(const Tin* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
               const __nv_bfloat16* __restrict__ gb, int ldgb, Tout* __restrict__ y, int ldy, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int n_rows, float eps) {

@@ -61,22 +61,28 @@ class _StackWeights:
 
 
 def _stack_step(sw: _StackWeights, x_last: Tensor, style_last: Optional[Tensor], kv_caches: Sequence[Tensor], key_mask: Optional[Tensor],
-                pos: int, hid_out: Optional[List[Tensor]] = None) -> Tensor:
+                pos: int, hid_out: Optional[List[Tensor]] = None, pos_dev: Optional[Tensor] = None) -> Tensor:
     """One new position through the stack.  x_last fp32 [B, D]; kv_caches[l] bf16 [B, cap, 128] already holding rows < pos;
-    row `pos` is written here.  Returns the final-norm output fp32 [B, D]."""
+    row `pos` is written here (by the attention kernel itself).  With `pos_dev` (device int64 [1]) the position is only known on
+    the device -- `pos` is ignored and every launch is CUDA-graph replayable.  Returns the final-norm output fp32 [B, D]."""
     gb_all = None
     if sw.ada:
         gb_all = K.gemm(K.cast_bf16(style_last.float().contiguous()), sw.w_ada, bias=sw.b_ada, out_dtype=BF16)
-    rowmask = None if key_mask is None else key_mask[:, pos].contiguous()
+    if key_mask is None:
+        rowmask = None
+    elif pos_dev is None:
+        rowmask = key_mask[:, pos].contiguous()
+    else:
+        rowmask = key_mask.index_select(1, pos_dev).reshape(-1).contiguous()
     cur = x_last
-    hq = sw.H * 64
     for l, w in enumerate(sw.layers):
         if hid_out is not None:
             hid_out.append(cur)
         xn = sw.norm(2 * l, cur, gb_all)
         qkv = K.gemm(xn, w["wqkv"], out_dtype=BF16)
-        kv_caches[l][:, pos].copy_(qkv[:, hq:])
-        o = K.attention_decode(qkv, kv_caches[l], key_mask, w["ls"], sw.H, pos + 1, pos)
+        cap = kv_caches[l].shape[1]
+        o = K.attention_decode(qkv, kv_caches[l], key_mask, w["ls"], sw.H, cap if pos_dev is not None else pos + 1, pos,
+                               pos_dev=pos_dev, append_kv=True)
         cur = K.gemm(o, w["wo"], residual=cur, rowmask=rowmask, out_dtype=F32)
         xn = sw.norm(2 * l + 1, cur, gb_all)
         u = K.gemm(xn, w["w1"], bias=w["b1"], out_dtype=BF16)
@@ -113,7 +119,7 @@ def cached_stack_step(tr, x: Tensor, mask: Optional[Tensor], style: Optional[Ten
 @torch.no_grad()
 def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor, style: Tensor, mask: Optional[Tensor] = None,
                  fields: Sequence[int] = (3, 5, 10, 11), temperature: float = 1.0, top_k: Optional[int] = 1,
-                 generator: Optional[torch.Generator] = None, teacher: Optional[Tensor] = None) -> Tensor:
+                 generator: Optional[torch.Generator] = None, teacher: Optional[Tensor] = None, use_graph: bool = True) -> Tensor:
     """Fill `fields` of every note >= 1 of `perf` [B, T, F], note by note, for all B scores in lockstep.
 
     perf / masked_perf: int64 [B, T, F]; score_hidden fp32 [B, T, D]; style fp32 [B, T, S]; mask bool [B, T].
@@ -121,6 +127,8 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     softmax at `temperature`; `top_k=None` uses the reference default ceil(0.1 * V).
     `teacher` [B, T, F] (optional) is fed as the already-rendered prefix instead of the model's own samples (teacher forcing,
     used by the parity tests to compare every step independently); the returned tensor still holds the model's predictions.
+    `use_graph`: capture one note-step in a CUDA graph and replay it (positions are device-side); sampling with a custom
+    `generator` runs eagerly.
     """
     dec = model.perf_decoder.model
     te_mod, head = dec.token_emb, dec.lm_head
@@ -152,24 +160,31 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     cat_buf = torch.empty((B, 2 * dec.dim), dtype=BF16, device=dev)
     cat2 = torch.empty((B, 2 * dec.dim), dtype=BF16, device=dev)
 
-    for i in range(T - 1):
+    # The position lives on the device: every index below is a device gather / scatter, so ONE captured step replays for
+    # all T-1 notes (`use_graph`), instead of ~50 host launches per note.
+    pos_t = torch.zeros(1, dtype=torch.int64, device=dev)                    # i
+    field_idx = torch.tensor(list(fields), dtype=torch.int64, device=dev)
+    neg_inf = -float("inf")
+
+    def step():
+        nxt = pos_t + 1
         # decoder position i: full tuple of note i, masked tuple / context / style of note i+1 (wrappers.py:409-431)
-        x1, _, _ = K.embed_ln_fwd(feed[:, i].contiguous(), table, sizes, ln_w, ln_b)
-        x2, _, _ = K.embed_ln_fwd(masked_perf[:, i + 1].contiguous(), table, sizes, ln_w, ln_b)
+        x1, _, _ = K.embed_ln_fwd(feed.index_select(1, pos_t).reshape(B, F).contiguous(), table, sizes, ln_w, ln_b)
+        x2, _, _ = K.embed_ln_fwd(masked_perf.index_select(1, nxt).reshape(B, F).contiguous(), table, sizes, ln_w, ln_b)
         K.gemm(x1, wp16, bias=bp, out=cat_buf[:, :dec.dim])
         K.gemm(x2, wp16, bias=bp, out=cat_buf[:, dec.dim:])
         te = K.gemm(cat_buf, wm16, bias=bm, out_dtype=F32)
         K.layer_norm_fwd(te, en_w, en_b, out=cat2[:, :dec.dim], need_stats=False)
-        cat2[:, dec.dim:].copy_(ctx16[:, i + 1])
+        cat2[:, dec.dim:].copy_(ctx16.index_select(1, nxt).reshape(B, -1))
         x = K.gemm(cat2, wc16, bias=bc, out_dtype=F32)
-        hid = _stack_step(sw, x, style[:, i + 1], kv_caches, km, i)
+        hid = _stack_step(sw, x, style.index_select(1, nxt).reshape(B, -1), kv_caches, km, 0, pos_dev=pos_t)
         # tied head for the masked fields only (wrappers.py:364-380)
         e_raw = K.gemm(K.cast_bf16(hid), whead16, trans_b=True, out_dtype=BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)
+        toks = []
         for f in fields:
             lg = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + sizes[f]], out_dtype=F32)
-            lg[:, 0] = -float("inf")
-            lg[:, 1] = -float("inf")
+            lg[:, :2] = neg_inf                                             # PAD / MASK are never emitted
             k = top_k if top_k is not None else -(-sizes[f] // 10)
             if k == 1:
                 tok = lg.argmax(dim=-1)
@@ -177,5 +192,30 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
                 val, ind = torch.topk(lg, k)
                 probs = torch.softmax(val / temperature, dim=-1)
                 tok = ind.gather(1, torch.multinomial(probs, 1, generator=generator)).squeeze(1)
-            out[:, i + 1, f] = tok
+            toks.append(tok)
+        # out[:, i+1, fields] = toks
+        out_rows = out.view(B, T * F)
+        dst = nxt * F + field_idx                                           # [n_fields] flat column indices
+        out_rows.index_copy_(1, dst, torch.stack(toks, dim=1))
+        pos_t.add_(1)
+
+    n_steps = T - 1
+    graph_ok = use_graph and generator is None and n_steps > 4
+    if not graph_ok:
+        for _ in range(n_steps):
+            step()
+        return out
+    # two eager steps warm every lazily-initialised path, then one step is captured and replayed for the rest
+    step()
+    step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    before = K.LAUNCHES
+    with torch.cuda.graph(graph):
+        step()                                   # recorded, not executed
+    per_step = K.LAUNCHES - before
+    K.LAUNCHES = before                          # the recording itself launched nothing ...
+    for _ in range(n_steps - 2):
+        graph.replay()
+    K.LAUNCHES += per_step * (n_steps - 2)       # ... each replay launches every recorded kernel
     return out

@@ -257,14 +257,21 @@ def attention_bwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, ou
     return dqkv
 
 
-def attention_decode(q: Tensor, kv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, H: int, n_keys: int, q_pos: int) -> Tensor:
-    """q bf16 [B, >=H*64]; kv bf16 [B, cap, 128] (k | v); returns bf16 [B, H*64]."""
+def attention_decode(q: Tensor, kv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, H: int, n_keys: int, q_pos: int,
+                     pos_dev: Optional[Tensor] = None, append_kv: bool = False) -> Tensor:
+    """q bf16 [B, >=H*64]; kv bf16 [B, cap, 128] (k | v); returns bf16 [B, H*64].
+
+    With `pos_dev` (device int64 [1]) the position is read on the device and `n_keys` is the cache capacity, so the launch can
+    be replayed from a CUDA graph; `append_kv` first stores q[:, H*64:H*64+128] as cache row q_pos."""
     _require_cuda(q, kv)
     assert q.dtype == BF16 and kv.dtype == BF16 and q.stride(1) == 1 and kv.stride(2) == 1
+    assert pos_dev is None or (pos_dev.dtype == torch.int64 and pos_dev.is_cuda)
+    assert not append_kv or q.shape[1] >= H * 64 + 128
     B = q.shape[0]
     out = torch.empty((B, H * 64), dtype=BF16, device=q.device)
     _call("spb_attention_decode", _p(q), q.stride(0), _p(kv), kv.stride(1), kv.stride(0), _p(key_mask),
-          key_mask.stride(0) if key_mask is not None else 0, _p(logslopes), _p(out), out.stride(0), B, H, 64, n_keys, q_pos, _stream())
+          key_mask.stride(0) if key_mask is not None else 0, _p(logslopes), _p(out), out.stride(0), B, H, 64, n_keys, q_pos,
+          _p(pos_dev), int(append_kv), _stream())
     _count()
     return out
 

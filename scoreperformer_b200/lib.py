@@ -35,7 +35,7 @@ SIGNATURES = {
     "spb_attention_fwd": [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
     "spb_attention_fwd_tc": [_P, _I, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
     "spb_attention_bwd": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
-    "spb_attention_decode": [_P, _I, _P, _I, c_longlong, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "spb_attention_decode": [_P, _I, _P, _I, c_longlong, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "spb_latent_level_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "spb_latent_level_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "spb_mmd_fwd_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
