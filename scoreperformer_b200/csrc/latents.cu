@@ -228,7 +228,15 @@ small_gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restri
     for (int kk = k0; kk < k1; kk += 32) {
         const int kt = min(32, k1 - kk);
         __syncthreads();
-        for (int i = threadIdx.x; i < kt * m; i += 256) sA[i] = A[(size_t)(kk + i / m) * lda + i % m];
+        // A = dlatents: rows of empty / padded segments are exactly zero (most rows in the sync-free [B, T+4] layout), and a
+        // chunk of 32 all-zero rows contributes nothing
+        int live = 0;
+        for (int i = threadIdx.x; i < kt * m; i += 256) {
+            const float a = A[(size_t)(kk + i / m) * lda + i % m];
+            sA[i] = a;
+            live |= (a != 0.f);
+        }
+        if (!__syncthreads_or(live)) continue;
         for (int i = threadIdx.x; i < kt * n; i += 256) sB[i] = Bm[(size_t)(kk + i / n) * ldb + i % n];
         __syncthreads();
 #pragma unroll

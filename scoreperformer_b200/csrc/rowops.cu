@@ -218,6 +218,8 @@ glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ 
 
 // du[n, 2H] from dh[n, H]; dbias[2H] += column sums of du.  Block b walks rows b, b+grid, ...; thread t owns
 // the 4-column groups t, t+256, ... so column sums accumulate in registers (H <= 4096).
+// (8-byte accesses on purpose: the 16-byte / 8-column form needs ~90 registers, drops to 2 blocks per SM and measured
+//  15-40% slower on B200 in two separate attempts -- bytes in flight per SM matter more than bytes per instruction here.)
 template <int MAXG>
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
