@@ -99,6 +99,13 @@ seg_latent_kernel(float* __restrict__ pooled, const int* __restrict__ counts, co
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (slot >= n_slots) return;
     const int cnt = counts[slot];
+    if (cnt == 0 && !force_valid) {
+        // empty slot (most of the [B, T+4] table in the sync-free layout): its pooled row is all zero, so it is invalid
+        // and its latent is zero -- nothing to read or multiply
+        if (lane == 0) lmask[slot] = 0;
+        for (int o = lane; o < z; o += 32) latents[(size_t)slot * z + o] = 0.f;
+        return;
+    }
     const float inv = 1.f / (float)max(cnt, 1);
     float v[DREGS];
     bool all_nz = true;
@@ -164,6 +171,13 @@ seg_latent_bwd_kernel(float* __restrict__ dlat, const float* __restrict__ dlat_d
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (slot >= n_slots) return;
     const bool valid = lmask[slot] != 0;
+    if (!valid) {
+        // invalid slot: its latent gradient is dropped; dpooled is only ever read for slots that own tokens
+        for (int o = lane; o < z; o += 32) dlat[(size_t)slot * z + o] = 0.f;
+        if (counts[slot] > 0)
+            for (int c = lane; c < d_total; c += 32) dpooled[(size_t)slot * MAX_D + c] = 0.f;
+        return;
+    }
     const float inv = 1.f / (float)max(counts[slot], 1);
     float acc[DREGS];
 #pragma unroll
