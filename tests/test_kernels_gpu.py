@@ -61,6 +61,39 @@ def test_gemm_splitk_wgrad(k):
     assert rel_err(out2, 2 * ref) < 1e-4
 
 
+@pytest.mark.parametrize("mode", [{"SPB_GEMM_NCTA": "2"}, {"SPB_GEMM_NCTA": "2", "SPB_GEMM_BN": "256"}, {"SPB_GEMM_EPI": "direct"},
+                                  {"SPB_GEMM_BN": "128"}])
+def test_gemm_alternate_paths(k, mode, monkeypatch):
+    """The opt-in CTA-pair kernel (cta_group::2, 256-row tiles), forced tile widths and the direct (non-TMA) epilogue fallback
+    must agree with the default path on every epilogue variant, including ragged M / N and split-K."""
+    torch.manual_seed(7)
+    cases = [(1000, 384, 256, False, False), (2048, 512, 512, False, True), (515, 256, 1024, False, False)]
+    wg_dy, wg_x = randn(8200, 384, dtype=BF16), randn(8200, 256, dtype=BF16)
+    outs = {}
+    for tag in ("default", "alt"):
+        if tag == "alt":
+            for kk, vv in mode.items():
+                monkeypatch.setenv(kk, vv)
+        res = []
+        for (M, N, K_, ta, tb) in cases:
+            g = torch.Generator(device="cuda").manual_seed(M + N)
+            A = torch.randn(M, K_, device="cuda", generator=g).to(BF16)
+            B = torch.randn(N, K_, device="cuda", generator=g).to(BF16)
+            b = B.t().contiguous() if tb else B
+            bias = torch.randn(N, device="cuda", generator=g)
+            resid = torch.randn(M, N, device="cuda", generator=g)
+            mask = torch.rand(M, device="cuda", generator=g) > 0.3
+            res.append(k.gemm(A, b, trans_b=tb, bias=bias, out_dtype=BF16))
+            res.append(k.gemm(A, b, trans_b=tb, residual=resid, rowmask=mask, out_dtype=F32))
+        res.append(k.gemm(wg_dy, wg_x, trans_a=True, trans_b=True, out_dtype=F32, split_k=0))
+        outs[tag] = res
+    for i, (d, a_) in enumerate(zip(outs["default"], outs["alt"])):
+        tol = 1e-4 if i == len(outs["default"]) - 1 else 0.0      # split-K sums in a different order
+        assert rel_err(a_, d) <= tol, (mode, i)
+    ref = wg_dy.float().t() @ wg_x.float()
+    assert rel_err(outs["alt"][-1], ref) < 1e-4
+
+
 def test_gemm_strided_views(k):
     torch.manual_seed(2)
     big = randn(300, 1536, dtype=BF16)
