@@ -119,26 +119,52 @@ clf_heads_kernel(const float* __restrict__ x, int ldx, const uint8_t* __restrict
                 a0 = spb_keep16(hsh, 0, drop_thresh24 >> 8) ? x0 * keep_scale : 0.f;
                 a1 = spb_keep16(hsh, 1, drop_thresh24 >> 8) ? x1 * keep_scale : 0.f;
             }
-            // lane c (< C) keeps logit c
-            float my_logit = -INFINITY;
-            for (int c = 0; c < C; ++c) {
-                float s = a0 * sW[(off + c) * 64 + lane] + a1 * sW[(off + c) * 64 + lane + 32];
-                s = warp_sum(s) + sB[off + c];
-                if (lane == c) my_logit = s;
+            // All (<= 16) class dot products of the head at once: every lane forms its partial for each class, then a
+            // transposing butterfly (16 shuffles instead of 5 per class) leaves the total of class c in lanes 2c and 2c+1.
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                v[c] = c < C ? a0 * sW[(off + c) * 64 + lane] + a1 * sW[(off + c) * 64 + lane + 32] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool hi = lane & 16;
+                const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool hi = lane & 8;
+                const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool hi = lane & 4;
+                const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+                const bool hi = lane & 2;
+                const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+                v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            const int cls = lane >> 1;                                  // class held by this lane pair
+            const bool owner = (lane & 1) == 0 && cls < C;
+            const float my_logit = owner ? v[0] + sB[off + cls] : -INFINITY;
             const float mx = warp_max(my_logit);
-            const float e = lane < C ? __expf(my_logit - mx) : 0.f;
+            const float e = owner ? __expf(my_logit - mx) : 0.f;
             const float se = warp_sum(e);
             const float lse = mx + __logf(se);
-            const float ly = __shfl_sync(0xffffffffu, my_logit, (int)y);
+            const float ly = __shfl_sync(0xffffffffu, my_logit, 2 * (int)y);
             const float wy = sCW[off + y];
             if (dl == nullptr) {
                 if (lane == 0) {
                     atomicAdd(&s_num[g], wy * (lse - ly));
                     atomicAdd(&s_den[g], wy);
                 }
-            } else if (lane < C) {
-                dl[(size_t)row * hd.total + off + lane] = dlogit_scale[g] * wy * (e / se - (lane == y ? 1.f : 0.f));
+            } else if (owner) {
+                dl[(size_t)row * hd.total + off + cls] = dlogit_scale[g] * wy * (e / se - (cls == y ? 1.f : 0.f));
             }
         }
     }
