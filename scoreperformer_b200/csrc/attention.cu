@@ -436,7 +436,7 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
 }
 
 // dQ and d(logslope): grid (ceil(T/64), H, B); same tiling as the forward.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_do, const float* __restrict__ lse,
                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int ld_dqkv,
                    float* __restrict__ dlogslopes) {
