@@ -332,9 +332,14 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
         load_tile_async(sQ[buf], base, p.ld, qt * TQ, h * DH, T);
         load_tile_async(sDO[buf], dbase, ld_do, qt * TQ, h * DH, T);
         if (threadIdx.x < TQ) {
+            // asynchronous like the tiles (a plain load here parks the warp on the long scoreboard every iteration).  Rows
+            // beyond T are zero-filled: their Q and dO rows are zero too, so P stays finite and dS = dV-contribution = 0.
             const int i = qt * TQ + threadIdx.x;
-            sLse[buf][threadIdx.x] = i < T ? lse[((size_t)b * H + h) * T + i] : INFINITY;   // +inf -> P = 0
-            sDelta[buf][threadIdx.x] = i < T ? delta[((size_t)b * H + h) * T + i] : 0.f;
+            const bool ok = i < T;
+            const size_t src = ((size_t)b * H + h) * T + (ok ? i : 0);
+            const int bytes = ok ? 4 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&sLse[buf][threadIdx.x])), "l"(lse + src), "r"(bytes) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&sDelta[buf][threadIdx.x])), "l"(delta + src), "r"(bytes) : "memory");
         }
     };
 
