@@ -17,6 +17,7 @@ constexpr int DH = 64;
 constexpr int TQ = 64;   // queries per CTA
 constexpr int TK = 64;   // keys per tile
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ATT_MAX_T = 8192;   // key-validity bits of one sequence live in shared memory (32 keys per word)
 
 struct AttnParams {
     const __nv_bfloat16* qkv;
@@ -146,7 +147,7 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
     __shared__ __align__(128) uint8_t sQ[TQ * 128];
     __shared__ __align__(128) uint8_t sK[2][TK * 128];
     __shared__ __align__(128) uint8_t sV[2][TK * 128];
-    __shared__ uint32_t sMaskBits[2][2];
+    __shared__ uint32_t sMaskAll[ATT_MAX_T / 32];    // key validity of the whole sequence, built once
 
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,17 +164,18 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
     auto load_kv = [&](int kt, int buf) {
         load_tile_async(sK[buf], base, p.ld, kt * TK, kcol, T);
         load_tile_async(sV[buf], base, p.ld, kt * TK, vcol, T);
-        if (threadIdx.x < TK) {      // warps 0,1: 64-bit validity mask of the key tile
-            const int j = kt * TK + threadIdx.x;
-            const bool ok = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
-            const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-            if (lane == 0) sMaskBits[buf][warp] = bits;
-        }
     };
 
     load_tile_async(sQ, base, p.ld, q0, h * DH, T);
     load_kv(0, 0);
     cp_async_commit();
+    // key-validity words for every key tile, once per CTA (a per-tile global load would sit on the critical path)
+    for (int w = warp; w * 32 < n_kt * TK; w += 4) {
+        const int j = w * 32 + lane;
+        const bool ok = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) sMaskAll[w] = bits;
+    }
 
     float o_acc[8][4];
 #pragma unroll
@@ -200,22 +202,30 @@ attn_fwd_kernel(AttnParams p, __nv_bfloat16* __restrict__ out, int ld_out, float
         mma_a_tile_nt(s, qf, smem_u32(sK[buf]), lane);
 
         // scores in base-2 units: s*scale2 - slope*|i-j|; the mask / causal tests only run on tiles that need them
-        const uint32_t mlo = sMaskBits[buf][0] >> ((lane & 3) * 2), mhi = sMaskBits[buf][1] >> ((lane & 3) * 2);
+        const uint32_t w0 = sMaskAll[kt * 2], w1 = sMaskAll[kt * 2 + 1];
         const bool diag = p.causal && (kt == qt);
-        const bool simple = !diag && sMaskBits[buf][0] == 0xffffffffu && sMaskBits[buf][1] == 0xffffffffu;
         const float dbase0 = (float)(r_lo - (kt * TK + (lane & 3) * 2));     // i - j for e = 0, nt = 0
+        if (diag || (w0 & w1) != 0xffffffffu) {
+            // only tiles with padded keys or on the causal diagonal pay for masking: masked scores become -inf up front
+            const uint32_t mlo = w0 >> ((lane & 3) * 2), mhi = w1 >> ((lane & 3) * 2);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d = dbase0 + (float)((e >> 1) * 8 - nt * 8 - (e & 1));
+                    const uint32_t word = nt < 4 ? mlo : mhi;
+                    const bool ok = ((word >> ((nt & 3) * 8 + (e & 1))) & 1u) && (!diag || d >= 0.f);
+                    if (!ok) s[nt][e] = -INFINITY;
+                }
+            }
+        }
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float d = dbase0 + (float)((e >> 1) * 8 - nt * 8 - (e & 1));
-                float v = fmaf(-slope, fabsf(d), s[nt][e] * scale2);
-                if (!simple) {
-                    const uint32_t word = nt < 4 ? mlo : mhi;
-                    const bool ok = ((word >> ((nt & 3) * 8 + (e & 1))) & 1u) && (!diag || d >= 0.f);
-                    v = ok ? v : -INFINITY;
-                }
+                const float v = fmaf(-slope, fabsf(d), s[nt][e] * scale2);      // -inf stays -inf
                 s[nt][e] = v;
                 mx[e >> 1] = fmaxf(mx[e >> 1], v);
             }
@@ -361,6 +371,7 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
         const int j = j_lo + r * 8;
         key_ok[r] = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
     }
+    const bool keys_plain = __all_sync(0xffffffffu, key_ok[0] && key_ok[1]);     // no padded key among this warp's 16
 
     for (int it = 0; it < iters; ++it) {
         const int buf = it & 1;
@@ -393,6 +404,17 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
         uint32_t pf[4][4];
         const bool diag = p.causal && (qt == kt);
         const float dbase0 = (float)(qt * TQ + (lane & 3) * 2 - j_lo);       // i - j for e = 0, nt = 0
+        if (diag || !keys_plain) {
+            // masked scores become -inf up front (P = exp2(-inf) = 0), so the main loop carries no mask logic
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d = dbase0 + (float)(nt * 8 + (e & 1) - (e >> 1) * 8);
+                    if (!(key_ok[e >> 1] && (!diag || d >= 0.f))) st[nt][e] = -INFINITY;
+                }
+            }
+        }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             float pd[4];
@@ -401,9 +423,8 @@ attn_bwd_dkv_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float d = dbase0 + (float)(nt * 8 + (e & 1) - (e >> 1) * 8);
-                const bool ok = key_ok[e >> 1] && (!diag || d >= 0.f);
                 const float lse_i = (e & 1) ? lse2.y : lse2.x;
-                float pv = ok ? exp2f(fmaf(-slope, fabsf(d), st[nt][e] * scale2) - lse_i) : 0.f;
+                const float pv = exp2f(fmaf(-slope, fabsf(d), st[nt][e] * scale2) - lse_i);
                 float keep = 1.f;
                 if (drop.on) {
                     const int i = qt * TQ + nt * 8 + (lane & 3) * 2 + (e & 1);
@@ -451,7 +472,7 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
     uint8_t* sDO = sQ + TQ * 128;
     uint8_t (*sK)[TK * 128] = reinterpret_cast<uint8_t (*)[TK * 128]>(sDO + TQ * 128);
     uint8_t (*sV)[TK * 128] = reinterpret_cast<uint8_t (*)[TK * 128]>(sDO + TQ * 128 + 2 * TK * 128);
-    __shared__ uint32_t sMaskBits[2][2];
+    __shared__ uint32_t sMaskAll[ATT_MAX_T / 32];    // key validity of the whole sequence, built once
 
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -469,17 +490,18 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
     auto load_kv = [&](int kt, int buf) {
         load_tile_async(sK[buf], base, p.ld, kt * TK, kcol, T);
         load_tile_async(sV[buf], base, p.ld, kt * TK, vcol, T);
-        if (threadIdx.x < TK) {
-            const int j = kt * TK + threadIdx.x;
-            const bool ok = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
-            const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-            if (lane == 0) sMaskBits[buf][warp] = bits;
-        }
     };
     load_tile_async(sQ, base, p.ld, q0, h * DH, T);
     load_tile_async(sDO, dbase, ld_do, q0, h * DH, T);
     load_kv(0, 0);
     cp_async_commit();
+    // key-validity words for every key tile, once per CTA (a per-tile global load would sit on the critical path)
+    for (int w = warp; w * 32 < n_kt * TK; w += 4) {
+        const int j = w * 32 + lane;
+        const bool ok = (j < T) && (p.key_mask == nullptr || p.key_mask[(size_t)b * T + j]);
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) sMaskAll[w] = bits;
+    }
 
     const int r_lo = q0 + warp * 16 + (lane >> 2);
     float lse_r[2], delta_r[2];
@@ -516,10 +538,23 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
             for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
         mma_a_tile_nt(s, qf, smem_u32(sK[buf]), lane);     // S = Q K^T
         mma_a_tile_nt(dp, dof, smem_u32(sV[buf]), lane);   // dP = dO V^T
-        const uint32_t mlo = sMaskBits[buf][0] >> ((lane & 3) * 2), mhi = sMaskBits[buf][1] >> ((lane & 3) * 2);
+        const uint32_t w0 = sMaskAll[kt * 2], w1 = sMaskAll[kt * 2 + 1];
         const bool diag = p.causal && (kt == qt);
-        const bool simple = !diag && sMaskBits[buf][0] == 0xffffffffu && sMaskBits[buf][1] == 0xffffffffu;
         const float dbase0 = (float)(r_lo - (kt * TK + (lane & 3) * 2));
+        if (diag || (w0 & w1) != 0xffffffffu) {
+            // masked scores become -inf up front (P = exp2(-inf) = 0), so the main loop carries no mask logic
+            const uint32_t mlo = w0 >> ((lane & 3) * 2), mhi = w1 >> ((lane & 3) * 2);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d = dbase0 + (float)((e >> 1) * 8 - nt * 8 - (e & 1));
+                    const uint32_t word = nt < 4 ? mlo : mhi;
+                    const bool ok = ((word >> ((nt & 3) * 8 + (e & 1))) & 1u) && (!diag || d >= 0.f);
+                    if (!ok) s[nt][e] = -INFINITY;
+                }
+            }
+        }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             uint32_t hsh[2] = {0, 0};
@@ -532,12 +567,7 @@ attn_bwd_dq_kernel(AttnParams p, const __nv_bfloat16* __restrict__ dout, int ld_
             for (int e = 0; e < 4; ++e) {
                 const float d = dbase0 + (float)((e >> 1) * 8 - nt * 8 - (e & 1));
                 const float dist = fabsf(d);
-                float pv = exp2f(fmaf(-slope, dist, s[nt][e] * scale2) - lse_r[e >> 1]);
-                if (!simple) {
-                    const uint32_t word = nt < 4 ? mlo : mhi;
-                    const bool ok = ((word >> ((nt & 3) * 8 + (e & 1))) & 1u) && (!diag || d >= 0.f);
-                    pv = ok ? pv : 0.f;
-                }
+                const float pv = exp2f(fmaf(-slope, dist, s[nt][e] * scale2) - lse_r[e >> 1]);
                 float keep = 1.f;
                 if (drop.on) {
                     const uint32_t u16 = (e & 1) ? (hsh[e >> 1] >> 16) : (hsh[e >> 1] & 0xffffu);
@@ -586,6 +616,7 @@ int fill_params(AttnParams& p, const void* qkv, int ld, const uint8_t* key_mask,
     p.rng_offset = rng_offset;
     SPB_CHECK_ARG(qkv && logslopes, "attention: null pointer");
     SPB_CHECK_ARG(dim_head == DH, "attention: dim_head must be %d, got %d", DH, dim_head);
+    SPB_CHECK_ARG(T <= ATT_MAX_T, "attention: at most %d positions per sequence, got %d", ATT_MAX_T, T);
     SPB_CHECK_ARG(ld % 8 == 0 && ld >= H * DH + 2 * DH, "attention: qkv row stride %d too small / unaligned", ld);
     SPB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p must be in [0,1)");
     p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
