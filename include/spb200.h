@@ -47,6 +47,14 @@ int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, in
                   const float* bias, const float* residual, int ldr, const uint8_t* rowmask, int c_fp32, int split_k, int accumulate,
                   const float* alpha, spb_stream_t stream);
 
+/* spb_gemm_bf16 with a bf16 C (no residual / split-K) whose epilogue also emits the per-head row dots
+ *   rowdot_out[(b*H + h)*T + t] = sum_{c in head h} C[b*T + t, c] * X[b*T + t, c]     (N == H*64, X bf16 [M, ld_x])
+ * = attention backward's delta = rowsum(dO * O), produced while dO = dY Wo is written (then call spb_attention_bwd with
+ * delta_ready = 1). */
+int spb_gemm_bf16_rowdot(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda, int ldb, int ldc,
+                         const float* bias, const uint8_t* rowmask, const float* alpha, const void* X, int ld_x, float* rowdot_out, int T,
+                         int H, spb_stream_t stream);
+
 /* LayerNorm / AdaptiveLayerNorm over the last dim (256, 512, 1280 or 1536); pass (w,b) or gb = [gamma | beta] bf16 [n, 2*dim].
  * Replaces nn.LayerNorm and modules/layers.py:31-47. */
 int spb_layer_norm_fwd(const void* x, int x_fp32, int ldx, const float* w, const float* b, const void* gb, int ldgb, void* y, int y_fp32,
@@ -95,7 +103,8 @@ int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_mask, uint3
 /* dqkv bf16 [B*T, ld_dqkv] in the qkv column layout; delta fp32 [B,H,T] scratch; dlogslopes fp32 [H] ACCUMULATED. */
 int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out, const void* dout,
                       int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv, float* dlogslopes, int B, int T, int H,
-                      int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset, spb_stream_t stream);
+                      int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset, int delta_ready,
+                      spb_stream_t stream);
 
 /* KV-cached incremental decode (one new query per sequence): q bf16 [B, H*64]; kv cache bf16 rows of (k | v); the query sits at
  * position q_pos.  Replaces the cached path of attention.py:155-156 / transformer.py:161-186 without the per-step torch.cat.

@@ -653,16 +653,18 @@ extern "C" int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mas
 extern "C" int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out,
                                  const void* dout, int ld_out, const float* lse, float* delta, void* dqkv, int ld_dqkv,
                                  float* dlogslopes, int B, int T, int H, int dim_head, int causal, float dropout_p,
-                                 uint64_t seed, const uint64_t* rng_offset, cudaStream_t stream) {
+                                 uint64_t seed, const uint64_t* rng_offset, int delta_ready, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return SPB_OK;
     AttnParams p;
     int rc = fill_params(p, qkv, ld, key_mask, logslopes, B, T, H, dim_head, causal, dropout_p, seed, rng_offset);
     if (rc != SPB_OK) return rc;
     SPB_CHECK_ARG(out && dout && lse && delta && dqkv, "spb_attention_bwd: null pointer");
-    const int n_warps = B * T * H;
-    attn_delta_kernel<<<ceil_div((int64_t)n_warps * 32, 256), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
-    SPB_CHECK_LAUNCH();
+    if (!delta_ready) {      // delta = rowsum(dO * O); the out-projection dgrad GEMM can emit it instead (spb_gemm_bf16_rowdot)
+        const int n_warps = B * T * H;
+        attn_delta_kernel<<<ceil_div((int64_t)n_warps * 32, 256), 256, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), ld_out, delta, B, T, H);
+        SPB_CHECK_LAUNCH();
+    }
     constexpr int BWD_SMEM = 6 * 64 * 128;
     static bool configured = false;
     if (!configured) {

@@ -44,6 +44,8 @@ struct GemmParams {
     int ldr;
     const uint8_t* rowmask;  // [M] (bool) or null
     const float* alpha;      // device scalar multiplying the accumulator, or null
+    float* rowdot_out;       // optional: out[(b*H + h)*T + t] = sum over the 64 columns of head h of C[m, :] * X[m, :] (m = b*T + t)
+    int rd_T, rd_H;
     int tma_epi;             // 1: C (and the residual) go through TMA boxes; 0: direct vector stores
 };
 
@@ -106,7 +108,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int a = 0; a < 2 * EPI_WARPS; ++a) mbar_init(&res_bar[a], 1);
         if (p.tma_epi) {
             tma_prefetch_desc(&tmC);
-            if (p.residual != nullptr) tma_prefetch_desc(&tmR);
+            if (p.residual != nullptr || p.rowdot_out != nullptr) tma_prefetch_desc(&tmR);
         }
         fence_mbar_init();
     }
@@ -278,7 +280,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t my = stage_a + (uint32_t)(ubuf * 4096 + lane * 128);
                     if (lane == 0) bulk_wait_group_read<1>();          // the store that last used this box has read it
                     __syncwarp();
-                    if (p.residual != nullptr && lane == 0) {
+                    if ((p.residual != nullptr || p.rowdot_out != nullptr) && lane == 0) {
+                        // auxiliary input tile of this unit (fp32 residual, or the bf16 X of the fused row dot) -> the box
                         mbar_arrive_expect_tx(&rbar[ubuf], 4096);
                         tma_load_2d(st, &tmR, &rbar[ubuf], col0, row_base);
                     }
@@ -322,6 +325,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             __syncwarp();
                             if (lane == 0) release_acc(acc);
                         }
+                        if (p.rowdot_out != nullptr) {
+                            mbar_wait(&rbar[ubuf], (rphase >> ubuf) & 1u);
+                            rphase ^= 1u << ubuf;
+                        }
+                        float dot = 0.f;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
@@ -329,13 +337,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 b0 = lds_f4(bias_a + (uint32_t)((u * 64 + 8 * j) * 4));
                                 b1 = lds_f4(bias_a + (uint32_t)((u * 64 + 8 * j + 4) * 4));
                             }
+                            float x[8];
+                            x[0] = fmaf(__uint_as_float(v[8 * j]), alpha, b0.x); x[1] = fmaf(__uint_as_float(v[8 * j + 1]), alpha, b0.y);
+                            x[2] = fmaf(__uint_as_float(v[8 * j + 2]), alpha, b0.z); x[3] = fmaf(__uint_as_float(v[8 * j + 3]), alpha, b0.w);
+                            x[4] = fmaf(__uint_as_float(v[8 * j + 4]), alpha, b1.x); x[5] = fmaf(__uint_as_float(v[8 * j + 5]), alpha, b1.y);
+                            x[6] = fmaf(__uint_as_float(v[8 * j + 6]), alpha, b1.z); x[7] = fmaf(__uint_as_float(v[8 * j + 7]), alpha, b1.w);
+                            const uint32_t slot = my + (((uint32_t)j ^ sw) << 4);
+                            if (p.rowdot_out != nullptr) {
+                                // fused row dot (attention backward's delta = rowsum(dO * O)): X tile sits in the box we overwrite
+                                const uint4 xr = lds_u4(slot);
+                                const float2 a0 = unpack_bf16x2(xr.x), a1 = unpack_bf16x2(xr.y), a2 = unpack_bf16x2(xr.z), a3 = unpack_bf16x2(xr.w);
+                                dot += x[0] * a0.x + x[1] * a0.y + x[2] * a1.x + x[3] * a1.y + x[4] * a2.x + x[5] * a2.y + x[6] * a3.x + x[7] * a3.y;
+                            }
                             uint4 o;
-                            o.x = pack_bf16x2(fmaf(__uint_as_float(v[8 * j]), alpha, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), alpha, b0.y));
-                            o.y = pack_bf16x2(fmaf(__uint_as_float(v[8 * j + 2]), alpha, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), alpha, b0.w));
-                            o.z = pack_bf16x2(fmaf(__uint_as_float(v[8 * j + 4]), alpha, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), alpha, b1.y));
-                            o.w = pack_bf16x2(fmaf(__uint_as_float(v[8 * j + 6]), alpha, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), alpha, b1.w));
+                            o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+                            o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
                             if (!keep) o = make_uint4(0u, 0u, 0u, 0u);
-                            sts_u4(my + (((uint32_t)j ^ sw) << 4), o);
+                            sts_u4(slot, o);
+                        }
+                        if (p.rowdot_out != nullptr && row < p.M) {
+                            const int bb = row / p.rd_T, tt = row - bb * p.rd_T;
+                            p.rowdot_out[((size_t)bb * p.rd_H + (col0 >> 6)) * p.rd_T + tt] = keep ? dot : 0.f;
                         }
                     }
                     fence_proxy_async();
@@ -574,10 +596,9 @@ int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint6
     return SPB_OK;
 }
 
-// C-ABI entry point; see include/spb200.h for the contract.
-extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
-                             int ldb, int ldc, const float* bias, const float* residual, int ldr, const uint8_t* rowmask,
-                             int c_fp32, int split_k, int accumulate, const float* alpha, cudaStream_t stream) {
+static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda, int ldb, int ldc,
+                     const float* bias, const float* residual, int ldr, const uint8_t* rowmask, int c_fp32, int split_k, int accumulate,
+                     const float* alpha, const void* rowdot_x, int ld_x, float* rowdot_out, int rd_T, int rd_H, cudaStream_t stream) {
     SPB_CHECK_ARG(A && B && C, "spb_gemm_bf16: null operand");
     SPB_CHECK_ARG(M > 0 && N > 0 && K > 0, "spb_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
     SPB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "spb_gemm_bf16: lda=%d / ldb=%d must be multiples of 8 (TMA 16 B rule)", lda,
@@ -618,6 +639,13 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
     int tma_epi = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ((size_t)ldc * esize) % 16 == 0) ? 1 : 0;
     if (residual != nullptr && !(c_fp32 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ((size_t)ldr * 4) % 16 == 0)) tma_epi = 0;
     if (const char* e = getenv("SPB_GEMM_EPI")) { if (e[0] == 'd') tma_epi = 0; }
+    if (rowdot_out != nullptr) {
+        SPB_CHECK_ARG(rowdot_x != nullptr && !c_fp32 && residual == nullptr && split_k <= 1 && !accumulate,
+                      "spb_gemm_bf16_rowdot: needs a bf16 C without residual / split-K");
+        SPB_CHECK_ARG(rd_T > 0 && rd_H > 0 && N == rd_H * 64 && M % rd_T == 0, "spb_gemm_bf16_rowdot: N must be H*64 and M a multiple of T");
+        SPB_CHECK_ARG((reinterpret_cast<uintptr_t>(rowdot_x) & 15) == 0 && ld_x % 8 == 0, "spb_gemm_bf16_rowdot: X must be 16-byte aligned");
+        SPB_CHECK_ARG(tma_epi, "spb_gemm_bf16_rowdot: C must satisfy the TMA alignment rules (16-byte base and row pitch)");
+    }
     CUtensorMap tmC, tmR;
     memset(&tmC, 0, sizeof(tmC));
     memset(&tmR, 0, sizeof(tmR));
@@ -627,6 +655,9 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
         if (rc != SPB_OK) return rc;
         if (residual != nullptr) {
             rc = spb_make_tmap_f32_2d(&tmR, residual, (uint64_t)N, (uint64_t)M, (uint64_t)ldr * 4, 32, 32);
+            if (rc != SPB_OK) return rc;
+        } else if (rowdot_out != nullptr) {
+            rc = spb_make_tmap_bf16_2d(&tmR, rowdot_x, (uint64_t)N, (uint64_t)M, (uint64_t)ld_x * 2, 64, 32);
             if (rc != SPB_OK) return rc;
         }
     }
@@ -638,6 +669,7 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
     p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
     p.atomic = (splits > 1 || accumulate) ? 1 : 0;
     p.tma_epi = tma_epi;
+    p.rowdot_out = rowdot_out; p.rd_T = rd_T; p.rd_H = rd_H;
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.rowmask = rowmask; p.alpha = alpha;
 
     if (splits > 1 && !accumulate) {
@@ -658,4 +690,23 @@ extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
     if (BN == 256) { SPB_DISPATCH(256, 1) }
     SPB_DISPATCH(128, 1)
 #undef SPB_DISPATCH
+}
+
+// C-ABI entry points; see include/spb200.h for the contracts.
+extern "C" int spb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
+                             int ldb, int ldc, const float* bias, const float* residual, int ldr, const uint8_t* rowmask,
+                             int c_fp32, int split_k, int accumulate, const float* alpha, cudaStream_t stream) {
+    return gemm_impl(A, B, C, M, N, K, trans_a, trans_b, lda, ldb, ldc, bias, residual, ldr, rowmask, c_fp32, split_k, accumulate, alpha,
+                     nullptr, 0, nullptr, 0, 0, stream);
+}
+
+// Same GEMM (bf16 C, no residual / split-K) whose epilogue also emits the per-head row dots
+//   rowdot_out[(b*H + h)*T + t] = sum_{c in head h} C[b*T + t, c] * X[b*T + t, c]        (N == H*64)
+// i.e. attention backward's delta = rowsum(dO * O) while dO = dY Wo is being produced (attend.py backward, flash form).
+extern "C" int spb_gemm_bf16_rowdot(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda,
+                                    int ldb, int ldc, const float* bias, const uint8_t* rowmask, const float* alpha, const void* X,
+                                    int ld_x, float* rowdot_out, int T, int H, cudaStream_t stream) {
+    SPB_CHECK_ARG(X && rowdot_out, "spb_gemm_bf16_rowdot: null X / rowdot_out");
+    return gemm_impl(A, B, C, M, N, K, trans_a, trans_b, lda, ldb, ldc, bias, nullptr, 0, rowmask, 0, 1, 0, alpha, X, ld_x, rowdot_out, T,
+                     H, stream);
 }

@@ -434,10 +434,11 @@ class TransformerStackFn(torch.autograd.Function):
             # ---- attention backward:  x_out = x + mask * Wo attn(Wqkv LN(x))
             p_q, p_k, p_v, p_o, p_ls = params[base + 2:base + 7]
             grads[base + 5] = wgrad(p_o, g16, rec_a["o"])
-            do = K.gemm(g16, rec_a["wo16"], trans_b=True, out_dtype=BF16)
+            # dO = dY Wo and delta = rowsum(dO * O) in one GEMM (the epilogue owns whole rows of a head)
+            do, delta = K.gemm_rowdot(g16, rec_a["wo16"], rec_a["o"], T, H, trans_b=True)
             dls, d_ls = take(p_ls)
             dqkv = K.attention_bwd(rec_a["qkv"], mask, rec_a["ls"], rec_a["o"], do, rec_a["lse"], dls, B, T, H, spec.causal, p_attn,
-                                   ctx.seeds[2 * l])
+                                   ctx.seeds[2 * l], delta=delta)
             grads[base + 6] = None if d_ls else dls.view(p_ls.shape)
             g_qkv = direct_grad_cat([p_q, p_k, p_v])
             if g_qkv is not None:

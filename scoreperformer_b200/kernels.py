@@ -247,14 +247,37 @@ def attention_fwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, B:
 
 
 def attention_bwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, out: Tensor, dout: Tensor, lse: Tensor,
-                  dlogslopes: Tensor, B: int, T: int, H: int, causal: bool, dropout_p: float, seed: int) -> Tensor:
+                  dlogslopes: Tensor, B: int, T: int, H: int, causal: bool, dropout_p: float, seed: int,
+                  delta: Optional[Tensor] = None) -> Tensor:
+    """`delta` fp32 [B, H, T] = rowsum(dO * O) may be supplied (gemm_rowdot produces it with dO); otherwise it is computed here."""
     assert dout.dtype == BF16 and dout.stride(1) == 1 and dout.stride(0) == out.stride(0)
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+    ready = delta is not None
+    if delta is None:
+        delta = torch.empty((B, H, T), dtype=F32, device=qkv.device)
+    assert delta.dtype == F32 and delta.numel() == B * H * T and delta.is_contiguous()
     _call("spb_attention_bwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), _p(dout), out.stride(0), _p(lse), _p(delta),
-          _p(dqkv), dqkv.stride(0), _p(dlogslopes), B, T, H, 64, int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
-    _count(3)
+          _p(dqkv), dqkv.stride(0), _p(dlogslopes), B, T, H, 64, int(causal), float(dropout_p), seed, _p(RNG_OFFSET), int(ready),
+          _stream())
+    _count(2 if ready else 3)
     return dqkv
+
+
+def gemm_rowdot(a: Tensor, b: Tensor, x: Tensor, T: int, H: int, *, trans_b: bool = False, bias: Optional[Tensor] = None,
+                rowmask: Optional[Tensor] = None, alpha: Optional[Tensor] = None):
+    """C = A op(B)^T as bf16 [M, H*64] plus delta[b, h, t] = sum over head h's 64 columns of C[b*T+t, :] * x[b*T+t, :].
+    Returns (C, delta fp32 [M/T, H, T])."""
+    _require_cuda(a, b, x)
+    assert a.dtype == BF16 and b.dtype == BF16 and x.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1 and x.stride(1) == 1
+    M, Kd = a.shape
+    N = b.shape[1] if trans_b else b.shape[0]
+    assert N == H * 64 and M % T == 0 and x.shape == (M, N)
+    out = torch.empty((M, N), dtype=BF16, device=a.device)
+    delta = torch.empty((M // T, H, T), dtype=F32, device=a.device)
+    _call("spb_gemm_bf16_rowdot", _p(a), _p(b), _p(out), M, N, Kd, 0, int(trans_b), a.stride(0), b.stride(0), out.stride(0), _p(bias),
+          _p(rowmask), _p(alpha), _p(x), x.stride(0), _p(delta), T, H, _stream())
+    _count()
+    return out, delta
 
 
 def attention_decode(q: Tensor, kv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, H: int, n_keys: int, q_pos: int,

@@ -94,6 +94,19 @@ def test_gemm_alternate_paths(k, mode, monkeypatch):
     assert rel_err(outs["alt"][-1], ref) < 1e-4
 
 
+@pytest.mark.parametrize("B,T", [(3, 130), (2, 512)])
+def test_gemm_rowdot_delta(k, B, T):
+    """dO = dY Wo with the attention-backward delta = rowsum(dO * O) per head emitted by the same epilogue."""
+    torch.manual_seed(8)
+    H = 4
+    dy, wo, o = randn(B * T, 256, dtype=BF16), randn(256, 256, dtype=BF16) * 0.1, randn(B * T, 256, dtype=BF16)
+    do, delta = k.gemm_rowdot(dy, wo, o, T, H, trans_b=True)
+    ref_do = dy.float() @ wo.float()
+    assert torch.equal(do, k.gemm(dy, wo, trans_b=True, out_dtype=BF16))          # same values as the plain GEMM
+    ref_delta = (ref_do * o.float()).view(B, T, H, 64).sum(-1).permute(0, 2, 1)
+    assert delta.shape == (B, H, T) and rel_err(delta, ref_delta) < 2e-3
+
+
 def test_gemm_strided_views(k):
     torch.manual_seed(2)
     big = randn(300, 1536, dtype=BF16)
