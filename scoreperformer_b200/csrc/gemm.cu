@@ -617,9 +617,11 @@ static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K,
     int splits = 1;
     if (split_k > 1) splits = split_k;
     else if (split_k == 0 && c_fp32 && bias == nullptr && residual == nullptr && rowmask == nullptr) {
-        // auto split-K for tall-K / small-output problems (wgrad): aim at ~2 CTAs per SM
+        // auto split-K for tall-K / small-output problems (wgrad)
         const int tiles = ceil_div(M, BM * ncta) * ceil_div(N, BN);
-        const int units = spb_num_sms() / ncta, target = 2 * units;
+        int mult = 1;      // one work item per SM measured best (fewer partial tiles to reduce-add into the same lines)
+        if (const char* e = getenv("SPB_GEMM_SPLIT_MULT")) { int v = atoi(e); if (v >= 1 && v <= 8) mult = v; }
+        const int units = spb_num_sms() / ncta, target = mult * units;
         if (tiles < units && total_kb >= 8) splits = max(1, min(total_kb / 4, target / tiles));
     }
     int kb_per_split = ceil_div(total_kb, splits);
