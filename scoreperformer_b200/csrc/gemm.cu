@@ -61,6 +61,31 @@ constexpr int gemm_smem_bytes() {
     return gemm_stages<BN, NCTA>() * (A_STAGE_BYTES + BN / NCTA * BK * 2) + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 
+// Tile walk of one role: t = t0, t0 + step, ... decoded as (split, m-tile, n-tile) with n fastest.  The coordinates advance by
+// carries instead of a division / modulo per tile (an integer division is ~40 instructions on the epilogue's critical path).
+struct TileWalk {
+    int split, m, n;
+    int step_split, step_m, step_n, tiles_m, tiles_n;
+    __device__ __forceinline__ TileWalk(int t0, int step, int tiles_m_, int tiles_n_) : tiles_m(tiles_m_), tiles_n(tiles_n_) {
+        const int tiles_mn = tiles_m_ * tiles_n_;
+        split = t0 / tiles_mn;
+        int rem = t0 - split * tiles_mn;
+        m = rem / tiles_n_;
+        n = rem - m * tiles_n_;
+        step_split = step / tiles_mn;
+        rem = step - step_split * tiles_mn;
+        step_m = rem / tiles_n_;
+        step_n = rem - step_m * tiles_n_;
+    }
+    __device__ __forceinline__ void advance() {
+        n += step_n;
+        m += step_m;
+        split += step_split;
+        if (n >= tiles_n) { n -= tiles_n; ++m; }
+        if (m >= tiles_m) { m -= tiles_m; ++split; }
+    }
+};
+
 // Persistent, warp-specialised GEMM: one CTA per SM walks the tile list (n fastest, so co-running CTAs share the A panel in
 // L2).  The TMA producer and the MMA issuer run ahead across tile boundaries; the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -126,9 +151,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            for (int t = tile0; t < total_tiles; t += tile_step) {
-                const int split = t / tiles_mn, rem = t % tiles_mn;
-                const int m0 = (rem / tiles_n) * BM_TILE + rank * BM, n0 = (rem % tiles_n) * BN + rank * BN_CTA;
+            TileWalk tw(tile0, tile_step, tiles_m, tiles_n);
+            for (int t = tile0; t < total_tiles; t += tile_step, tw.advance()) {
+                const int split = tw.split;
+                const int m0 = tw.m * BM_TILE + rank * BM, n0 = tw.n * BN + rank * BN_CTA;
                 const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[s], phase ^ 1);
@@ -179,8 +205,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
             int s = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int t = tile0; t < total_tiles; t += tile_step) {
-                const int split = t / tiles_mn;
+            TileWalk tw(tile0, tile_step, tiles_m, tiles_n);
+            for (int t = tile0; t < total_tiles; t += tile_step, tw.advance()) {
+                const int split = tw.split;
                 const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);       // epilogue (of both CTAs) has drained this accumulator buffer
                 tc_fence_after();
@@ -240,18 +267,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t acc_phase = 0;
             // the bias row of a tile is fetched one tile ahead (registers), so its global latency hides behind the previous tile
             float bias_next[BIAS_PER_LANE];
-            auto fetch_bias = [&](int t) {
-                const int n0 = ((t % tiles_mn) % tiles_n) * BN;
+            auto fetch_bias = [&](int t, int n_tile) {
+                const int n0 = n_tile * BN;
 #pragma unroll
                 for (int i = 0; i < BIAS_PER_LANE; ++i) {
                     const int c = n0 + i * 32 + lane;
                     bias_next[i] = (p.bias != nullptr && t < total_tiles && c < p.N) ? __ldg(p.bias + c) : 0.f;
                 }
             };
-            fetch_bias(tile0);
+            TileWalk tw(tile0, tile_step, tiles_m, tiles_n);
+            fetch_bias(tile0, tw.n);
             for (int t = tile0; t < total_tiles; t += tile_step) {
-                const int rem = t % tiles_mn;
-                const int m0 = (rem / tiles_n) * BM_TILE + rank * BM, n0 = (rem % tiles_n) * BN;
+                const int m0 = tw.m * BM_TILE + rank * BM, n0 = tw.n * BN;
+                tw.advance();                        // tw now describes the NEXT tile of this CTA (bias prefetch below)
                 const int row_base = m0 + q * 32;
                 const int row = row_base + lane;
                 if (p.bias != nullptr) {
@@ -264,7 +292,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
-                if (p.bias != nullptr) fetch_bias(t + tile_step);
+                if (p.bias != nullptr) fetch_bias(t + tile_step, tw.n);
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
                 if (last_u < 0 || row_base >= p.M) {
                     // nothing of this tile belongs to this warp: hand the accumulator back at once
@@ -392,7 +420,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = tile0; t < total_tiles; t += tile_step) {
-                const int rem = t % tiles_mn;
+                const int rem = t % tiles_mn;      // (fallback path: keeps the plain decode)
                 const int m0 = (rem / tiles_n) * BM_TILE + rank * BM, n0 = (rem % tiles_n) * BN;
                 const int row_base = m0 + q * 32;
                 mbar_wait(&acc_full[acc], acc_phase);
