@@ -65,6 +65,8 @@ class TrainStep:
         self.static_losses: Optional[Dict[str, Tensor]] = None
         self.launches_per_step = 0
         self._warm = 0
+        self._copy_stream = None
+        self._stage: Optional[Dict[str, Tensor]] = None
 
     # ------------------------------------------------------------------ pieces
     def _forward_backward(self, batch: Dict[str, Tensor]):
@@ -88,6 +90,42 @@ class TrainStep:
         K.adamw_step(self.flat_param, self.flat_grad, self.flat_m, self.flat_v, None, norm, self.opt_step, lr=self.lr,
                      betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, max_norm=self.grad_clip or 0.0,
                      grad_scale=1.0 / self.world)
+
+    # ------------------------------------------------------------------ input pipeline (host batches)
+    def prefetch(self, batch: Dict[str, Tensor]) -> None:
+        """Start copying the NEXT step's (pinned) host batch to the device on a side stream, so the transfer overlaps the step
+        that is currently running.  Consume it with `step_prefetched()`."""
+        dev = self.flat_grad.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copied = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        if self._stage is None or any(self._stage[k].shape != v.shape for k, v in batch.items()):
+            self._stage = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+        self._copy_stream.wait_event(self._stage_free)           # the previous step has taken its copy out of the stage
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in batch.items():
+                self._stage[k].copy_(v, non_blocking=True)
+            self._copied.record()
+
+    def step_prefetched(self) -> Tensor:
+        """One training step on the batch handed to the last `prefetch()` call."""
+        assert self._stage is not None, "call prefetch(batch) first"
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copied)
+        if not self.use_graph or self._warm < 3 or self.graph is None:
+            batch = {k: v.clone() for k, v in self._stage.items()}
+            self._stage_free.record()
+            return self.step(batch)
+        for k, v in self._stage.items():
+            self.static_batch[k].copy_(v, non_blocking=True)      # device-to-device, ~10 us
+        self._stage_free.record()
+        self.graph.replay()
+        if self.world > 1:
+            self._update()
+        self.losses = self.static_losses
+        return self.static_loss
 
     def set_lr(self, lr: float):
         """ExponentialLR etc. (experiments/optimizers.py:121-149): the rate is baked into a captured graph, so re-capture."""

@@ -91,3 +91,28 @@ def test_train_step_graph_matches_eager_and_redraws_dropout():
     ts = TrainStep(m, lr=0.0, use_graph=True)     # lr 0: only the dropout masks / prior samples change between replays
     vals = [float(ts.losses["Velocity"]) for _ in range(6) if ts.step(batch) is not None]
     assert len(set(round(v, 6) for v in vals[3:])) == 3, f"graph replays must redraw dropout masks, got {vals}"
+
+
+def test_prefetched_host_batches_feed_the_same_steps():
+    """`prefetch()` + `step_prefetched()` (pinned host batch copied on a side stream, overlapping the running step) trains on
+    exactly the batches it was given: with dropouts off and lr 0 the per-batch losses equal those of plain `step()`."""
+    from scoreperformer_b200.train_step import TrainStep
+    torch.manual_seed(0)
+    m = parity.build_model(dropout=False, device="cuda")
+    m.train()
+    m.perf_encoder.exact_latent_shapes = False
+    ts = TrainStep(m, lr=0.0, use_graph=True)
+    host = [{k: v.pin_memory() for k, v in parity.make_batch(2, 64, seed=s).items()} for s in (5, 6, 7)]
+    dev = [{k: v.cuda() for k, v in b.items()} for b in host]
+    want = []
+    for i in range(9):                                   # warm-ups, capture, replays; round-robin over three batches
+        want.append(float(ts.losses["Velocity"]) if ts.step(dev[i % 3]) is not None else None)
+    got = []
+    ts.prefetch(host[0])
+    for i in range(9):
+        loss = ts.step_prefetched()
+        ts.prefetch(host[(i + 1) % 3])                   # next batch's copy overlaps this step
+        assert loss is not None
+        got.append(float(ts.losses["Velocity"]))
+    for i in range(9):
+        assert abs(got[i] - want[i % 3 + 6]) < 1e-4 * abs(got[i]), (i, got, want)
