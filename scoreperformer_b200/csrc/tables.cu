@@ -39,14 +39,20 @@ __device__ __forceinline__ float mish_grad(float x) {
     return t + x * (1.f - t * t) * sig;
 }
 
-// grid (row blocks, F), 128 threads = the E output columns; 8 rows per CTA iteration share W1 through shared memory.
+// grid (row blocks, F), 128 threads = the E output columns; 8 rows per CTA iteration.  W1 is staged once per CTA in shared
+// memory with a padded row stride (thread c walks row c: a stride of E floats would be a 32-way bank conflict, and reading it
+// straight from global memory touches 32 different lines per warp load -- that was 65 us per launch).
+constexpr int FWD_W1_STRIDE = E + 1;
 __global__ void __launch_bounds__(E)
 table_fwd_kernel(TableFields tf, float* __restrict__ table) {
+    extern __shared__ float s_w1p[];                // [E][E + 1]
     __shared__ float sh[8][E];
     const int f = blockIdx.y, c = threadIdx.x;
     const int V = tf.size[f];
+    if ((int)blockIdx.x * 8 >= V) return;
     const float w0 = tf.w0[f][c], b0 = tf.b0[f][c], b1 = tf.b1[f][c];
-    const float* __restrict__ w1 = tf.w1[f];
+    for (int i = c; i < E * E; i += E) s_w1p[(i / E) * FWD_W1_STRIDE + (i % E)] = tf.w1[f][i];      // coalesced read
+    const float* __restrict__ w1 = s_w1p + c * FWD_W1_STRIDE;
     for (int r0 = blockIdx.x * 8; r0 < V; r0 += gridDim.x * 8) {
         __syncthreads();
 #pragma unroll
@@ -59,7 +65,7 @@ table_fwd_kernel(TableFields tf, float* __restrict__ table) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = b1;
         for (int j = 0; j < E; ++j) {
-            const float w = w1[(size_t)c * E + j];
+            const float w = w1[j];
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, sh[k][j], acc[k]);
         }
@@ -160,7 +166,13 @@ extern "C" int spb_table_build_fwd(const int* field_sizes, int n_fields, const v
     int rc = fill(tf, field_sizes, n_fields, ptrs, 7, false);
     if (rc != SPB_OK) return rc;
     SPB_CHECK_ARG(table != nullptr, "spb_table_build_fwd: null output");
-    table_fwd_kernel<<<dim3(8, n_fields), E, 0, stream>>>(tf, table);
+    constexpr int FWD_SMEM = E * FWD_W1_STRIDE * 4;
+    static bool fwd_configured = false;
+    if (!fwd_configured) {
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(table_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+        fwd_configured = true;
+    }
+    table_fwd_kernel<<<dim3(8, n_fields), E, FWD_SMEM, stream>>>(tf, table);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
