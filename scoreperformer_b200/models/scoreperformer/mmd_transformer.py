@@ -15,7 +15,7 @@ from torch import Tensor
 
 from ... import fused
 from ...modules.transformer import TransformerConfig
-from ...utils import ExplicitEnum
+from ...utils import ExplicitEnum, SideBranch
 from .embeddings import TupleTokenEmbeddingsConfig
 from .transformer import TupleTransformer, TupleTransformerConfig, TupleTransformerOutput
 
@@ -178,7 +178,8 @@ class MMDTupleTransformer(TupleTransformer):
     def forward(self, x: Tensor, mask: Optional[Tensor] = None, x_extra=None, latents=None, bars: Optional[Tensor] = None,
                 beats: Optional[Tensor] = None, onsets: Optional[Tensor] = None, deadpan_mask: Optional[Tensor] = None,
                 return_embeddings: bool = False, return_attn: bool = False, compute_loss: bool = True,
-                z_prior: Optional[List[Tensor]] = None, table_cache: Optional[dict] = None, **kwargs):
+                z_prior: Optional[List[Tensor]] = None, table_cache: Optional[dict] = None, side_branch: Optional[SideBranch] = None,
+                **kwargs):
         if latents is not None or not self._fused_supported() or self._mask_bars:
             raise NotImplementedError(
                 "scoreperformer_b200.MMDTupleTransformer: the sm_100a path implements hierarchical-with-context levels over "
@@ -207,6 +208,7 @@ class MMDTupleTransformer(TupleTransformer):
         lat_list, lmask_list = list(res[1::2]), list(res[2::2])
 
         losses: Dict[str, Tensor] = {}
+        branch = side_branch if side_branch is not None else SideBranch(hidden.device)
         out_latents = []
         drop_tok = None            # [B, T, n_levels] bool: token-level latent dropout (inclusive over coarser levels)
         level_drops = []
@@ -216,11 +218,12 @@ class MMDTupleTransformer(TupleTransformer):
                 lat, lmask = lat[:, 1:2], torch.ones(b, 1, dtype=torch.bool, device=hidden.device)
             out_latents.append(lat)
             if compute_loss:
-                losses[f"MMD/{mode}"] = self.loss_weight * self.criterion(lat, mask=lmask, z=None if z_prior is None else z_prior[i])
-                if self.deadpan_zero_latent:
-                    sel = (deadpan_mask[:, None] & lmask)[..., None].to(lat.dtype)       # mmd_transformer.py:268-273
-                    denom = sel.sum() * lat.shape[-1]
-                    losses[f"MMD/{mode}/deadpan"] = (lat.pow(2) * sel).sum() / denom.clamp(min=1.0)
+                with branch.run(lat, lmask):      # nothing downstream needs these terms before the final loss sum
+                    losses[f"MMD/{mode}"] = self.loss_weight * self.criterion(lat, mask=lmask, z=None if z_prior is None else z_prior[i])
+                    if self.deadpan_zero_latent:
+                        sel = (deadpan_mask[:, None] & lmask)[..., None].to(lat.dtype)       # mmd_transformer.py:268-273
+                        denom = sel.sum() * lat.shape[-1]
+                        losses[f"MMD/{mode}/deadpan"] = (lat.pow(2) * sel).sum() / denom.clamp(min=1.0)
             # latent dropout (mmd_transformer.py:349-364, 537-542): Bernoulli per valid segment, broadcast to its notes
             p = self.latent_dropout[i]
             if mode != "mean" and self.training and p > 0.:
@@ -244,8 +247,11 @@ class MMDTupleTransformer(TupleTransformer):
 
         loss = None
         if compute_loss:
-            loss = sum(losses.values())
-            losses["MMD"] = loss
+            with branch.run():
+                loss = sum(losses.values())
+                losses["MMD"] = loss
+            if side_branch is None:               # standalone use: rejoin at once; ScorePerformer.forward joins after the decoder
+                branch.join(*losses.values())
         return MMDTupleTransformerOutput(hidden_state=hidden, logits=out_t.logits, attentions=None, latents=out_latents,
                                          embeddings=embeddings, full_embeddings=full_embeddings, dropout_mask=drop_mask, loss=loss,
                                          losses=losses)

@@ -19,6 +19,7 @@ from ..classifiers.model import (MultiHeadEmbeddingClassifier, MultiHeadEmbeddin
                                  MultiHeadEmbeddingClassifierOutput)
 from .embeddings import TupleTokenLMHeadConfig
 from .mmd_transformer import MMDTupleTransformer, MMDTupleTransformerOutput
+from ...utils import SideBranch
 from .transformer import TupleTransformer, TupleTransformerConfig, TupleTransformerOutput
 from .wrappers import LMWrapper, ScorePerformerLMModes, ScorePerformerLMWrappers
 
@@ -161,7 +162,7 @@ class ScorePerformer(_LMMixin, Model):
         self.z_prior: Optional[List[Tensor]] = None
 
     def forward_encoders(self, perf=None, perf_mask=None, score=None, score_mask=None, bars=None, beats=None, onsets=None,
-                         deadpan_mask=None, compute_loss: bool = True, table_cache: Optional[dict] = None):
+                         deadpan_mask=None, compute_loss: bool = True, table_cache: Optional[dict] = None, side_branch=None):
         table_cache = {} if table_cache is None else table_cache
         score_emb = perf_emb = None
         score_enc_out = perf_enc_out = None
@@ -170,7 +171,8 @@ class ScorePerformer(_LMMixin, Model):
             score_emb = score_enc_out.hidden_state
         if self.perf_encoder is not None:
             perf_enc_out = self.perf_encoder(perf, mask=perf_mask, bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask,
-                                             compute_loss=compute_loss, z_prior=self.z_prior, table_cache=table_cache)
+                                             compute_loss=compute_loss, z_prior=self.z_prior, table_cache=table_cache,
+                                             side_branch=side_branch)
             perf_emb = perf_enc_out.embeddings
         return ScorePerformerEncoderOutputs(score_embeddings=score_emb, score_mask=score_mask, perf_embeddings=perf_emb,
                                             score_encoder=score_enc_out, perf_encoder=perf_enc_out)
@@ -181,26 +183,39 @@ class ScorePerformer(_LMMixin, Model):
                 beats: Optional[Tensor] = None, onsets: Optional[Tensor] = None, directions: Optional[Tensor] = None,
                 deadpan_mask: Optional[Tensor] = None):
         table_cache: dict = {}
+        # MMD terms and the classifier heads are dozens of tiny kernels nothing else waits for: they run on a side stream
+        # (a parallel branch of the captured graph) underneath the decoder and are joined just before the losses are summed
+        branch = SideBranch(perf.device)
         enc_out = self.forward_encoders(
             perf=default(noisy_perf, perf), perf_mask=default(noisy_perf_mask, perf_mask), score=score, score_mask=score_mask,
-            bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask, table_cache=table_cache)
-
-        perf_dec_out = self.perf_decoder(perf, mask=perf_mask, style_embeddings=enc_out.perf_embeddings,
-                                         context=enc_out.score_embeddings, context_mask=enc_out.score_mask, labels=labels,
-                                         seq_masked=masked_perf, table_cache=table_cache)
-        loss, losses = perf_dec_out.loss, perf_dec_out.losses
-
-        if enc_out.perf_encoder is not None and enc_out.perf_encoder.loss is not None:
-            loss = loss + enc_out.perf_encoder.loss
-            losses.update(**enc_out.perf_encoder.losses)
+            bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask, table_cache=table_cache, side_branch=branch)
 
         clf_out = None
         if self.classifiers is not None:
             clf_mask = perf_mask if deadpan_mask is None else perf_mask & (~deadpan_mask[:, None])
             # fused replacement of `full_embeddings[clf_mask]` / `directions[clf_mask]` (model.py:323-329): rows are
             # selected inside the kernel, so no dynamic-shape gather and no host sync
-            clf_out = self.classifiers(embeddings=enc_out.perf_encoder.full_embeddings, labels=directions, rowmask=clf_mask,
-                                       with_logits=not self.training)
+            with branch.run(enc_out.perf_encoder.full_embeddings, directions, clf_mask):
+                clf_out = self.classifiers(embeddings=enc_out.perf_encoder.full_embeddings, labels=directions, rowmask=clf_mask,
+                                           with_logits=not self.training)
+
+        perf_dec_out = self.perf_decoder(perf, mask=perf_mask, style_embeddings=enc_out.perf_embeddings,
+                                         context=enc_out.score_embeddings, context_mask=enc_out.score_mask, labels=labels,
+                                         seq_masked=masked_perf, table_cache=table_cache)
+        loss, losses = perf_dec_out.loss, perf_dec_out.losses
+
+        side_out = []
+        if enc_out.perf_encoder is not None and enc_out.perf_encoder.loss is not None:
+            side_out += list(enc_out.perf_encoder.losses.values())
+        if clf_out is not None:
+            side_out += [clf_out.loss] + list(clf_out.losses.values()) + [getattr(clf_out, "logits", None)]
+        branch.join(*[t for t in side_out if isinstance(t, torch.Tensor)])
+
+        if enc_out.perf_encoder is not None and enc_out.perf_encoder.loss is not None:
+            loss = loss + enc_out.perf_encoder.loss
+            losses.update(**enc_out.perf_encoder.losses)
+
+        if clf_out is not None:
             if clf_out.loss is not None:
                 loss = loss + clf_out.loss
                 losses.update(**clf_out.losses)

@@ -42,3 +42,52 @@ class ExplicitEnum(str, Enum):
     @classmethod
     def list(cls):
         return list(map(lambda c: c.value, cls))
+
+
+# ----------------------------------------------------------------------------- side-stream fork / join
+# Loss-side work that nothing downstream waits for (MMD terms, classifier heads) consists of dozens of tiny kernels.  Run on a
+# second CUDA stream it overlaps the large decoder kernels, in eager mode and as a parallel branch of the captured step graph;
+# autograd replays each node on the stream of its forward, so the backward overlaps as well.  SPB_SIDE_STREAM=0 disables it.
+import contextlib as _contextlib
+import os as _os
+
+_SIDE_STREAMS = {}
+
+
+class SideBranch:
+    def __init__(self, device):
+        import torch
+        self.torch = torch
+        self.enabled = device.type == "cuda" and _os.environ.get("SPB_SIDE_STREAM", "1") != "0"
+        self.side = None
+        if self.enabled:
+            key = device.index if device.index is not None else torch.cuda.current_device()
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+            self.side = _SIDE_STREAMS[key]
+        self.used = False
+
+    @_contextlib.contextmanager
+    def run(self, *inputs):
+        """Execute the body on the side stream, after everything issued so far on the current stream."""
+        if not self.enabled:
+            yield
+            return
+        cur = self.torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        for t in inputs:
+            if t is not None and t.is_cuda:
+                t.record_stream(self.side)
+        self.used = True
+        with self.torch.cuda.stream(self.side):
+            yield
+
+    def join(self, *outputs):
+        """Make the current stream wait for the side work; `outputs` are side-stream tensors about to be used here."""
+        if self.enabled and self.used:
+            cur = self.torch.cuda.current_stream()
+            cur.wait_stream(self.side)
+            for t in outputs:
+                if t is not None and t.is_cuda:
+                    t.record_stream(cur)
+            self.used = False
