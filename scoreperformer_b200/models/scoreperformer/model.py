@@ -8,6 +8,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Union
 
+import os as _os
+
 import torch
 from torch import Tensor
 
@@ -166,14 +168,25 @@ class ScorePerformer(_LMMixin, Model):
         table_cache = {} if table_cache is None else table_cache
         score_emb = perf_emb = None
         score_enc_out = perf_enc_out = None
+        enc_branch = None
         if self.score_encoder is not None:
-            score_enc_out = self.score_encoder(score, mask=score_mask, table_cache=table_cache)
-            score_emb = score_enc_out.hidden_state
+            # the two encoders are independent: the score encoder runs as a second branch next to the performance encoder
+            both = self.perf_encoder is not None and side_branch is not None and _os.environ.get("SPB_ENC_BRANCH", "1") == "1"
+            if both:
+                enc_branch = SideBranch(score.device, slot=1)
+                with enc_branch.run(score, score_mask):
+                    score_enc_out = self.score_encoder(score, mask=score_mask, table_cache=table_cache)
+                    score_emb = score_enc_out.hidden_state
+            else:
+                score_enc_out = self.score_encoder(score, mask=score_mask, table_cache=table_cache)
+                score_emb = score_enc_out.hidden_state
         if self.perf_encoder is not None:
             perf_enc_out = self.perf_encoder(perf, mask=perf_mask, bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask,
                                              compute_loss=compute_loss, z_prior=self.z_prior, table_cache=table_cache,
                                              side_branch=side_branch)
             perf_emb = perf_enc_out.embeddings
+        if enc_branch is not None:
+            enc_branch.join(score_emb)
         return ScorePerformerEncoderOutputs(score_embeddings=score_emb, score_mask=score_mask, perf_embeddings=perf_emb,
                                             score_encoder=score_enc_out, perf_encoder=perf_enc_out)
 

@@ -55,15 +55,19 @@ _SIDE_STREAMS = {}
 
 
 class SideBranch:
-    def __init__(self, device):
+    def __init__(self, device, slot: int = 0):
         import torch
         self.torch = torch
         self.enabled = device.type == "cuda" and _os.environ.get("SPB_SIDE_STREAM", "1") != "0"
         self.side = None
         if self.enabled:
-            key = device.index if device.index is not None else torch.cuda.current_device()
+            key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
             if key not in _SIDE_STREAMS:
                 _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+                # gradients of shared parameters are intentionally produced on different streams (autograd syncs them)
+                warn_off = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+                if warn_off is not None:
+                    warn_off(False)
             self.side = _SIDE_STREAMS[key]
         self.used = False
 
