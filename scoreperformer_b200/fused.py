@@ -10,10 +10,14 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
+import contextlib
+import os
+
 import torch
 from torch import Tensor
 
 from . import kernels as K
+from .utils import SideBranch
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -417,23 +421,35 @@ class TransformerStackFn(torch.autograd.Function):
             grads[j], grads[j + 1] = (None if d1 else dw), (None if d2 else db)
             return res if want16 else (res, None)
 
+        # weight-gradient GEMMs feed nothing downstream in this backward: they run on a side stream of their own (one per calling
+        # stream) and fill the gaps of the activation-gradient chain; joined before the gradients are handed to autograd
+        wb = None
+        if g_out.is_cuda and os.environ.get("SPB_WGRAD_BRANCH", "1") == "1":
+            for i in range(3):                                     # small fixed pool, created on the first (eager) call
+                SideBranch(g_out.device, slot=("wgrad", i))
+            wb = SideBranch(g_out.device, slot=("wgrad", (torch.cuda.current_stream().cuda_stream >> 6) % 3))
+        side = (lambda *ts: wb.run(*ts)) if wb is not None else (lambda *ts: contextlib.nullcontext())
+
         g, g16 = norm_bwd(2 * spec.depth, K.cast_bf16(g_out.contiguous().view(N, D)), ctx.final, None)
         for l in reversed(range(spec.depth)):
             base = l * (PARAMS_PER_ATTN + PARAMS_PER_FF)
             rec_a, rec_f = ctx.layers[l]
             # ---- feed-forward backward:  x_out = x + W2 glu(W1 LN(x) + b1)
             p_w1, p_b1, p_w2 = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
-            grads[base + PARAMS_PER_ATTN + 4] = wgrad(p_w2, g16, rec_f["h"])
+            with side(g16, rec_f["h"]):
+                grads[base + PARAMS_PER_ATTN + 4] = wgrad(p_w2, g16, rec_f["h"])
             dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
             db1, d_b1 = take(p_b1)
             du = K.glu_bwd(dh, rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
             grads[base + PARAMS_PER_ATTN + 3] = None if d_b1 else db1
-            grads[base + PARAMS_PER_ATTN + 2] = wgrad(p_w1, du, rec_f["xn"])
+            with side(du, rec_f["xn"]):
+                grads[base + PARAMS_PER_ATTN + 2] = wgrad(p_w1, du, rec_f["xn"])
             dxn = K.gemm(du, rec_f["w1_16"], trans_b=True, out_dtype=BF16)
             g, g16 = norm_bwd(2 * l + 1, dxn, rec_f, g)
             # ---- attention backward:  x_out = x + mask * Wo attn(Wqkv LN(x))
             p_q, p_k, p_v, p_o, p_ls = params[base + 2:base + 7]
-            grads[base + 5] = wgrad(p_o, g16, rec_a["o"])
+            with side(g16, rec_a["o"]):
+                grads[base + 5] = wgrad(p_o, g16, rec_a["o"])
             # dO = dY Wo and delta = rowsum(dO * O) in one GEMM (the epilogue owns whole rows of a head)
             do, delta = K.gemm_rowdot(g16, rec_a["wo16"], rec_a["o"], T, H, trans_b=True)
             dls, d_ls = take(p_ls)
@@ -441,12 +457,13 @@ class TransformerStackFn(torch.autograd.Function):
                                    ctx.seeds[2 * l], delta=delta)
             grads[base + 6] = None if d_ls else dls.view(p_ls.shape)
             g_qkv = direct_grad_cat([p_q, p_k, p_v])
-            if g_qkv is not None:
-                K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out=g_qkv, split_k=0, accumulate=True)
-            else:
-                dwqkv = K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
-                hq = H * spec.dim_head
-                grads[base + 2], grads[base + 3], grads[base + 4] = dwqkv[:hq], dwqkv[hq:hq + spec.dim_head], dwqkv[hq + spec.dim_head:]
+            with side(dqkv, rec_a["xn"]):
+                if g_qkv is not None:
+                    K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out=g_qkv, split_k=0, accumulate=True)
+                else:
+                    dwqkv = K.gemm(dqkv, rec_a["xn"], trans_a=True, trans_b=True, out_dtype=F32, split_k=0)
+                    hq = H * spec.dim_head
+                    grads[base + 2], grads[base + 3], grads[base + 4] = dwqkv[:hq], dwqkv[hq:hq + spec.dim_head], dwqkv[hq + spec.dim_head:]
             dxn = K.gemm(dqkv, rec_a["wqkv16"], trans_b=True, out_dtype=BF16)
             g, g16 = norm_bwd(2 * l, dxn, rec_a, g)
         d_style = None
@@ -459,6 +476,8 @@ class TransformerStackFn(torch.autograd.Function):
                 grads[j + 1] = db_ada[i * 2 * D:(i + 1) * 2 * D]
             if ctx.needs_input_grad[3]:
                 d_style = K.gemm(dgb_all, w_ada16, trans_b=True, out_dtype=F32).view(ctx.style_shape)
+        if wb is not None:
+            wb.join(*[t for t in grads if isinstance(t, Tensor)])
         return (None, g.view(B, T, D), None, d_style, None) + tuple(grads)
 
 
