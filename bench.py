@@ -265,6 +265,11 @@ def main():
         import scoreperformer_b200.fused as fused_mod
         fused_mod.K.gemm = timed_gemm
         ts.use_graph = False
+        # the timed step overlaps independent branches on side streams; for the per-kernel roofline every GEMM must own the GPU
+        # while it is timed, so the instrumented eager steps run single-stream
+        branch_env = {k: os.environ.get(k) for k in ("SPB_SIDE_STREAM", "SPB_ENC_BRANCH", "SPB_WGRAD_BRANCH")}
+        for k in branch_env:
+            os.environ[k] = "0"
         for _ in range(3):                    # first eager passes only warm the allocator (the graph owns a private pool)
             records.clear()
             torch.cuda._sleep(int(60e6))      # ~30 ms spin kernel: lets the CPU run ahead so event pairs see GPU time only
@@ -272,6 +277,11 @@ def main():
             torch.cuda.synchronize()
         K.gemm = orig
         fused_mod.K.gemm = orig
+        for k, v in branch_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in records)
         tot_fl = sum(f for _, _, f, _ in records)
         # dominant launch shape = the one with the largest share of GEMM time (FFN1 forward at C2)
