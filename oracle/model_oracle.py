@@ -61,14 +61,14 @@ def field_table(sd: Dict[str, Tensor], prefix: str, key: str, discrete_ids=(0, 1
     Linear(1,E) -> Mish -> Linear(E,E)), :91-99 (weight = token_weight + value_weight).
     """
     p = f"{prefix}.embs.{key}."
-    ids = torch.as_tensor(list(discrete_ids), dtype=torch.long)
     iw = sd[p + "index_weight"]
+    ids = torch.as_tensor(list(discrete_ids), dtype=torch.long, device=iw.device)
     tok = torch.zeros_like(iw)
     tok[ids] = iw[ids]
     tv = sd[p + "token_values"].to(iw.dtype)
     h = F.mish(F.linear(tv, sd[p + "value_layer.0.0.weight"], sd[p + "value_layer.0.0.bias"]))
     val = F.linear(h, sd[p + "value_layer.1.0.weight"], sd[p + "value_layer.1.0.bias"])
-    keep = torch.ones(val.shape[0], 1, dtype=val.dtype)
+    keep = torch.ones(val.shape[0], 1, dtype=val.dtype, device=val.device)
     keep[ids] = 0.0
     return tok + val * keep
 
@@ -92,8 +92,8 @@ def tuple_embed(sd, prefix: str, tokens: Tensor, keys: Sequence[str], spec: Orac
 # ----------------------------------------------------------------------------- a5/a6: attention
 def alibi_bias(i: int, j: int, k: int, slopes: Tensor) -> Tensor:
     """-slope_h * |col - (row + k)|; modules/transformer/embeddings.py:294-315 (symmetric)."""
-    rows = torch.arange(k, i + k)
-    cols = torch.arange(j)
+    rows = torch.arange(k, i + k, device=slopes.device)
+    cols = torch.arange(j, device=slopes.device)
     dist = -(cols[None, :] - rows[:, None]).abs().to(slopes.dtype)
     return slopes.view(-1, 1, 1) * dist[None]
 
@@ -117,11 +117,11 @@ def attention(sd, prefix: str, x: Tensor, mask: Optional[Tensor], causal: bool, 
     j = k.shape[1]
     slopes = sd[f"{prefix}.rel_pos.learned_logslopes"].exp().view(-1)
     bias = alibi_bias(n, j, j - n, slopes)[None].expand(b, -1, -1, -1)
-    allowed = torch.ones(b, 1, n, j, dtype=torch.bool)
+    allowed = torch.ones(b, 1, n, j, dtype=torch.bool, device=x.device)
     if mask is not None:
         allowed = allowed & mask[:, None, None, :]
     if causal:
-        allowed = allowed & ~torch.ones(n, j, dtype=torch.bool).triu(j - n + 1)
+        allowed = allowed & ~torch.ones(n, j, dtype=torch.bool, device=x.device).triu(j - n + 1)
     fill = -torch.finfo(x.dtype).max // 2
     bias = bias.masked_fill(~allowed, fill)
     scores = torch.einsum("bhid,bjd->bhij", q, k) * (dh ** -0.5) + bias
@@ -240,10 +240,10 @@ def segment_mean(x: Tensor, segments: Tensor):
     """
     b, t, d = x.shape
     s = int(segments.max()) + 1
-    sums = torch.zeros(b, s, d, dtype=x.dtype).index_put_(
-        (torch.arange(b)[:, None].expand(b, t), segments), x, accumulate=True)
-    counts = torch.zeros(b, s, dtype=torch.long).index_put_(
-        (torch.arange(b)[:, None].expand(b, t), segments), torch.ones(b, t, dtype=torch.long), accumulate=True)
+    rows = torch.arange(b, device=x.device)[:, None].expand(b, t)
+    sums = torch.zeros(b, s, d, dtype=x.dtype, device=x.device).index_put_((rows, segments), x, accumulate=True)
+    counts = torch.zeros(b, s, dtype=torch.long, device=x.device).index_put_(
+        (rows, segments), torch.ones(b, t, dtype=torch.long, device=x.device), accumulate=True)
     return sums / counts.clamp(min=1)[..., None].to(x.dtype), counts
 
 
@@ -260,11 +260,14 @@ def mmd(z: Tensor, y: Tensor) -> Tensor:
 
 
 def perf_encoder_forward(sd, batch, spec: OracleSpec, z_prior: Optional[List[Tensor]], training: bool,
-                         compute_loss: bool = True):
+                         compute_loss: bool = True, mmd_perm: Optional[List[Optional[Tensor]]] = None):
     """MMDTupleTransformer.forward, hierarchical_with_context, dropouts off.
 
     models/scoreperformer/mmd_transformer.py:169-302 and _forward_latents :304-368.
     `z_prior[l]` is the injected N(0,I) sample [256, z_l] of MMDLoss.forward (:519).
+    `mmd_perm[l]` injects the `randperm(n)[:max_num_latents]` draw of MMDLoss.forward (:515-517) for levels with more
+    than `max_num_latents` valid latents; without it a fresh permutation is drawn.  The rows actually used are returned
+    as `mmd_rows[l]` = (sample index, segment index) pairs, so a test can hand the SAME subsample to the CUDA path.
     """
     mask = batch["perf_mask"]
     hidden = encoder_forward(sd, "perf_encoder", batch["perf"], mask, list(spec.num_tokens), spec.depth_perf, spec)
@@ -272,13 +275,13 @@ def perf_encoder_forward(sd, batch, spec: OracleSpec, z_prior: Optional[List[Ten
     out = hidden * m3
     b, t, _ = out.shape
     seg_of = {"bar_mean": batch.get("bars"), "beat_mean": batch.get("beats"), "onset_mean": batch.get("onsets")}
-    latents, embs, losses, counts_all = [], [], {}, []
+    latents, embs, losses, counts_all, mmd_rows = [], [], {}, [], []
     for lvl, (mode, zl) in enumerate(zip(spec.aggregate_mode, spec.latent_dim)):
         w = sd[f"perf_encoder.vae_head.{mode}.linear.weight"]
         bias = sd[f"perf_encoder.vae_head.{mode}.linear.bias"]
         if mode == "mean":
             pooled = (out.sum(dim=1) / m3.sum(dim=1))[:, None]                      # :325-327
-            lmask = torch.ones(b, 1, dtype=torch.bool)
+            lmask = torch.ones(b, 1, dtype=torch.bool, device=out.device)
             counts_all.append(mask.sum(1, keepdim=True))
         else:
             pooled, counts = segment_mean(out, seg_of[mode])                         # :330-340
@@ -288,15 +291,20 @@ def perf_encoder_forward(sd, batch, spec: OracleSpec, z_prior: Optional[List[Ten
         if mode == "mean":
             emb = lat.expand(-1, t, -1)                                              # :356-359
         else:
-            emb = lat[torch.arange(b)[:, None].expand(b, t), seg_of[mode]]           # :362-364
+            emb = lat[torch.arange(b, device=lat.device)[:, None].expand(b, t), seg_of[mode]]           # :362-364
         emb = emb * m3                                                               # :366
         latents.append(lat)
         embs.append(emb)
         out = torch.cat([out, emb], dim=-1)                                          # :259-261
         if compute_loss:
             y = lat[lmask]
-            if y.shape[0] > spec.mmd_max_latents:
-                raise NotImplementedError("oracle parity runs keep n <= max_num_latents (SURVEY B.3)")
+            rows = None
+            if y.shape[0] > spec.mmd_max_latents:                                    # :515-517
+                perm = mmd_perm[lvl] if mmd_perm is not None and mmd_perm[lvl] is not None else \
+                    torch.randperm(y.shape[0], device=y.device)[:spec.mmd_max_latents]
+                y = y[perm]
+                rows = torch.nonzero(lmask)[perm]                                    # [max, 2] = (sample, segment)
+            mmd_rows.append(rows)
             losses[f"MMD/{mode}"] = spec.mmd_loss_weight * mmd(z_prior[lvl].to(y.dtype), y)   # :266, :519-520
             if spec.deadpan_zero_latent:
                 dp = lat[batch["deadpan_mask"][:, None] & lmask]                     # :268-273
@@ -308,7 +316,7 @@ def perf_encoder_forward(sd, batch, spec: OracleSpec, z_prior: Optional[List[Ten
         loss = sum(losses.values())
         losses["MMD"] = loss
     return dict(hidden_state=hidden, latents=latents, embeddings=embeddings, full_embeddings=embeddings,
-                loss=loss, losses=losses, counts=counts_all)
+                loss=loss, losses=losses, counts=counts_all, mmd_rows=mmd_rows)
 
 
 # ----------------------------------------------------------------------------- a11: classifiers
@@ -339,12 +347,12 @@ def classifiers_forward(sd, emb: Tensor, labels: Tensor, spec: OracleSpec):
 
 # ----------------------------------------------------------------------------- a12: whole step
 def scoreperformer_forward(sd, batch: Dict[str, Tensor], spec: OracleSpec, z_prior: Optional[List[Tensor]] = None,
-                           training: bool = True):
+                           training: bool = True, mmd_perm: Optional[List[Optional[Tensor]]] = None):
     """ScorePerformer.forward, default recipe, all dropouts 0; models/scoreperformer/model.py:280-341
     + ScorePerformerMixedLMWrapper.forward (wrappers.py:409-431) + LM loss (wrappers.py:44-59)."""
     score_hidden = encoder_forward(sd, "score_encoder", batch["score"], batch["score_mask"],
                                    list(spec.num_score_tokens), spec.depth_score, spec)
-    enc = perf_encoder_forward(sd, batch, spec, z_prior, training)
+    enc = perf_encoder_forward(sd, batch, spec, z_prior, training, mmd_perm=mmd_perm)
 
     # MixedLM shift (wrappers.py:409-431)
     seq = batch["perf"][:, :-1]
@@ -376,7 +384,8 @@ def scoreperformer_forward(sd, batch: Dict[str, Tensor], spec: OracleSpec, z_pri
         losses.update(clf["losses"])
     return dict(loss=loss, losses=losses, logits=logits, dec_hidden=dec_hidden, score_hidden=score_hidden,
                 perf_hidden=enc["hidden_state"], latents=enc["latents"], embeddings=enc["embeddings"],
-                counts=enc["counts"], clf_logits=None if clf is None else clf["logits"], lm_loss=lm_loss)
+                counts=enc["counts"], clf_logits=None if clf is None else clf["logits"], lm_loss=lm_loss,
+                mmd_rows=enc["mmd_rows"])
 
 
 # ----------------------------------------------------------------------------- a13: greedy rendering
@@ -392,7 +401,7 @@ def render_greedy(sd, spec: OracleSpec, perf: Tensor, perf_masked: Tensor, score
     out = perf.clone()
     t_total = out.shape[1]
     if mask is None:
-        mask = torch.ones(out.shape[:2], dtype=torch.bool)
+        mask = torch.ones(out.shape[:2], dtype=torch.bool, device=out.device)
     unmask = out == 1
     caches = None
     tok_cache = None

@@ -50,23 +50,68 @@ SIGNATURES = {
 _lib: Optional[ctypes.CDLL] = None
 
 
-def nvcc_command(out: str = LIB_PATH):
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(os.path.dirname(_HERE), "build")
+
+
+def _digest(paths) -> str:
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every kernel for sm_100a into scoreperformer_b200/csrc/libspb200.so (in-tree, git-ignored)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    """Compile every kernel for sm_100a into scoreperformer_b200/csrc/libspb200.so (in-tree, git-ignored).
+
+    One nvcc process per .cu (in parallel), objects cached under build/ by the hash of the source + common.cuh + flags, so
+    only edited files recompile; the library is relinked whenever an object changed.  A shipped prebuilt library is kept
+    only if it was linked from exactly the current sources (the hash list is stored next to it)."""
+    from concurrent.futures import ThreadPoolExecutor
+    common = os.path.join(CSRC, "common.cuh")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    digests = [_digest([s, common]) for s in srcs]
+    stamp = LIB_PATH + ".srchash"
+    want = "\n".join(digests)
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == want:
         return LIB_PATH
-    cmd = nvcc_command()
+    import shutil
+    if shutil.which("nvcc") is None:
+        if os.path.exists(LIB_PATH):      # GPU box without a toolchain: the snapshot's library is what there is
+            return LIB_PATH
+        raise RuntimeError("nvcc not found and no prebuilt libspb200.so: scoreperformer_b200 has no CPU / PyTorch fallback")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    objs = [os.path.join(BUILD_DIR, f"{os.path.splitext(os.path.basename(s))[0]}.{d}.o") for s, d in zip(srcs, digests)]
+
+    def compile_one(job):
+        src, obj = job
+        if os.path.exists(obj) and not force:
+            return None
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            print(" ".join(cmd))
+            print(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n" + res.stderr[-4000:])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as pool:
+        list(pool.map(compile_one, zip(srcs, objs)))
+    cmd = ["nvcc", "-shared", "-o", LIB_PATH] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        print(" ".join(cmd))
-        print(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libspb200.so:\n" + res.stderr[-4000:])
+        raise RuntimeError("linking libspb200.so failed:\n" + res.stderr[-4000:])
+    with open(stamp, "w") as f:
+        f.write(want)
+    # drop objects of older source versions
+    keep = set(objs)
+    for name in os.listdir(BUILD_DIR):
+        path = os.path.join(BUILD_DIR, name)
+        if name.endswith(".o") and path not in keep:
+            os.remove(path)
     return LIB_PATH
 
 

@@ -72,12 +72,16 @@ class MMDLoss(nn.Module):
         self.num_samples = num_samples
         self.max_num_latents = max_num_latents
 
-    def forward(self, latents: Tensor, mask: Optional[Tensor] = None, z: Optional[Tensor] = None):
-        """latents [..., d]; mask [...] bool (True = valid).  `z` injects the prior sample (parity runs)."""
+    def forward(self, latents: Tensor, mask: Optional[Tensor] = None, z: Optional[Tensor] = None, rows: Optional[Tensor] = None):
+        """latents [..., d]; mask [...] bool (True = valid).  `z` injects the prior sample and `rows` ([n, 2] = (sample,
+        segment) pairs) the `randperm` subsample of mmd_transformer.py:515-517 (parity runs)."""
         d = latents.shape[-1]
         y = latents.reshape(-1, d)
         w = torch.ones(y.shape[0], dtype=torch.bool, device=y.device) if mask is None else mask.reshape(-1)
-        if y.shape[0] > self.max_num_latents:
+        if rows is not None:
+            idx = rows[:, 0].to(y.device) * latents.shape[-2] + rows[:, 1].to(y.device)
+            y, w = y.index_select(0, idx), w.index_select(0, idx)
+        elif y.shape[0] > self.max_num_latents:
             # device-side replacement of `latents[mask][randperm(n)[:max]]`: the `max` smallest random keys among the valid
             # rows (all valid rows when n <= max) -- same distribution, no host sync, static shapes.
             keys = torch.rand(y.shape[0], device=y.device).masked_fill_(~w, 2.0)
@@ -179,6 +183,7 @@ class MMDTupleTransformer(TupleTransformer):
                 beats: Optional[Tensor] = None, onsets: Optional[Tensor] = None, deadpan_mask: Optional[Tensor] = None,
                 return_embeddings: bool = False, return_attn: bool = False, compute_loss: bool = True,
                 z_prior: Optional[List[Tensor]] = None, table_cache: Optional[dict] = None, side_branch: Optional[SideBranch] = None,
+                mmd_rows: Optional[List[Optional[Tensor]]] = None,
                 **kwargs):
         if latents is not None or not self._fused_supported() or self._mask_bars:
             raise NotImplementedError(
@@ -219,7 +224,8 @@ class MMDTupleTransformer(TupleTransformer):
             out_latents.append(lat)
             if compute_loss:
                 with branch.run(lat, lmask):      # nothing downstream needs these terms before the final loss sum
-                    losses[f"MMD/{mode}"] = self.loss_weight * self.criterion(lat, mask=lmask, z=None if z_prior is None else z_prior[i])
+                    losses[f"MMD/{mode}"] = self.loss_weight * self.criterion(lat, mask=lmask, z=None if z_prior is None else z_prior[i],
+                                                                                 rows=None if mmd_rows is None else mmd_rows[i])
                     if self.deadpan_zero_latent:
                         sel = (deadpan_mask[:, None] & lmask)[..., None].to(lat.dtype)       # mmd_transformer.py:268-273
                         denom = sel.sum() * lat.shape[-1]

@@ -162,6 +162,8 @@ class ScorePerformer(_LMMixin, Model):
         self._apply_mode(mode)
         # Optional injection points for parity runs: list of N(0, I) prior samples, one per latent level.
         self.z_prior: Optional[List[Tensor]] = None
+        # ... and of the (sample, segment) rows MMDLoss subsamples when a level has more than 4096 valid latents
+        self.mmd_rows: Optional[List[Optional[Tensor]]] = None
 
     def forward_encoders(self, perf=None, perf_mask=None, score=None, score_mask=None, bars=None, beats=None, onsets=None,
                          deadpan_mask=None, compute_loss: bool = True, table_cache: Optional[dict] = None, side_branch=None):
@@ -183,7 +185,7 @@ class ScorePerformer(_LMMixin, Model):
         if self.perf_encoder is not None:
             perf_enc_out = self.perf_encoder(perf, mask=perf_mask, bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask,
                                              compute_loss=compute_loss, z_prior=self.z_prior, table_cache=table_cache,
-                                             side_branch=side_branch)
+                                             side_branch=side_branch, mmd_rows=self.mmd_rows)
             perf_emb = perf_enc_out.embeddings
         if enc_branch is not None:
             enc_branch.join(score_emb)

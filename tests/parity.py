@@ -34,8 +34,8 @@ def build_model(dropout: bool = False, seed_weights: int = 0, device: str = "cpu
     return model.to(device)
 
 
-def oracle_state(model: torch.nn.Module, requires_grad: bool = True) -> Dict[str, torch.Tensor]:
-    """CPU fp32 copy of the state_dict that preserves parameter tying (aliases map to ONE tensor object)."""
+def oracle_state(model: torch.nn.Module, requires_grad: bool = True, device: str = "cpu") -> Dict[str, torch.Tensor]:
+    """fp32 copy of the state_dict (on `device`) that preserves parameter tying (aliases map to ONE tensor object)."""
     sd, first = {}, {}
     for k, v in model.state_dict(keep_vars=True).items():
         ptr = v.data_ptr()
@@ -43,7 +43,7 @@ def oracle_state(model: torch.nn.Module, requires_grad: bool = True) -> Dict[str
             sd[k] = sd[first[ptr]]
             continue
         first[ptr] = k
-        t = v.detach().cpu().clone()
+        t = v.detach().to(device).clone()
         if requires_grad and isinstance(v, torch.nn.Parameter):
             t.requires_grad_(True)
         sd[k] = t
@@ -67,48 +67,78 @@ def cosine_distance(a: torch.Tensor, b: torch.Tensor) -> float:
     return float(1 - torch.dot(a, b) / (a.norm() * b.norm()).clamp(min=1e-30))
 
 
-def run_product_step(model: ScorePerformer, batch, z):
+def run_product_step(model: ScorePerformer, batch, z, mmd_rows=None):
     """One training forward + backward of the CUDA model; returns the outputs object (grads live on the parameters)."""
     dev = next(model.parameters()).device
     model.train()
     model.zero_grad(set_to_none=True)
     model.z_prior = [t.to(dev) for t in z]
+    model.mmd_rows = None if mmd_rows is None else [None if r is None else r.to(dev) for r in mmd_rows]
     out = model(**{k: v.to(dev) for k, v in batch.items()})
     out.loss.backward()
     return out
 
 
-def run_oracle_step(model: ScorePerformer, batch, z):
-    sd = oracle_state(model)
+def run_oracle_step(model: ScorePerformer, batch, z, device: str = "cpu"):
+    """The oracle in strict fp32 (TF32 off) on `device`: "cpu", or "cuda" for the full-size configs (C2 64x512, C4 16x2048),
+    which the CPU would need minutes for."""
+    sd = oracle_state(model, device=device)
     spec = oracle_spec(model)
-    out = mo.scoreperformer_forward(sd, batch, spec, [t.clone() for t in z])
-    out["loss"].backward()
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = mo.scoreperformer_forward(sd, {k: v.to(device) for k, v in batch.items()}, spec, [t.clone().to(device) for t in z])
+        out["loss"].backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
     return out, sd
 
 
-def compare_step(model, batch, z, loss_rtol=2e-2, cos_tol=5e-3, verbose=True):
-    """north_star tolerances: losses/logits within 2e-2 relative (bf16), gradient cosine distance <= 5e-3."""
-    out = run_product_step(model, batch, z)
-    ref, sd = run_oracle_step(model, batch, z)
-    report = {}
+# north_star: "per-field losses and logits match within ... 2e-2 in bf16" -- max abs error relative to the tensor's max magnitude
+ACT_RTOL = 2e-2
+
+
+def compare_step(model, batch, z, loss_rtol=2e-2, cos_tol=5e-3, verbose=True, oracle_device: str = "cpu"):
+    """north_star tolerances: losses/logits within 2e-2 relative (bf16), gradient cosine distance <= 5e-3.  The oracle runs
+    first: when a latent level has more than 4096 valid rows it draws the MMD subsample (mmd_transformer.py:515-517) and the
+    CUDA path is handed the same rows, like the prior samples `z`.  Every deviation is collected and reported before the
+    single assert at the end, so one failing run shows the whole picture."""
+    ref, sd = run_oracle_step(model, batch, z, device=oracle_device)
+    out = run_product_step(model, batch, z, mmd_rows=ref["mmd_rows"])
+    model.mmd_rows = None
+    report = {"mmd_subsampled_levels": [i for i, r in enumerate(ref["mmd_rows"]) if r is not None]}
+    bad: List[str] = []
+
+    def check(cond: bool, msg: str):
+        if not cond:
+            bad.append(msg)
+
     for key, val in ref["losses"].items():
-        got = float(out.losses[key])
-        want = float(val)
+        got, want = float(out.losses[key]), float(val)
         report[f"loss/{key}"] = (got, want)
-        assert abs(got - want) <= loss_rtol * max(abs(want), 1e-2), f"loss {key}: {got} vs oracle {want}"
+        check(abs(got - want) <= loss_rtol * max(abs(want), 1e-2), f"loss {key}: {got} vs oracle {want}")
     got, want = float(out.loss), float(ref["loss"])
-    assert abs(got - want) <= loss_rtol * abs(want), f"total loss {got} vs oracle {want}"
-    # hidden states / embeddings
+    check(abs(got - want) <= loss_rtol * abs(want), f"total loss {got} vs oracle {want}")
+
+    def relerr(got_t, want_t):
+        want_t = want_t.detach()
+        return float((got_t.detach().float().to(want_t.device) - want_t).abs().max() / want_t.abs().max())
+
+    # hidden states / embeddings / logits of all 12 heads
     for name, got_t in (("score_hidden", out.score_encoder.hidden_state), ("perf_hidden", out.perf_encoder.hidden_state),
                         ("embeddings", out.perf_encoder.embeddings), ("dec_hidden", out.perf_decoder.hidden_state)):
-        want_t = ref[name]
-        err = float((got_t.detach().float().cpu() - want_t.detach()).abs().max() / want_t.detach().abs().max())
+        err = relerr(got_t, ref[name])
         report[f"relerr/{name}"] = err
-        assert err < 6e-2, f"{name}: max rel err {err}"
+        check(err < ACT_RTOL, f"{name}: max rel err {err}")
+    for key, want_t in ref["logits"].items():
+        err = relerr(out.perf_decoder.logits[key], want_t)
+        report["relerr/logits"] = max(report.get("relerr/logits", 0.0), err)
+        check(err < ACT_RTOL, f"logits/{key}: max rel err {err}")
     # pooling membership is bit-exact: the latents' validity pattern must match exactly
     for lat, lat_ref in zip(out.perf_encoder.latents, ref["latents"]):
-        assert lat.shape == lat_ref.shape, (lat.shape, lat_ref.shape)
-        assert torch.equal((lat.detach().cpu() != 0).any(-1), (lat_ref.detach() != 0).any(-1)), "latent validity differs"
+        check(lat.shape == lat_ref.shape, f"latent shape {tuple(lat.shape)} vs {tuple(lat_ref.shape)}")
+        if lat.shape == lat_ref.shape:
+            check(torch.equal((lat.detach().cpu() != 0).any(-1), (lat_ref.detach().cpu() != 0).any(-1)), "latent validity differs")
     # gradients
     worst = (0.0, None)
     seen = set()
@@ -118,22 +148,25 @@ def compare_step(model, batch, z, loss_rtol=2e-2, cos_tol=5e-3, verbose=True):
             continue
         seen.add(p.data_ptr())
         g_ref = sd[k].grad
-        assert p.grad is not None, f"no gradient for {k}"
-        assert g_ref is not None, f"oracle has no gradient for {k}"
+        if p.grad is None or g_ref is None:
+            check(False, f"missing gradient for {k} (cuda: {p.grad is not None}, oracle: {g_ref is not None})")
+            continue
+        g_ref = g_ref.cpu()
         g_got = p.grad.detach().float().cpu()
         if float(g_ref.norm()) == 0.0:      # e.g. index rows of an unlabelled field: exactly no gradient in the reference
-            assert float(g_got.abs().max()) == 0.0, f"{k}: reference gradient is exactly zero, got {float(g_got.abs().max())}"
+            check(float(g_got.abs().max()) == 0.0, f"{k}: reference gradient is exactly zero, got {float(g_got.abs().max())}")
             continue
         cd = cosine_distance(g_got, g_ref)
         norm_ratio = float(g_got.norm() / g_ref.norm())
-        assert 0.9 < norm_ratio < 1.1, f"grad norm ratio {norm_ratio:.3f} for {k}"
+        check(0.9 < norm_ratio < 1.1, f"grad norm ratio {norm_ratio:.3f} for {k}")
         if cd > worst[0]:
             worst = (cd, k)
-        assert cd <= cos_tol, f"grad cosine distance {cd:.2e} > {cos_tol} for {k}"
+        check(cd <= cos_tol, f"grad cosine distance {cd:.2e} > {cos_tol} for {k}")
     report["worst_grad_cosine_distance"] = worst
-    if verbose:
+    if verbose or bad:
         for k, v in report.items():
             print(f"  {k}: {v}")
+    assert not bad, "parity violations:\n  " + "\n  ".join(bad)
     return report
 
 
