@@ -96,9 +96,20 @@ int spb_attention_fwd(const void* qkv, int ld, const uint8_t* key_mask, const fl
                       int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed, const uint64_t* rng_offset,
                       spb_stream_t stream);
 /* tcgen05/TMEM/TMA implementation of the same forward (4 heads x dim 64): 32 positions x 4 heads form the 128-row MMA tile, the
- * softmax runs one row per thread out of TMEM.  mask_bits_scratch: uint32 [B, ceil(T/32)] (used when key_mask != NULL). */
+ * softmax runs one row per thread out of TMEM.  mask_bits_scratch: uint32 [B, ceil(T/32)] (written when key_mask != NULL; the
+ * tcgen05 backward reads it again).  edist (fp32 [B,H,T] or NULL): E_i[|i-j|] under the attention weights, the forward-side
+ * statistic spb_attention_bwd_tc needs for the ALiBi slope gradient (modules/transformer/embeddings.py:318-325). */
 int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_mask, uint32_t* mask_bits_scratch, const float* logslopes, void* out,
-                         int ld_out, float* lse, int B, int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed,
+                         int ld_out, float* lse, float* edist, int B, int T, int H, int dim_head, int causal, float dropout_p,
+                         uint64_t seed, const uint64_t* rng_offset, spb_stream_t stream);
+/* tcgen05/TMEM/TMA backward: dQ, dK, dV and d(logslope) in one kernel (a CTA owns 128 keys and walks the query tiles; the five
+ * contractions S, dP, dV, dK, dQ are tcgen05.mma chains with TMEM accumulators; dQ leaves through TMA tensor reduce-adds).
+ * mask_bits / edist: side outputs of spb_attention_fwd_tc (mask_bits NULL = no padding); delta fp32 [B,H,T] = rowsum(dO * O)
+ * (spb_gemm_bf16_rowdot); dq_acc: fp32 [B*T, H*64] scratch that must be ZERO on entry and is zero again on return;
+ * dqkv bf16 [B*T, ld_dqkv] receives dq | dk | dv; dlogslopes fp32 [H] ACCUMULATED.  Autograd of attend.py:58-126. */
+int spb_attention_bwd_tc(const void* qkv, int ld, const uint32_t* mask_bits, const float* logslopes, const void* dout, int ld_do,
+                         const float* lse, const float* delta, const float* edist, float* dq_acc, void* dqkv, int ld_dqkv,
+                         float* dlogslopes, int B, int T, int H, int dim_head, int causal, float dropout_p, uint64_t seed,
                          const uint64_t* rng_offset, spb_stream_t stream);
 /* dqkv bf16 [B*T, ld_dqkv] in the qkv column layout; delta fp32 [B,H,T] scratch; dlogslopes fp32 [H] ACCUMULATED. */
 int spb_attention_bwd(const void* qkv, int ld, const uint8_t* key_mask, const float* logslopes, const void* out, const void* dout,

@@ -31,6 +31,7 @@ struct TcParams {
     __nv_bfloat16* out;
     int ld_out;
     float* lse;                  // [B, H, T] base-2 units
+    float* edist;                // [B, H, T] E_i[|i-j|] under the undropped attention weights (backward's slope gradient), or null
     int B, T;
     float scale;
     int causal;
@@ -153,7 +154,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float o_reg[DH];
 #pragma unroll
         for (int d = 0; d < DH; ++d) o_reg[d] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, d_run = 0.f;      // running max, sum of numerators, sum of numerators * |i-j|
 
         for (int kt = 0; kt < n_kt; ++kt) {
             // validity bits of this tile's four 32-key chunks (key padding, sequence tail, causal limit for THIS row)
@@ -197,7 +198,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float corr = exp2f(m_run - m_use);
             m_run = m_new;
             // ---- pass 2: numerators, dropout, bf16 pack into the swizzled A-operand tile
-            float rsum = 0.f;
+            float rsum = 0.f, dsum = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
@@ -213,10 +214,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const uint32_t bits = vbits[c];
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
-                    const float x = fmaf(-slope, fabsf(dbase - (float)jj), __uint_as_float(v[jj]) * scale2);
+                    const float dist = fabsf(dbase - (float)jj);
+                    const float x = fmaf(-slope, dist, __uint_as_float(v[jj]) * scale2);
                     float e = exp2f(x - m_use);
                     if (bits != 0xffffffffu) e = ((bits >> jj) & 1u) ? e : 0.f;
                     rsum += e;
+                    dsum = fmaf(e, dist, dsum);
                     v[jj] = __float_as_uint(e);
                 }
                 if (drop_on) {
@@ -240,6 +243,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             }
             l_run = l_run * corr + rsum;
+            d_run = d_run * corr + dsum;
             fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
@@ -270,6 +274,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 *reinterpret_cast<uint4*>(dst + d) = u;
             }
             if (p.lse != nullptr) p.lse[((size_t)b * NH + h) * T + i] = l_run > 0.f ? (m_run + log2f(l_run)) : INFINITY;
+            if (p.edist != nullptr) p.edist[((size_t)b * NH + h) * T + i] = d_run * inv;
         }
     }
     tc_fence_before();
@@ -291,10 +296,11 @@ __global__ void mask_bits_kernel(const uint8_t* __restrict__ mask, uint32_t* __r
 }  // namespace
 
 // tcgen05 forward.  Same contract as spb_attention_fwd plus `mask_bits_scratch` (uint32 [B, ceil(T/32)], only touched when
-// key_mask != NULL).  Requires H == 4, dim_head == 64, ld and ld_out multiples of 8.
+// key_mask != NULL; the backward reads it again) and `edist` (fp32 [B, H, T] or NULL): E_i[|i-j|] under the attention weights,
+// which spb_attention_bwd_tc needs for the slope gradient.  Requires H == 4, dim_head == 64, ld and ld_out multiples of 8.
 extern "C" int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_mask, uint32_t* mask_bits_scratch, const float* logslopes,
-                                    void* out, int ld_out, float* lse, int B, int T, int H, int dim_head, int causal, float dropout_p,
-                                    uint64_t seed, const uint64_t* rng_offset, cudaStream_t stream) {
+                                    void* out, int ld_out, float* lse, float* edist, int B, int T, int H, int dim_head, int causal,
+                                    float dropout_p, uint64_t seed, const uint64_t* rng_offset, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return SPB_OK;
     SPB_CHECK_ARG(qkv && logslopes && out, "spb_attention_fwd_tc: null pointer");
     SPB_CHECK_ARG(H == NH && dim_head == DH, "spb_attention_fwd_tc: needs 4 heads of dim 64 (got %d x %d)", H, dim_head);
@@ -318,6 +324,7 @@ extern "C" int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ld_out = ld_out;
     p.lse = lse;
+    p.edist = edist;
     p.B = B; p.T = T;
     p.scale = 1.f / sqrtf((float)dim_head);
     p.causal = causal;
@@ -332,11 +339,7 @@ extern "C" int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_
     p.keep_scale = 1.f / (1.f - dropout_p);
     p.kcol = H * DH;
     p.vcol = H * DH + DH;
-    static bool configured = false;
-    if (!configured) {
-        SPB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        configured = true;
-    }
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attn_fwd_tc_kernel<<<dim3(ceil_div(T, QP), B), 160, TC_SMEM_BYTES, stream>>>(tmQ, tmKV, p);
     SPB_CHECK_LAUNCH();
     return SPB_OK;

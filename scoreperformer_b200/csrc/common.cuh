@@ -340,3 +340,6 @@ int spb_make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uin
 // 3-D bf16 tensor map [d2][d1][d0] (d0 contiguous) with 128-byte swizzle and a {box0, box1, 1} box; out-of-range rows read as zero.
 int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                           uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+// same for fp32 elements (box0 * 4 must be <= 128 bytes); used for tensor reduce-adds that must clip at a sequence end
+int spb_make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                         uint64_t stride2_bytes, uint32_t box0, uint32_t box1);

@@ -601,8 +601,8 @@ int spb_make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uin
     return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
 
-int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                          uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+static int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
     PFN_encodeTiled fn = get_encode_fn();
     if (fn == nullptr) {
         spb_set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -614,7 +614,7 @@ int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint6
     cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -622,6 +622,15 @@ int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint6
         return SPB_ERR_DRIVER;
     }
     return SPB_OK;
+}
+
+int spb_make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                          uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+    return make_tmap_3d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, d0, d1, d2, stride1_bytes, stride2_bytes, box0, box1);
+}
+int spb_make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                         uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+    return make_tmap_3d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, d0, d1, d2, stride1_bytes, stride2_bytes, box0, box1);
 }
 
 static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K, int trans_a, int trans_b, int lda, int ldb, int ldc,

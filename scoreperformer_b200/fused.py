@@ -236,17 +236,17 @@ class AttentionCoreFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, mask, logslopes, B, T, H, causal, dropout_p, seed):
         ls = logslopes.detach().reshape(-1).contiguous()
-        o, lse = K.attention_fwd(qkv, mask, ls, B, T, H, causal, dropout_p, seed)
-        ctx.saved = (qkv, mask, ls, o, lse)
+        o, lse, aux = K.attention_fwd(qkv, mask, ls, B, T, H, causal, dropout_p, seed)
+        ctx.saved = (qkv, mask, ls, o, lse, aux)
         ctx.meta = (B, T, H, causal, dropout_p, seed, logslopes.shape)
         return o
 
     @staticmethod
     def backward(ctx, do):
-        qkv, mask, ls, o, lse = ctx.saved
+        qkv, mask, ls, o, lse, aux = ctx.saved
         B, T, H, causal, dropout_p, seed, ls_shape = ctx.meta
         dls = torch.zeros(H, dtype=F32, device=qkv.device)
-        dqkv = K.attention_bwd(qkv, mask, ls, o, do.contiguous(), lse, dls, B, T, H, causal, dropout_p, seed)
+        dqkv = K.attention_bwd(qkv, mask, ls, o, do.contiguous(), lse, dls, B, T, H, causal, dropout_p, seed, aux=aux)
         return dqkv, None, dls.view(ls_shape), None, None, None, None, None, None
 
 
@@ -341,12 +341,12 @@ class TransformerStackFn(torch.autograd.Function):
             wqkv16 = w16_cat([to_q, to_k, to_v])
             qkv = K.gemm(xn, wqkv16, out_dtype=BF16)
             ls = logslopes.detach().reshape(-1).contiguous()
-            o, lse = K.attention_fwd(qkv, mask, ls, B, T, H, spec.causal, p_attn, seeds[2 * l])
+            o, lse, aux = K.attention_fwd(qkv, mask, ls, B, T, H, spec.causal, p_attn, seeds[2 * l], need_aux=keep)
             wo16 = w16(to_out)
             nxt = K.gemm(o, wo16, residual=cur, rowmask=None if mask is None else mask.view(-1), out_dtype=F32)
             if spec.return_hiddens:
                 kvs[l].copy_(qkv[:, H * dh:])
-            rec_a = dict(x=cur, mean=mean, rstd=rstd, xn=xn, wqkv16=wqkv16, qkv=qkv, ls=ls, o=o, lse=lse, wo16=wo16) if keep else None
+            rec_a = dict(x=cur, mean=mean, rstd=rstd, xn=xn, wqkv16=wqkv16, qkv=qkv, ls=ls, o=o, lse=lse, wo16=wo16, aux=aux) if keep else None
             cur = nxt
             # ---- feed-forward sub-layer
             proj_w, proj_b, out_w = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
@@ -454,7 +454,7 @@ class TransformerStackFn(torch.autograd.Function):
             do, delta = K.gemm_rowdot(g16, rec_a["wo16"], rec_a["o"], T, H, trans_b=True)
             dls, d_ls = take(p_ls)
             dqkv = K.attention_bwd(rec_a["qkv"], mask, rec_a["ls"], rec_a["o"], do, rec_a["lse"], dls, B, T, H, spec.causal, p_attn,
-                                   ctx.seeds[2 * l], delta=delta)
+                                   ctx.seeds[2 * l], delta=delta, aux=rec_a["aux"])
             grads[base + 6] = None if d_ls else dls.view(p_ls.shape)
             g_qkv = direct_grad_cat([p_q, p_k, p_v])
             with side(dqkv, rec_a["xn"]):

@@ -18,9 +18,9 @@ LAUNCHES = 0
 # Optional device-side uint64 counter mixed into every dropout seed (set by train_step.TrainStep): kernels captured in a CUDA
 # graph read it at run time, so replays draw fresh masks although the host-side seeds were baked in at capture.
 RNG_OFFSET: Optional[Tensor] = None
-# "tcgen05" (TMEM/TMA kernel, needs 4 heads) or "mma" (legacy mma.sync kernel); SPB_ATTN_FWD overrides.
+# "tcgen05" (TMEM/TMA forward + backward kernels, need 4 heads) or "mma" (legacy mma.sync kernels); SPB_ATTN overrides.
 import os as _os
-ATTENTION_FWD_IMPL = _os.environ.get("SPB_ATTN_FWD", "mma")
+ATTENTION_IMPL = _os.environ.get("SPB_ATTN", "tcgen05")
 
 
 def _count(n: int = 1) -> None:
@@ -227,31 +227,70 @@ def embed_ln_bwd(dy: Tensor, tokens: Tensor, table: Tensor, sizes: Sequence[int]
 
 
 # ----------------------------------------------------------------------------- attention
+class AttnAux:
+    """Side outputs of the tcgen05 forward that its backward consumes: key-validity bit words and E_i[|i-j|]."""
+    __slots__ = ("impl", "mask_bits", "edist")
+
+    def __init__(self, impl: str, mask_bits: Optional[Tensor] = None, edist: Optional[Tensor] = None):
+        self.impl, self.mask_bits, self.edist = impl, mask_bits, edist
+
+
+def attention_impl(H: int) -> str:
+    """"tcgen05" (TMEM/TMA kernels, need 4 heads) unless SPB_ATTN=mma selects the legacy mma.sync kernels."""
+    return "tcgen05" if (H == 4 and ATTENTION_IMPL == "tcgen05") else "mma"
+
+
 def attention_fwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, B: int, T: int, H: int, causal: bool,
-                  dropout_p: float, seed: int):
-    """qkv bf16 [B*T, H*64+128] -> (out bf16 [B*T, H*64], lse fp32 [B,H,T])."""
+                  dropout_p: float, seed: int, impl: Optional[str] = None, need_aux: bool = True):
+    """qkv bf16 [B*T, H*64+128] -> (out bf16 [B*T, H*64], lse fp32 [B,H,T], aux).  `aux` goes to attention_bwd unchanged."""
     _require_cuda(qkv)
     assert qkv.dtype == BF16 and qkv.stride(1) == 1 and logslopes.dtype == F32
     out = torch.empty((B * T, H * 64), dtype=BF16, device=qkv.device)
     lse = torch.empty((B, H, T), dtype=F32, device=qkv.device)
-    if H == 4 and ATTENTION_FWD_IMPL == "tcgen05":
+    impl = impl or attention_impl(H)
+    if impl == "tcgen05":
         bits = torch.empty((B, (T + 31) // 32), dtype=torch.int32, device=qkv.device) if key_mask is not None else None
+        edist = torch.empty((B, H, T), dtype=F32, device=qkv.device) if need_aux else None
         _call("spb_attention_fwd_tc", _p(qkv), qkv.stride(0), _p(key_mask), _p(bits), _p(logslopes), _p(out), out.stride(0), _p(lse),
-              B, T, H, 64, int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
+              _p(edist), B, T, H, 64, int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
         _count(2 if key_mask is not None else 1)
-        return out, lse
+        return out, lse, AttnAux("tcgen05", bits, edist)
     _call("spb_attention_fwd", _p(qkv), qkv.stride(0), _p(key_mask), _p(logslopes), _p(out), out.stride(0), _p(lse), B, T, H, 64,
           int(causal), float(dropout_p), seed, _p(RNG_OFFSET), _stream())
     _count()
-    return out, lse
+    return out, lse, AttnAux("mma")
+
+
+_DQ_ACC = {}
+
+
+def _dq_accumulator(n: int, cols: int, device) -> Tensor:
+    """fp32 [n, cols] scratch of the tcgen05 backward: zero between calls (the kernel's last pass re-zeroes it), one per
+    (stream, shape), so backward branches running on different streams never share one."""
+    key = (torch.cuda.current_stream().cuda_stream, n, cols, str(device))
+    buf = _DQ_ACC.get(key)
+    if buf is None:
+        buf = _DQ_ACC[key] = torch.zeros((n, cols), dtype=F32, device=device)
+    return buf
 
 
 def attention_bwd(qkv: Tensor, key_mask: Optional[Tensor], logslopes: Tensor, out: Tensor, dout: Tensor, lse: Tensor,
                   dlogslopes: Tensor, B: int, T: int, H: int, causal: bool, dropout_p: float, seed: int,
-                  delta: Optional[Tensor] = None) -> Tensor:
-    """`delta` fp32 [B, H, T] = rowsum(dO * O) may be supplied (gemm_rowdot produces it with dO); otherwise it is computed here."""
+                  delta: Optional[Tensor] = None, aux: Optional[AttnAux] = None) -> Tensor:
+    """`delta` fp32 [B, H, T] = rowsum(dO * O) may be supplied (gemm_rowdot produces it with dO); otherwise it is computed here.
+    `aux` is what attention_fwd returned: it selects the matching backward implementation."""
     assert dout.dtype == BF16 and dout.stride(1) == 1 and dout.stride(0) == out.stride(0)
     dqkv = torch.empty_like(qkv)
+    if aux is not None and aux.impl == "tcgen05":
+        assert aux.edist is not None, "the tcgen05 backward needs the forward's edist (attention_fwd(need_aux=True))"
+        if delta is None:
+            delta = (dout.float().view(B, T, H, 64) * out.float().view(B, T, H, 64)).sum(-1).permute(0, 2, 1).contiguous()
+        acc = _dq_accumulator(B * T, H * 64, qkv.device)
+        _call("spb_attention_bwd_tc", _p(qkv), qkv.stride(0), _p(aux.mask_bits), _p(logslopes), _p(dout), dout.stride(0), _p(lse),
+              _p(delta), _p(aux.edist), _p(acc), _p(dqkv), dqkv.stride(0), _p(dlogslopes), B, T, H, 64, int(causal), float(dropout_p),
+              seed, _p(RNG_OFFSET), _stream())
+        _count(2)
+        return dqkv
     ready = delta is not None
     if delta is None:
         delta = torch.empty((B, H, T), dtype=F32, device=qkv.device)

@@ -15,7 +15,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libspb200.so")
-SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "latents.cu", "heads.cu", "head_ce.cu", "tables.cu", "optim.cu"]
+SOURCES = ["api.cu", "gemm.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "latents.cu", "heads.cu", "head_ce.cu", "tables.cu", "optim.cu"]
 
 _P, _I, _F, _L, _U64 = c_void_p, c_int, c_float, c_int64, c_uint64
 
@@ -33,7 +33,8 @@ SIGNATURES = {
     "spb_embed_ln_fwd": [_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _F, _P],
     "spb_embed_ln_bwd": [_P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "spb_attention_fwd": [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
-    "spb_attention_fwd_tc": [_P, _I, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
+    "spb_attention_fwd_tc": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
+    "spb_attention_bwd_tc": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _P],
     "spb_attention_bwd": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _U64, _P, _I, _P],
     "spb_attention_decode": [_P, _I, _P, _I, c_longlong, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "spb_latent_level_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -16,9 +16,10 @@ qkv = torch.randn(64 * 512, 384, device="cuda").bfloat16()
 mask = torch.ones(64, 512, dtype=torch.bool, device="cuda")
 ls = torch.log(torch.tensor([0.25, 0.0625, 0.015625, 0.0039], device="cuda"))
 for impl in ("mma", "tcgen05"):
-    K.ATTENTION_FWD_IMPL = impl
     for _ in range(2):
         flush.zero_()
-        K.attention_fwd(qkv, mask, ls, 64, 512, 4, False, 0.1, 1)
+        out, lse, aux = K.attention_fwd(qkv, mask, ls, 64, 512, 4, False, 0.1, 1, impl=impl)
+        flush.zero_()
+        K.attention_bwd(qkv, mask, ls, out, torch.randn_like(out), lse, torch.zeros(4, device="cuda"), 64, 512, 4, False, 0.1, 1, aux=aux)
 torch.cuda.synchronize()
 print("done")

@@ -238,8 +238,12 @@ def ref_attention(qkv, mask, logslopes, B, T, H, causal):
     return torch.einsum("bhij,bjd->bhid", p, v).transpose(1, 2).reshape(B * T, H * 64)
 
 
-@pytest.mark.parametrize("B,T,causal", [(2, 64, False), (3, 47, True), (2, 200, False), (2, 511, True), (1, 130, True)])
-def test_attention_fwd_bwd(k, B, T, causal):
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("B,T,causal", [(2, 64, False), (3, 47, True), (2, 200, False), (2, 511, True), (1, 130, True), (2, 511, False),
+                                        (2, 2048, True), (1, 2048, False)])
+def test_attention_fwd_bwd(k, B, T, causal, impl):
+    """Both implementations (tcgen05/TMEM/TMA default, legacy mma.sync) against the fp32 statement of attend.py:58-126: ragged
+    key-padding masks, causal and not, sequence lengths off the tile grid (47, 130, 511) and the long-context length."""
     torch.manual_seed(6)
     H = 4
     qkv = randn(B * T, H * 64 + 128, dtype=BF16)
@@ -250,12 +254,14 @@ def test_attention_fwd_bwd(k, B, T, causal):
     qr = qkv.float().requires_grad_(True)
     lr = logslopes.clone().requires_grad_(True)
     ref = ref_attention(qr, mask, lr, B, T, H, causal)
-    out, lse = k.attention_fwd(qkv, mask, logslopes, B, T, H, causal, 0.0, 0)
+    out, lse, aux = k.attention_fwd(qkv, mask, logslopes, B, T, H, causal, 0.0, 0, impl=impl)
     assert rel_err(out, ref) < 1.5e-2
     dout = randn(B * T, H * 64, dtype=BF16)
     ref.backward(dout.float())
     dls = torch.zeros(H, device="cuda")
-    dqkv = k.attention_bwd(qkv, mask, logslopes, out, dout, lse, dls, B, T, H, causal, 0.0, 0)
+    dqkv = k.attention_bwd(qkv, mask, logslopes, out, dout, lse, dls, B, T, H, causal, 0.0, 0, aux=aux)
+    if impl == "tcgen05":      # the fp32 dQ accumulator must be handed back zeroed
+        assert float(k._dq_accumulator(B * T, H * 64, qkv.device).abs().max()) == 0.0
     assert cos_dist(dqkv[:, :256], qr.grad[:, :256]) < 1e-3
     assert cos_dist(dqkv[:, 256:320], qr.grad[:, 256:320]) < 1e-3
     assert cos_dist(dqkv[:, 320:], qr.grad[:, 320:]) < 1e-3
@@ -263,21 +269,22 @@ def test_attention_fwd_bwd(k, B, T, causal):
     assert rel_err(dls, lr.grad) < 3e-2
 
 
-def test_attention_dropout_consistency(k):
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+def test_attention_dropout_consistency(k, impl):
     """Backward must regenerate the forward's dropout mask: finite-difference-free check via linearity in V."""
     torch.manual_seed(7)
     B, T, H = 2, 96, 4
     qkv = randn(B * T, H * 64 + 128, dtype=BF16)
     mask = torch.ones(B, T, dtype=torch.bool, device="cuda")
     ls = torch.log(torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda"))
-    out, lse = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 99)
-    out2, _ = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 99)
+    out, lse, aux = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 99, impl=impl)
+    out2, _, _ = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 99, impl=impl)
     assert torch.equal(out, out2)
-    out3, _ = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 100)
+    out3, _, _ = k.attention_fwd(qkv, mask, ls, B, T, H, False, 0.3, 100, impl=impl)
     assert not torch.equal(out, out3)
     # O is linear in V: <dO, O> == <dV, V> when dO is the upstream gradient
     dout = randn(B * T, H * 64, dtype=BF16)
-    dqkv = k.attention_bwd(qkv, mask, ls, out, dout, lse, torch.zeros(H, device="cuda"), B, T, H, False, 0.3, 99)
+    dqkv = k.attention_bwd(qkv, mask, ls, out, dout, lse, torch.zeros(H, device="cuda"), B, T, H, False, 0.3, 99, aux=aux)
     lhs = float((dout.float() * out.float()).sum())
     rhs = float((dqkv[:, 320:].float() * qkv[:, 320:].float()).sum())
     assert abs(lhs - rhs) / abs(lhs) < 3e-2

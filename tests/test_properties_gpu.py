@@ -118,11 +118,7 @@ def test_attention_rows_are_convex_combinations_full_size():
     mask = torch.arange(T, device="cuda")[None] < lengths[:, None]
     ls = torch.log(torch.tensor([0.25, 0.0625, 0.015625, 0.0039], device="cuda"))
     for impl in ("mma", "tcgen05"):
-        K.ATTENTION_FWD_IMPL = impl
-        try:
-            for causal in (False, True):
-                out, _ = K.attention_fwd(qkv, mask, ls, B, T, H, causal, 0.0, 0)
-                want = const.float()[:, None, None].expand(B, T, 256)
-                assert float((out.view(B, T, 256).float() - want).abs().max()) < 2e-2, (impl, causal)
-        finally:
-            K.ATTENTION_FWD_IMPL = "mma"
+        for causal in (False, True):
+            out, _, _ = K.attention_fwd(qkv, mask, ls, B, T, H, causal, 0.0, 0, impl=impl)
+            want = const.float()[:, None, None].expand(B, T, 256)
+            assert float((out.view(B, T, 256).float() - want).abs().max()) < 2e-2, (impl, causal)
