@@ -7,15 +7,11 @@
 //   O_part[128 x 64] = P[128 x 128] V         P goes registers -> bf16 -> 128B-swizzled smem (A operand), V is the MN-major B
 // Warp 4 owns all asynchronous work (TMA loads of Q / K / V tiles through 3-D tensor maps, MMA issue, commits); warps 0-3
 // own the arithmetic.  Two CTAs fit per SM (96 KB smem, 256 TMEM columns each) and overlap each other's MMA / softmax phases.
-#include "common.cuh"
+#include "attention_tc.cuh"
 
 namespace {
+using namespace attn_tc;
 
-constexpr int DH = 64;
-constexpr int QP = 32;        // query positions per CTA
-constexpr int NH = 4;         // query heads stacked into the M dimension
-constexpr int TKEY = 128;     // keys per tile
-constexpr float LOG2E = 1.4426950408889634f;
 
 constexpr int SQ_OFF = 0;
 constexpr int SK_OFF = 16384;           // 2 stages x 16 KB
@@ -37,15 +33,10 @@ struct TcParams {
     int causal;
     uint64_t seed;
     const uint64_t* rng_offset;
-    uint32_t thr16;
+    uint32_t thr32;
     float keep_scale;
     int kcol, vcol;
 };
-
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return x;
-}
 
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, TcParams p) {
@@ -143,12 +134,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         const float slope = __expf(p.logslopes[h]) * LOG2E;
         const float scale2 = p.scale * LOG2E;
-        uint64_t seed = p.seed;
-        if (p.rng_offset != nullptr) seed += *p.rng_offset * 0x9E3779B97F4A7C15ull;
-        const uint32_t seed32 = (uint32_t)(seed ^ (seed >> 32));
-        const uint32_t half_t = (uint32_t)((T + 1) >> 1);
-        const uint32_t row_lin = (uint32_t)((b * NH + h) * T + i);
-        const bool drop_on = p.thr16 != 0;
+        DropParams drop;
+        drop.seedmix = drop_seedmix(p.seed, p.rng_offset);
+        drop.thr32 = p.thr32;
+        drop.quarter_t = (uint32_t)((T + 3) >> 2);
+        drop.keep_scale = p.keep_scale;
+        const uint32_t drop_row = drop_row_base(drop, (uint32_t)((b * NH + h) * T + i));
+        const bool drop_on = p.thr32 != 0;
         uint8_t* sP = smem + SP_OFF;
 
         float o_reg[DH];
@@ -223,11 +215,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     v[jj] = __float_as_uint(e);
                 }
                 if (drop_on) {
+                    const uint32_t base = drop_row + (uint32_t)(j0 >> 2) * DROP_K;
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj += 2) {
-                        const uint32_t hsh = hash32((row_lin * half_t + (uint32_t)((j0 + jj) >> 1)) * 0x9E3779B9u + seed32);
-                        v[jj] = (hsh & 0xffffu) >= p.thr16 ? __float_as_uint(__uint_as_float(v[jj]) * p.keep_scale) : 0u;
-                        v[jj + 1] = (hsh >> 16) >= p.thr16 ? __float_as_uint(__uint_as_float(v[jj + 1]) * p.keep_scale) : 0u;
+                    for (int jj = 0; jj < 32; jj += 4) {
+                        const uint32_t qh = drop_quad(base + (uint32_t)(jj >> 2) * DROP_K);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            v[jj + e] = drop_keep(qh, e, drop.thr32) ? __float_as_uint(__uint_as_float(v[jj + e]) * drop.keep_scale) : 0u;
                     }
                 }
                 uint8_t* dst_row = sP + (c >> 1) * 16384 + r * 128;
@@ -330,12 +324,7 @@ extern "C" int spb_attention_fwd_tc(const void* qkv, int ld, const uint8_t* key_
     p.causal = causal;
     p.seed = seed;
     p.rng_offset = rng_offset;
-    const double t16 = (double)dropout_p * 65536.0;
-    // same quantisation as attention.cu (drop_thresh24 >> 8) so forward and backward agree on the mask
-    double t24 = (double)dropout_p * 16777216.0;
-    const uint32_t thr24 = dropout_p > 0.f ? (uint32_t)(t24 < 1 ? 1 : t24) : 0;
-    (void)t16;
-    p.thr16 = thr24 >> 8;
+    p.thr32 = host_drop_thr32(dropout_p);     // spb_attention_bwd_tc evaluates the same mask function (attention_tc.cuh)
     p.keep_scale = 1.f / (1.f - dropout_p);
     p.kcol = H * DH;
     p.vcol = H * DH + DH;

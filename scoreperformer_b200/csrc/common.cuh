@@ -119,6 +119,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity);
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -142,6 +143,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+
+// Same wait expanded at the call site, so profiler samples of a stalled wait are attributed to the line that waits.
+#define SPB_MBAR_WAIT(bar, parity)                                                        \
+    do {                                                                                  \
+        uint64_t* _b = (bar);                                                             \
+        const uint32_t _p = (parity);                                                     \
+        if (!mbar_try_wait(_b, _p)) {                                                     \
+            const long long _t0 = clock64();                                              \
+            while (!mbar_try_wait(_b, _p)) {                                              \
+                if (clock64() - _t0 > 4000000000ll) __trap();                             \
+            }                                                                             \
+        }                                                                                 \
+    } while (0)
 
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
