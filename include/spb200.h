@@ -73,6 +73,16 @@ int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p,
 int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p, uint64_t seed,
                 const uint64_t* rng_offset, spb_stream_t stream);
 
+/* Fused feed-forward sub-layer forward: out = resid + W2 . dropout(value * silu(gate)), [value | gate] = xn W1^T + b1
+ * (modules/transformer/feedforward.py:13-22,35-64 inside the pre-norm residual of transformer.py:139-232).  One tcgen05 kernel:
+ * the [n, 2*hidden] pre-activation and the [n, hidden] activation stay in TMEM / shared memory.  xn bf16 [n, dim]; w1 bf16
+ * [2*hidden, dim] (value rows, then gate rows); b1 fp32 [2*hidden]; w2 bf16 [dim, hidden]; resid fp32 or NULL; out fp32.
+ * u_save (bf16 [n, 2*hidden]) / h_save (bf16 [n, hidden]) are optional side outputs for the backward (same dropout mask function
+ * as spb_glu_fwd / spb_glu_bwd).  Built for dim 256, hidden 1024. */
+int spb_ffn_fwd(const void* xn, int ld_xn, const void* w1, const float* b1, const void* w2, const float* resid, int ld_res, float* out,
+                int ld_out, void* u_save, void* h_save, int n_rows, int dim, int hidden, float dropout_p, uint64_t seed,
+                const uint64_t* rng_offset, spb_stream_t stream);
+
 /* Computed per-field tables W_f = index rows {discrete ids} + MLP(token_values) (modules/transformer/embeddings.py:124-143,199-211),
  * all fields in one launch.  ptrs is a HOST array of device pointers, 7 per field for the forward (index_weight [V,128], token_values
  * [V], discrete mask [V] fp32 0/1, W0 [128], b0 [128], W1 [128,128], b1 [128]) and 12 per field for the backward (+ the five gradient

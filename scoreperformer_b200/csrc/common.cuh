@@ -52,6 +52,13 @@ static inline int spb_num_sms() {
 
 __host__ __device__ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// drop when hash < threshold: 32-bit threshold of a drop probability (0 = dropout off)
+static inline uint32_t spb_drop_thr32(float p) {
+    if (p <= 0.f) return 0u;
+    const double t = (double)p * 4294967296.0;
+    return t < 1.0 ? 1u : (t > 4294967295.0 ? 4294967295u : (uint32_t)t);
+}
+
 // ----------------------------------------------------------------------------- small device utils
 #ifdef __CUDACC__
 
@@ -102,6 +109,18 @@ __device__ __forceinline__ uint32_t spb_pair_hash(uint32_t seed32, uint32_t pair
 // half = 0 / 1 selects the element of the pair; thr16 = drop_thresh24 >> 8
 __device__ __forceinline__ bool spb_keep16(uint32_t pair_hash, int half, uint32_t thr16) {
     return ((pair_hash >> (16 * half)) & 0xFFFFu) >= thr16;
+}
+
+// Cheapest form, for kernels bound by their element-wise instruction stream (GLU inside the fused feed-forward, attention):
+// ONE weak 32-bit mix per FOUR adjacent elements of a row; the four decisions are the products of it with four odd constants,
+// each compared with a 32-bit threshold (keep-probability resolution 2^-32).  quad_idx = (row * row_len + col) / 4.
+__device__ __forceinline__ uint32_t spb_quad_hash(uint32_t seed32, uint32_t quad_idx) {
+    const uint32_t pre = quad_idx * 0x9E3779B9u + seed32;
+    return (pre ^ (pre >> 15)) * 0x846ca68bu;
+}
+__device__ __forceinline__ bool spb_quad_keep(uint32_t quad_hash, int k, uint32_t thr32) {      // k = col & 3 (compile-time in the loops)
+    const uint32_t mul = k == 0 ? 1u : (k == 1 ? 0x7feb352du : (k == 2 ? 0xc2b2ae35u : 0x27d4eb2fu));
+    return quad_hash * mul >= thr32;
 }
 
 // ----------------------------------------------------------------------------- PTX: mbarrier / TMA / tcgen05

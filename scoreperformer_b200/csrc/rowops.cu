@@ -187,9 +187,9 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const Tin* __restr
 // u: [n, 2H] (value | gate) -> h[n, H] = value * silu(gate) * dropout_keep / (1-p);  8 elements (16 bytes) per thread
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, int n_rows, int H, uint64_t seed,
-               const uint64_t* __restrict__ rng_offset, uint32_t drop_thresh24, float keep_scale) {
+               const uint64_t* __restrict__ rng_offset, uint32_t thr32, float keep_scale) {
     if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
-    const uint32_t seed32 = spb_seed32(seed), thr16 = drop_thresh24 >> 8;
+    const uint32_t seed32 = spb_seed32(seed);
     const int per_row = H / 8;
     const int64_t total = (int64_t)n_rows * per_row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -198,18 +198,18 @@ glu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ 
         float xs[8], gs[8], o[8];
         Ld8<__nv_bfloat16>::load(u + (size_t)row * 2 * H + c, xs);
         Ld8<__nv_bfloat16>::load(u + (size_t)row * 2 * H + H + c, gs);
-        const uint32_t pair0 = (uint32_t)row * (uint32_t)(H >> 1) + (uint32_t)(c >> 1);
+        const uint32_t quad0 = (uint32_t)row * (uint32_t)(H >> 2) + (uint32_t)(c >> 2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float sig = 1.f / (1.f + __expf(-gs[j]));
             o[j] = xs[j] * gs[j] * sig;
         }
-        if (drop_thresh24 != 0) {
+        if (thr32 != 0) {         // the mask function of the fused feed-forward kernel (ffn.cu) and of glu_bwd_kernel
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                const uint32_t hsh = spb_pair_hash(seed32, pair0 + (uint32_t)(j >> 1));
-                o[j] = spb_keep16(hsh, 0, thr16) ? o[j] * keep_scale : 0.f;
-                o[j + 1] = spb_keep16(hsh, 1, thr16) ? o[j + 1] * keep_scale : 0.f;
+            for (int j = 0; j < 8; j += 4) {
+                const uint32_t qh = spb_quad_hash(seed32, quad0 + (uint32_t)(j >> 2));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[j + e] = spb_quad_keep(qh, e, thr32) ? o[j + e] * keep_scale : 0.f;
             }
         }
         Ld8<__nv_bfloat16>::store(h + (size_t)row * H + c, o);
@@ -224,9 +224,9 @@ template <int MAXG>
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
                float* __restrict__ dbias, int n_rows, int H, uint64_t seed, const uint64_t* __restrict__ rng_offset,
-               uint32_t drop_thresh24, float keep_scale) {
+               uint32_t thr32, float keep_scale) {
     if (rng_offset != nullptr) seed += *rng_offset * 0x9E3779B97F4A7C15ull;
-    const uint32_t seed32 = spb_seed32(seed), thr16 = drop_thresh24 >> 8;
+    const uint32_t seed32 = spb_seed32(seed);
     float sx[MAXG][4], sg[MAXG][4];
 #pragma unroll
     for (int k = 0; k < MAXG; ++k)
@@ -245,14 +245,10 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __rest
                 const float2 g0 = unpack_bf16x2(gv.x), g1 = unpack_bf16x2(gv.y);
                 float ds[4] = {d0.x, d0.y, d1.x, d1.y}, xs[4] = {x0.x, x0.y, x1.x, x1.y}, gs[4] = {g0.x, g0.y, g1.x, g1.y};
                 float ox[4], og[4];
-                if (drop_thresh24 != 0) {      // same (seed, pair) hashes as the forward kernel
-                    const uint32_t pair0 = (uint32_t)row * (uint32_t)(H >> 1) + (uint32_t)(c >> 1);
+                if (thr32 != 0) {      // same (seed, quad) hashes as the forward kernels
+                    const uint32_t qh = spb_quad_hash(seed32, (uint32_t)row * (uint32_t)(H >> 2) + (uint32_t)(c >> 2));
 #pragma unroll
-                    for (int j = 0; j < 4; j += 2) {
-                        const uint32_t hsh = spb_pair_hash(seed32, pair0 + (uint32_t)(j >> 1));
-                        ds[j] = spb_keep16(hsh, 0, thr16) ? ds[j] * keep_scale : 0.f;
-                        ds[j + 1] = spb_keep16(hsh, 1, thr16) ? ds[j + 1] * keep_scale : 0.f;
-                    }
+                    for (int j = 0; j < 4; ++j) ds[j] = spb_quad_keep(qh, j, thr32) ? ds[j] * keep_scale : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -544,7 +540,7 @@ extern "C" int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float
     int64_t blocks = (total + 255) / 256;
     if (blocks > spb_num_sms() * 16) blocks = spb_num_sms() * 16;
     glu_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), reinterpret_cast<__nv_bfloat16*>(h),
-                                                    n_rows, hidden, seed, rng_offset, drop_thresh(dropout_p), 1.f / (1.f - dropout_p));
+                                                    n_rows, hidden, seed, rng_offset, spb_drop_thr32(dropout_p), 1.f / (1.f - dropout_p));
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
@@ -555,7 +551,7 @@ extern "C" int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias
     SPB_CHECK_ARG(dh && u && du && hidden % 4 == 0 && hidden <= 4096, "spb_glu_bwd: bad arguments (hidden <= 4096, multiple of 4)");
     int grid = spb_num_sms() * 4;
     if (grid > n_rows) grid = n_rows;
-    const uint32_t th = drop_thresh(dropout_p);
+    const uint32_t th = spb_drop_thr32(dropout_p);
     const float ks = 1.f / (1.f - dropout_p);
     if (hidden <= 1024)
         glu_bwd_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),

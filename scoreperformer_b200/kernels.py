@@ -161,6 +161,31 @@ def glu_fwd(u: Tensor, dropout_p: float, seed: int) -> Tensor:
     return h
 
 
+def ffn_fwd(xn: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, resid: Optional[Tensor], dropout_p: float, seed: int,
+            save: bool = True):
+    """Fused feed-forward sub-layer (one tcgen05 kernel): resid + W2 . dropout(GLU(xn W1^T + b1)).
+    xn bf16 [n, 256]; w1 bf16 [2048, 256]; b1 fp32 [2048]; w2 bf16 [256, 1024]; resid fp32 [n, 256] or None.
+    Returns (out fp32 [n, 256], u bf16 [n, 2048] or None, h bf16 [n, 1024] or None): u / h are what the backward consumes."""
+    _require_cuda(xn, w1, w2)
+    n, dim = xn.shape
+    hidden = w2.shape[1]
+    assert xn.dtype == BF16 and w1.dtype == BF16 and w2.dtype == BF16 and b1.dtype == F32 and xn.stride(1) == 1
+    assert w1.is_contiguous() and w2.is_contiguous() and w1.shape == (2 * hidden, dim) and w2.shape == (dim, hidden)
+    out = torch.empty((n, dim), dtype=F32, device=xn.device)
+    u = torch.empty((n, 2 * hidden), dtype=BF16, device=xn.device) if save else None
+    h = torch.empty((n, hidden), dtype=BF16, device=xn.device) if save else None
+    if resid is not None:
+        assert resid.dtype == F32 and resid.stride(1) == 1
+    _call("spb_ffn_fwd", _p(xn), xn.stride(0), _p(w1), _p(b1), _p(w2), _p(resid), resid.stride(0) if resid is not None else 0, _p(out),
+          out.stride(0), _p(u), _p(h), n, dim, hidden, float(dropout_p), seed, _p(RNG_OFFSET), _stream())
+    _count()
+    return out, u, h
+
+
+def ffn_fused_ok(dim: int, hidden: int) -> bool:
+    return dim == 256 and hidden == 1024 and _os.environ.get("SPB_FFN", "fused") == "fused"
+
+
 def glu_bwd(dh: Tensor, u: Tensor, dbias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:
     assert dh.dtype == BF16 and dh.is_contiguous() and u.is_contiguous()
     n, two_h = u.shape

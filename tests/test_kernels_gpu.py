@@ -192,6 +192,38 @@ def test_glu(k, H):
     assert float(dud[:, :H][~m & (ref != 0)].abs().max()) == 0
 
 
+# ------------------------------------------------------------------ fused feed-forward sub-layer
+@pytest.mark.parametrize("n", [128, 333, 4099, 32768])
+def test_ffn_fused_forward(k, n):
+    """spb_ffn_fwd (one tcgen05 kernel, u / h on chip) against the fp32 statement of feedforward.py:13-22,56-64 plus the residual,
+    and against the unfused kernel chain it replaces: same side outputs u / h, same dropout mask."""
+    torch.manual_seed(11)
+    D, H = 256, 1024
+    xn = randn(n, D, dtype=BF16)
+    w1, b1, w2 = randn(2 * H, D, dtype=BF16, scale=D ** -0.5), randn(2 * H, scale=0.1), randn(D, H, dtype=BF16, scale=H ** -0.5)
+    resid = randn(n, D)
+    u_ref = xn.float() @ w1.float().t() + b1
+    a, g = u_ref.chunk(2, dim=-1)
+    h_ref = a * F.silu(g)
+    ref = resid + h_ref @ w2.float().t()
+    out, u, h = k.ffn_fwd(xn, w1, b1, w2, resid, 0.0, 0)
+    assert rel_err(u, u_ref) < 1e-2 and rel_err(h, h_ref) < 1e-2
+    assert rel_err(out, ref) < 1e-2
+    out2, _, _ = k.ffn_fwd(xn, w1, b1, w2, None, 0.0, 0, save=False)
+    assert rel_err(out2, ref - resid) < 1e-2
+    # the unfused chain on the same inputs (its u is rounded to bf16 before the GLU; the fused kernel keeps fp32 there)
+    u2 = k.gemm(xn, w1, bias=b1, out_dtype=BF16)
+    h2 = k.glu_fwd(u2, 0.0, 0)
+    out3 = k.gemm(h2, w2, residual=resid, out_dtype=F32)
+    assert rel_err(u, u2) < 1e-2 and rel_err(out, out3) < 1e-2
+    # dropout: the mask is the function spb_glu_fwd / spb_glu_bwd evaluate
+    outd, ud, hd = k.ffn_fwd(xn, w1, b1, w2, resid, 0.25, 77)
+    hd2 = k.glu_fwd(ud, 0.25, 77)
+    assert torch.equal(hd == 0, hd2 == 0) and rel_err(hd, hd2) < 1e-2
+    assert abs(float((hd != 0).float().mean()) - 0.75) < 0.02
+    assert rel_err(outd, resid + hd.float() @ w2.float().t()) < 1e-2
+
+
 # ------------------------------------------------------------------ tuple embedding
 @pytest.mark.parametrize("F_", [12, 10])
 def test_embed_ln(k, F_):
