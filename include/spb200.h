@@ -158,16 +158,20 @@ int spb_ce_rows(const float* logits, int ld, const int64_t* labels, int ld_lab, 
 /* Tied head of one tuple field fused with its cross-entropy (embeddings.py:345-353 + wrappers.py:49-59): the [n, V] logits
  * e_f . table_f^T stay in tensor memory; only loss_sum / count (ACCUMULATED), the optional bf16 gradient rows
  * dlogits = softmax - onehot (zero for ignored labels; columns [V, ld_d) zeroed) and the optional argmax leave the SM.
- * e bf16 [n, lde] (the field's 128 columns), table bf16 [V, ldt], V <= 256. */
+ * e bf16 [n, lde] (the field's 128 columns), table bf16 [V, ldt], V <= 256.
+ * stats (fp32 [3], ACCUMULATED, may be NULL) = the ScorePerformerEvaluator's sums over the labelled rows
+ * (models/scoreperformer/evaluator.py:38-46,72-104): #(argmax == label), sum |tv[argmax] - tv[label]|,
+ * sum_v softmax_v |tv[label] - tv[v]|, with tv = token_values (fp32 [V]; NULL leaves the two distances at 0). */
 int spb_head_ce(const void* e, int lde, const void* table, int ldt, int V, const int64_t* labels, int ld_lab, long long ignore_index,
-                float* loss_sum, float* count, void* dlogits, int ld_d, int* argmax, int n_rows, spb_stream_t stream);
+                float* loss_sum, float* count, void* dlogits, int ld_d, int* argmax, const float* token_values, float* stats,
+                int n_rows, spb_stream_t stream);
 
 /* Optimiser step on the flat buffers (experiments/optimizers.py:151-169): clip_grad_norm_(max_norm) + AdamW + bf16 shadow
  * refresh in one pass.  grad_norm = device scalar ||g||_2 before grad_scale (null / max_norm <= 0: no clipping);
- * step = device int64 with the 1-based step number. */
+ * step = device int64 with the 1-based step number; lr_dev = optional device scalar overriding lr (schedules under graph replay). */
 int spb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* grad_norm, float grad_scale,
                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, const int64_t* step,
-                   spb_stream_t stream);
+                   const float* lr_dev, spb_stream_t stream);
 
 /* Direction-classifier heads (models/classifiers/model.py:74-82,202-216): Dropout -> Linear(in_dim, C_g) -> weighted CE. */
 int spb_clf_heads(const float* x, int ldx, const uint8_t* rowmask, const int64_t* labels, int ld_lab, const float* W, const float* bias,

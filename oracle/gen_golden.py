@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 import ref_shim  # noqa: E402
 from weights import fill_model_  # noqa: E402
-from scoreperformer_b200.synthetic import make_batch  # noqa: E402
+from scoreperformer_b200.synthetic import make_batch, SyntheticTokenizer  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -131,14 +131,51 @@ def gen_train(name, B, T, seed):
         arrays[f"clf_logits/{key}"] = lg.detach().numpy()
     for k in GRAD_KEYS:
         arrays[f"grad/{k}"] = sd[k].grad.detach().numpy()
+    # the reference evaluator on these outputs (evaluator.py:48-106), recipe settings (base.yaml:195-198) and their complement
+    from scoreperformer.models.scoreperformer.evaluator import ScorePerformerEvaluator
+    recipe_ignore = ["Bar", "Position", "Pitch", "Duration", "TimeSig", "PositionShift", "NotesInOnset", "PositionInOnset"]
+    for tag, kw in (("recipe", dict(weighted_distance=True, ignore_keys=recipe_ignore)), ("plain", dict(weighted_distance=False))):
+        ev = ScorePerformerEvaluator(model, tokenizer=SyntheticTokenizer(), **kw)
+        metrics = ev({"labels": batch["labels"]}, out)
+        arrays[f"eval/{tag}/keys"] = np.array(list(metrics.keys()))
+        arrays[f"eval/{tag}/vals"] = np.array([float(v) for v in metrics.values()], dtype=np.float64)
     np.savez_compressed(os.path.join(GOLDEN_DIR, name), **arrays)
     print(name, "loss", float(out.loss), "n_z", len(rec.samples),
           {k: round(float(v), 5) for k, v in out.losses.items()})
 
 
+def gen_init(name, seed=23):
+    """Constructor parity: key order, shapes and a checksum of every tensor the UNMODIFIED reference constructor produces under
+    torch.manual_seed(seed) (same registration order => bit-identical initialisation)."""
+    ref_shim.install_stubs()
+    from scoreperformer.models import ScorePerformer
+    torch.manual_seed(seed)
+    model = ScorePerformer.init(ref_shim._wrap(ref_shim.default_model_config()))
+    sd = model.state_dict()
+    keys = list(sd.keys())
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, name), seed=seed, keys=np.array(keys),
+        shapes=np.array(["x".join(map(str, sd[k].shape)) for k in keys]),
+        sums=np.array([float(sd[k].double().sum()) for k in keys], dtype=np.float64),
+        abs_sums=np.array([float(sd[k].double().abs().sum()) for k in keys], dtype=np.float64),
+        first=np.array([float(sd[k].reshape(-1)[0]) if sd[k].numel() else 0.0 for k in keys], dtype=np.float64))
+    print(name, len(keys), "tensors")
+
+
 def gen_render(name, T, seed):
-    """Eval-mode encoders + cached greedy unmask_tokens for one score (generators.py:230-240)."""
+    """Eval-mode encoders + cached greedy unmask_tokens for one score (generators.py:230-240).  Every greedy decision is recorded
+    together with the gap between its two largest logits, so a test can demand exact tokens wherever the decision is not a
+    numerical coin toss."""
     from scoreperformer.modules.sampling import top_k
+    gaps, scales = [], []
+
+    def recording_top_k(logits, **kw):
+        top2 = logits.float().topk(2, dim=-1).values
+        gaps.append(float((top2[..., 0] - top2[..., 1]).min()))
+        finite = logits.float()[torch.isfinite(logits)]
+        scales.append(float(finite.abs().max()))           # banned tokens are -inf: the scale of the real logits
+        return top_k(logits, **kw)
+
     model, cfg = build()
     model.eval()
     batch = make_batch(1, T, seed=seed, full_length=True, deadpan_last=False)
@@ -151,15 +188,18 @@ def gen_render(name, T, seed):
         outs = {}
         for cached in (True, False):
             res = model.perf_decoder.unmask_tokens(
-                tokens, batch["masked_perf"], filter_logits_fn=top_k, filter_kwargs={"k": 1},
+                tokens, batch["masked_perf"], filter_logits_fn=recording_top_k if cached else top_k, filter_kwargs={"k": 1},
                 caches=None if cached else None, return_caches=False, disable_tqdm=True,
                 context=enc.score_embeddings, style_embeddings=enc.perf_embeddings)
             outs[cached] = res
     np.savez_compressed(
         os.path.join(GOLDEN_DIR, name), T=T, seed=seed,
         score_embeddings=enc.score_embeddings.numpy(), perf_embeddings=enc.perf_embeddings.numpy(),
-        tokens_in=tokens.numpy(), tokens_out=outs[True].numpy())
-    print(name, "rendered", T, "notes; changed fields:", int((outs[True] != tokens).sum()))
+        tokens_in=tokens.numpy(), tokens_out=outs[True].numpy(),
+        top2_gaps=np.array(gaps, dtype=np.float32),        # one per sampled field, in decoding order (note-major, then field)
+        logit_scales=np.array(scales, dtype=np.float32))   # max |logit| of the same decisions
+    print(name, "rendered", T, "notes; changed fields:", int((outs[True] != tokens).sum()), "decisions:", len(gaps),
+          "min top-2 gap:", min(gaps) if gaps else None)
 
 
 def gen_known_answers(name):
@@ -192,3 +232,5 @@ if __name__ == "__main__":
     gen_train("train_b2_t48.npz", 2, 48, seed=1234)
     gen_train("train_b3_t33.npz", 3, 33, seed=77)     # ragged: T-1 = 32, odd sizes
     gen_render("render_t24.npz", 24, seed=5)
+    gen_render("render_t256.npz", 256, seed=9)
+    gen_init("init_seed23.npz", seed=23)

@@ -281,6 +281,10 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same without the release fence: for signals that order nothing but tensor-memory reads (tcgen05.fence covers those)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, the byte count on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
     asm volatile(

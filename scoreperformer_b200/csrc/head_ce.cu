@@ -35,6 +35,9 @@ struct HeadCeParams {
     __nv_bfloat16* dlogits;     // [n_rows, ld_d] or null
     int ld_d;
     int* argmax;                // [n_rows] or null
+    const float* token_values;  // fp32 [V]: the value a token of this field stands for (evaluator distances), or null
+    float* stats;               // [3] accumulated over labelled rows: #(argmax == label), sum |tv[argmax] - tv[label]|,
+                                //     sum_v softmax_v |tv[label] - tv[v]|  (evaluator.py:38-46,72-104); or null
 };
 
 __global__ void __launch_bounds__(HC_THREADS, 1)
@@ -50,6 +53,7 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* acc_full = bars + 5;      // [2]
     uint64_t* acc_empty = bars + 7;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* s_tv = reinterpret_cast<float*>(bars + 16);          // token values of the field (HC_MAXN floats)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = (p.n_rows + HC_BM - 1) / HC_BM;
@@ -67,6 +71,8 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (p.stats != nullptr)
+        for (int i = threadIdx.x; i < HC_MAXN; i += HC_THREADS) s_tv[i] = (p.token_values != nullptr && i < p.V) ? p.token_values[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -120,6 +126,9 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int V = p.V;
         const int nchunk = (V + 31) / 32;
         float loss_acc = 0.f, cnt_acc = 0.f;
+        float hit_acc = 0.f, dist_acc = 0.f, wdist_acc = 0.f;      // evaluator statistics of the labelled rows
+        const bool stats_on = p.stats != nullptr;
+        const bool wdist_on = stats_on && p.token_values != nullptr;
         uint32_t ph = 0;
         int it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
@@ -145,8 +154,13 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             if (p.argmax != nullptr && row < p.n_rows) p.argmax[row] = amax;
-            // pass 2: sum of exponentials and the label's logit
-            float se = 0.f, xl = 0.f;
+            const float tv_lab = (wdist_on && use) ? s_tv[(int)lab] : 0.f;
+            if (stats_on && use) {
+                hit_acc += amax == (int)lab ? 1.f : 0.f;
+                dist_acc += fabsf(s_tv[amax] - tv_lab);
+            }
+            // pass 2: sum of exponentials and the label's logit (and, for the evaluator, the expected |value - target|)
+            float se = 0.f, xl = 0.f, wd = 0.f;
             const float mxs = mx * HC_LOG2E;
             for (int c = 0; c < nchunk; ++c) {
                 uint32_t v[32];
@@ -155,13 +169,18 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float x = __uint_as_float(v[j]);
-                    if (c * 32 + j < V) se += exp2f(fmaf(x, HC_LOG2E, -mxs));
+                    if (c * 32 + j < V) {
+                        const float ex = exp2f(fmaf(x, HC_LOG2E, -mxs));
+                        se += ex;
+                        if (wdist_on) wd = fmaf(ex, fabsf(tv_lab - s_tv[c * 32 + j]), wd);
+                    }
                     if (c * 32 + j == (int)lab) xl = x;
                 }
             }
             if (use) {
                 loss_acc += mx + __logf(se) - xl;
                 cnt_acc += 1.f;
+                if (wdist_on) wdist_acc += wd / se;
             }
             // pass 3: gradient rows (bf16), 16 bytes at a time; columns [V, ld_d) are written as zeros
             if (p.dlogits != nullptr) {
@@ -199,9 +218,19 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         loss_acc = warp_sum(loss_acc);
         cnt_acc = warp_sum(cnt_acc);
+        if (stats_on) {
+            hit_acc = warp_sum(hit_acc);
+            dist_acc = warp_sum(dist_acc);
+            wdist_acc = warp_sum(wdist_acc);
+        }
         if (lane == 0 && cnt_acc > 0.f) {
             atomicAdd(p.loss_sum, loss_acc);
             atomicAdd(p.count, cnt_acc);
+            if (stats_on) {
+                atomicAdd(p.stats, hit_acc);
+                atomicAdd(p.stats + 1, dist_acc);
+                atomicAdd(p.stats + 2, wdist_acc);
+            }
         }
     }
     __syncwarp();
@@ -210,16 +239,18 @@ head_ce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-constexpr int HC_SMEM = 2 * HC_MAXN * 128 + 2 * HC_A_STAGE + 1024 + 256;
+constexpr int HC_SMEM = 2 * HC_MAXN * 128 + 2 * HC_A_STAGE + 1024 + 128 + HC_MAXN * 4;
 
 }  // namespace
 
 // e bf16 [n_rows, lde] (the 128 columns of this field), table bf16 [V, 128] (ldt = row stride), labels int64 with stride
 // ld_lab.  loss_sum / count are ACCUMULATED into.  dlogits bf16 [n_rows, ld_d] (ld_d >= V, multiple of 8) and argmax int32
-// [n_rows] are optional.
+// [n_rows] are optional.  `stats` (fp32 [3], accumulated; may be NULL) receives the evaluator's sums over the labelled rows:
+// #(argmax == label), sum |tv[argmax] - tv[label]| and sum_v softmax_v |tv[label] - tv[v]| with tv = `token_values` (fp32 [V];
+// NULL: only the hit count) -- models/scoreperformer/evaluator.py:38-46,72-104 without materialising the logits.
 extern "C" int spb_head_ce(const void* e, int lde, const void* table, int ldt, int V, const int64_t* labels, int ld_lab,
-                           long long ignore_index, float* loss_sum, float* count, void* dlogits, int ld_d, int* argmax, int n_rows,
-                           cudaStream_t stream) {
+                           long long ignore_index, float* loss_sum, float* count, void* dlogits, int ld_d, int* argmax,
+                           const float* token_values, float* stats, int n_rows, cudaStream_t stream) {
     if (n_rows <= 0) return SPB_OK;
     SPB_CHECK_ARG(e && table && labels && loss_sum && count, "spb_head_ce: null pointer");
     SPB_CHECK_ARG(V > 0 && V <= HC_MAXN, "spb_head_ce: field vocabulary must be in 1..%d, got %d", HC_MAXN, V);
@@ -238,6 +269,7 @@ extern "C" int spb_head_ce(const void* e, int lde, const void* table, int ldt, i
     p.labels = labels; p.ld_lab = ld_lab; p.ignore_index = ignore_index;
     p.loss_sum = loss_sum; p.count = count;
     p.dlogits = reinterpret_cast<__nv_bfloat16*>(dlogits); p.ld_d = ld_d; p.argmax = argmax;
+    p.token_values = token_values; p.stats = stats;
     static bool configured = false;
     if (!configured) {
         SPB_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HC_SMEM));

@@ -14,7 +14,9 @@ namespace {
 __global__ void __launch_bounds__(256)
 adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   __nv_bfloat16* __restrict__ shadow, int64_t n4, const float* __restrict__ grad_norm, float grad_scale, float max_norm,
-                  float lr, float beta1, float beta2, float eps, float weight_decay, const int64_t* __restrict__ step) {
+                  float lr, const float* __restrict__ lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                  const int64_t* __restrict__ step) {
+    if (lr_dev != nullptr) lr = *lr_dev;       // schedulers write the rate on the device: a captured graph never has to be rebuilt
     const float t = (float)(*step);
     const float bc1 = 1.f - powf(beta1, t);
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
@@ -58,9 +60,10 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
 
 // p / g / m / v fp32 [n] (n % 4 == 0, 16-byte aligned); shadow bf16 [n] or null.  grad_norm: device scalar holding the L2 norm of
 // g BEFORE grad_scale (null or max_norm <= 0 disables clipping).  step: device int64 holding the 1-based step number t.
+// lr_dev: optional device scalar that overrides `lr` (learning-rate schedules under CUDA-graph replay).
 extern "C" int spb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, int64_t n, const float* grad_norm,
                               float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                              const int64_t* step, cudaStream_t stream) {
+                              const int64_t* step, const float* lr_dev, cudaStream_t stream) {
     if (n <= 0) return SPB_OK;
     SPB_CHECK_ARG(p && g && m && v && step, "spb_adamw_step: null pointer");
     SPB_CHECK_ARG(n % 4 == 0, "spb_adamw_step: n must be a multiple of 4 (flat buffers are padded to 8), got %lld", (long long)n);
@@ -72,7 +75,7 @@ extern "C" int spb_adamw_step(float* p, const float* g, float* m, float* v, void
     const int64_t cap = (int64_t)spb_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     adamw_flat_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow), n4, grad_norm, grad_scale,
-                                                       max_norm, lr, beta1, beta2, eps, weight_decay, step);
+                                                       max_norm, lr, lr_dev, beta1, beta2, eps, weight_decay, step);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

@@ -81,8 +81,12 @@ ln_fwd_kernel(const Tin* __restrict__ x, int ldx, const float* __restrict__ w, c
             const int c = g * 256 + lane * 8;
             float gam[8], bet[8], o[8];
             if (ADA) {
+                // gb holds (gamma - 1 | beta): gamma sits near its initial value 1 (layers.py:38-40), and bf16 keeps eight bits of
+                // the small deviation instead of eight bits of 1.0x
                 Ld8<__nv_bfloat16>::load(gb + (size_t)row * ldgb + c, gam);
                 Ld8<__nv_bfloat16>::load(gb + (size_t)row * ldgb + D + c, bet);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gam[j] += 1.f;
             } else {
                 Ld8<float>::load(w + c, gam);
                 Ld8<float>::load(b + c, bet);
@@ -125,8 +129,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const Tin* __restr
             float xv[8], dv[8], gam[8];
             Ld8<Tin>::load(x + (size_t)row * ldx + c, xv);
             Ld8<__nv_bfloat16>::load(dy + (size_t)row * lddy + c, dv);
-            if (ADA) Ld8<__nv_bfloat16>::load(gb + (size_t)row * ldgb + c, gam);
-            else Ld8<float>::load(w + c, gam);
+            if (ADA) {
+                Ld8<__nv_bfloat16>::load(gb + (size_t)row * ldgb + c, gam);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gam[j] += 1.f;       // gb = (gamma - 1 | beta), see ln_fwd_kernel
+            } else {
+                Ld8<float>::load(w + c, gam);
+            }
             float dgam[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -480,6 +489,7 @@ extern "C" int spb_layer_norm_fwd(const void* x, int x_fp32, int ldx, const floa
     else if (dim == 256 && !x_fp32 && !y_fp32 && !ada) LN_FWD(1, __nv_bfloat16, __nv_bfloat16, false);
     else if (dim == 256 && !x_fp32 && y_fp32 && !ada) LN_FWD(1, __nv_bfloat16, float, false);
     else if (dim == 1536 && !x_fp32 && !y_fp32 && !ada) LN_FWD(6, __nv_bfloat16, __nv_bfloat16, false);
+    else if (dim == 1536 && x_fp32 && !y_fp32 && !ada) LN_FWD(6, float, __nv_bfloat16, false);
     else if (dim == 1280 && !x_fp32 && !y_fp32 && !ada) LN_FWD(5, __nv_bfloat16, __nv_bfloat16, false);
     else if (dim == 512 && x_fp32 && !y_fp32 && !ada) LN_FWD(2, float, __nv_bfloat16, false);
     else if (dim == 512 && x_fp32 && !y_fp32 && ada) LN_FWD(2, float, __nv_bfloat16, true);
@@ -516,6 +526,7 @@ extern "C" int spb_layer_norm_bwd(const void* dy, int lddy, const void* x, int x
     else if (dim == 256 && x_fp32 && !dx_fp32 && !ada) LN_BWD(1, float, __nv_bfloat16, false);
     else if (dim == 256 && !x_fp32 && !dx_fp32 && !ada) LN_BWD(1, __nv_bfloat16, __nv_bfloat16, false);
     else if (dim == 1536 && !x_fp32 && !dx_fp32 && !ada) LN_BWD(6, __nv_bfloat16, __nv_bfloat16, false);
+    else if (dim == 1536 && x_fp32 && !dx_fp32 && !ada) LN_BWD(6, float, __nv_bfloat16, false);
     else if (dim == 1280 && !x_fp32 && !dx_fp32 && !ada) LN_BWD(5, __nv_bfloat16, __nv_bfloat16, false);
     else {
         spb_set_error("spb_layer_norm_bwd: unsupported combination dim=%d x_fp32=%d dx_fp32=%d ada=%d", dim, x_fp32, dx_fp32, (int)ada);

@@ -49,7 +49,7 @@ class _StackWeights:
         norms_b.append(b.detach())
         if self.ada:
             self.w_ada = K.cast_bf16(torch.cat(norms_w, 0).contiguous())
-            self.b_ada = torch.cat(norms_b, 0).float().contiguous()
+            self.b_ada = fused.ada_bias_minus_one(norms_b, self.D).contiguous()      # gb = (gamma - 1 | beta), see rowops.cu
         else:
             self.norm_w, self.norm_b = [w.float().contiguous() for w in norms_w], [b.float().contiguous() for b in norms_b]
 

@@ -28,6 +28,10 @@ BF16, F32 = torch.bfloat16, torch.float32
 #   start of this step.  Both flags are only True inside TrainStep's forward/backward, so stale shadows are never read.
 DIRECT_GRAD = False
 SHADOW_ACTIVE = False
+# STACK_BACKWARD_DONE: callable(params) or None.  TransformerStackFn.backward calls it once every weight gradient of its stack has
+#   been written (and the weight-gradient side streams have been joined): TrainStep launches that stack's gradient bucket on NCCL.
+STACK_BACKWARD_DONE = None
+HEAD_PROJ_FP32 = os.environ.get("SPB_HEAD_PROJ", "fp32") == "fp32"
 
 
 def _shadow(param: Tensor) -> Optional[Tensor]:
@@ -314,7 +318,8 @@ class TransformerStackFn(torch.autograd.Function):
             norm_b = [params[_norm_index(spec, i) + 1] for i in range(spec.n_norms)]
             style16 = K.cast_bf16(style.contiguous().view(N, -1))
             w_ada16 = w16_cat(norm_w)
-            gb_all = K.gemm(style16, w_ada16, bias=torch.cat(norm_b, dim=0), out_dtype=BF16)   # [N, n_norms * 2D]
+            # (gamma - 1 | beta) per norm: the kernels add the 1 back in fp32 (gamma stays near its initial value 1)
+            gb_all = K.gemm(style16, w_ada16, bias=ada_bias_minus_one(norm_b, D), out_dtype=BF16)   # [N, n_norms * 2D]
 
         def norm_fwd(i_norm, xin, out_dtype=BF16):
             if spec.ada:
@@ -352,10 +357,14 @@ class TransformerStackFn(torch.autograd.Function):
             proj_w, proj_b, out_w = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
             xn, mean, rstd = norm_fwd(2 * l + 1, cur)
             w1_16 = w16(proj_w)
-            u = K.gemm(xn, w1_16, bias=proj_b, out_dtype=BF16)
-            h = K.glu_fwd(u, p_ff, seeds[2 * l + 1])
             w2_16 = w16(out_w)
-            nxt = K.gemm(h, w2_16, residual=cur, out_dtype=F32)
+            if K.ffn_fused_ok(D, out_w.shape[1]):
+                # one kernel: GEMM1 -> GLU -> dropout -> GEMM2 -> +residual; u / h leave only as the backward's side outputs
+                nxt, u, h = K.ffn_fwd(xn, w1_16, proj_b, w2_16, cur, p_ff, seeds[2 * l + 1], save=keep)
+            else:
+                u = K.gemm(xn, w1_16, bias=proj_b, out_dtype=BF16)
+                h = K.glu_fwd(u, p_ff, seeds[2 * l + 1])
+                nxt = K.gemm(h, w2_16, residual=cur, out_dtype=F32)
             rec_f = dict(x=cur, mean=mean, rstd=rstd, xn=xn, w1_16=w1_16, u=u, h=h, w2_16=w2_16) if keep else None
             cur = nxt
             layers.append((rec_a, rec_f))
@@ -472,13 +481,37 @@ class TransformerStackFn(torch.autograd.Function):
             db_ada = K.colsum(dgb_all)
             for i in range(spec.n_norms):
                 j = _norm_index(spec, i)
-                grads[j] = dw_ada[i * 2 * D:(i + 1) * 2 * D]
-                grads[j + 1] = db_ada[i * 2 * D:(i + 1) * 2 * D]
+                gw, gb = dw_ada[i * 2 * D:(i + 1) * 2 * D], db_ada[i * 2 * D:(i + 1) * 2 * D]
+                dw_direct, db_direct = direct_grad(params[j]), direct_grad(params[j + 1])
+                if STACK_BACKWARD_DONE is not None and dw_direct is not None and db_direct is not None:
+                    # data parallel: the stack's gradient bucket leaves for NCCL at the end of this node, so nothing may be left
+                    # for autograd's AccumulateGrad to add afterwards
+                    dw_direct.add_(gw)
+                    db_direct.add_(gb)
+                else:
+                    grads[j], grads[j + 1] = gw, gb
             if ctx.needs_input_grad[3]:
                 d_style = K.gemm(dgb_all, w_ada16, trans_b=True, out_dtype=F32).view(ctx.style_shape)
         if wb is not None:
             wb.join(*[t for t in grads if isinstance(t, Tensor)])
+        if STACK_BACKWARD_DONE is not None and DIRECT_GRAD:
+            STACK_BACKWARD_DONE(params)
         return (None, g.view(B, T, D), None, d_style, None) + tuple(grads)
+
+
+_ADA_ONES = {}
+
+
+def ada_bias_minus_one(norm_b: Sequence[Tensor], D: int) -> Tensor:
+    """cat of the AdaLN linear biases with 1 subtracted from every gamma half: the batched GEMM then produces (gamma - 1 | beta),
+    which is what spb_layer_norm_fwd / _bwd expect in `gb`."""
+    key = (len(norm_b), D, str(norm_b[0].device))
+    ones = _ADA_ONES.get(key)
+    if ones is None:
+        ones = torch.zeros(len(norm_b), 2, D, dtype=F32, device=norm_b[0].device)
+        ones[:, 0] = 1.0
+        ones = _ADA_ONES[key] = ones.view(-1)
+    return torch.cat(list(norm_b), dim=0).float() - ones
 
 
 def _norm_index(spec: StackSpec, i_norm: int) -> int:
@@ -554,6 +587,21 @@ class MMDFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------- tied LM head + masked CE (a10)
+def _eval_stats_from_logits(logits: Tensor, labels: Tensor, tv: Optional[Tensor], ignore_index: int) -> Tensor:
+    """(hits, sum |tv[argmax]-tv[label]|, sum_v p_v |tv[label]-tv[v]|) over the labelled rows, from materialised logits: the
+    statement of what spb_head_ce accumulates in tensor memory (fields too wide for it take this path)."""
+    use = labels != ignore_index
+    lab = labels.clamp(min=0)
+    pred = logits.argmax(dim=-1)
+    hits = ((pred == lab) & use).sum().float()
+    if tv is None:
+        return torch.stack([hits, hits.new_zeros(()), hits.new_zeros(())])
+    tv = tv.to(logits.device, F32)
+    dist = ((tv[pred] - tv[lab]).abs() * use).sum()
+    wdist = ((logits.float().softmax(-1) * (tv[lab][:, None] - tv[None, :]).abs()).sum(-1) * use).sum()
+    return torch.stack([hits, dist, wdist])
+
+
 class TiedHeadCEFn(torch.autograd.Function):
     """loss = mean over labelled fields of CE(LN(h @ Wp)[field] @ table_field^T, labels[field]).
 
@@ -565,32 +613,40 @@ class TiedHeadCEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hidden, proj_w, ln_w, ln_b, table, labels, sizes: Tuple[int, ...], fields: Tuple[int, ...], emb: int,
-                ignore_index: int):
+                ignore_index: int, token_values=None):
+        """`token_values`: None, or one fp32 [V_f] tensor (or None) per field -- the value each token stands for.  When given,
+        the head kernel also accumulates the evaluator's statistics of the labelled rows (evaluator.py:38-46,72-104) while
+        the logits are in tensor memory: stats[f] = (hits, sum |tv[argmax]-tv[label]|, sum_v p_v |tv[label]-tv[v]|)."""
         n = hidden.shape[0]
         dev = hidden.device
         h16 = K.cast_bf16(hidden.contiguous()) if hidden.dtype == F32 else hidden.contiguous()
         wp16 = w16(proj_w)                                          # [dim, F*emb]
-        e_raw = K.gemm(h16, wp16, trans_b=True, out_dtype=BF16)     # [n, F*emb]
+        # the projection stays fp32 until its LayerNorm (one bf16 rounding less in front of the logits; 1536 columns only)
+        e_raw = K.gemm(h16, wp16, trans_b=True, out_dtype=F32 if HEAD_PROJ_FP32 else BF16)     # [n, F*emb]
         e, mean, rstd = K.layer_norm_fwd(e_raw, ln_w, ln_b, out_dtype=BF16)
         table16 = K.cast_bf16(table.contiguous())
         offs = [0]
         for v in sizes[:-1]:
             offs.append(offs[-1] + v)
         nf = len(sizes)
-        loss_sum = torch.zeros(nf, dtype=F32, device=dev)
-        count = torch.zeros(nf, dtype=F32, device=dev)
+        acc = torch.zeros((2, nf), dtype=F32, device=dev)           # one fill: loss sums, counts
+        loss_sum, count = acc[0], acc[1]
+        stats_buf = torch.zeros((nf, 3), dtype=F32, device=dev) if token_values is not None else None
         dlogits = {}
         need_grad = any(ctx.needs_input_grad)
         for f in fields:
             V = sizes[f]
             dl = torch.empty((n, (V + 7) // 8 * 8), dtype=BF16, device=dev) if need_grad else None
+            tv = token_values[f] if token_values is not None else None
             if emb == 128 and V <= 256:
-                # logits stay in tensor memory: GEMM + masked CE + gradient rows in one kernel
+                # logits stay in tensor memory: GEMM + masked CE + gradient rows (+ evaluator sums) in one kernel
                 K.head_ce(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + V], labels[:, f], loss_sum[f:f + 1], count[f:f + 1],
-                          dl, None, ignore_index)
+                          dl, None, ignore_index, token_values=tv, stats=None if stats_buf is None else stats_buf[f])
             else:
                 logits = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + V], out_dtype=F32)
                 K.ce_rows(logits, labels[:, f], V, loss_sum[f:f + 1], count[f:f + 1], dl, None, ignore_index)
+                if stats_buf is not None:
+                    stats_buf[f] = _eval_stats_from_logits(logits[:, :V], labels[:, f], tv, ignore_index)
             dlogits[f] = dl
         active = count > 0
         per_field = loss_sum / count.clamp(min=1.0)
@@ -599,11 +655,13 @@ class TiedHeadCEFn(torch.autograd.Function):
         ctx.saved = (h16, wp16, e_raw, e, mean, rstd, ln_w, table16, dlogits, count, active, n_active)
         ctx.params = (proj_w, ln_w, ln_b)
         ctx.meta = (sizes, fields, emb, offs, hidden.dtype)
-        ctx.mark_non_differentiable(per_field, count)
-        return loss, per_field, count
+        if stats_buf is None:
+            stats_buf = torch.zeros((0, 3), dtype=F32, device=dev)
+        ctx.mark_non_differentiable(per_field, count, stats_buf)
+        return loss, per_field, count, stats_buf
 
     @staticmethod
-    def backward(ctx, g, _g1, _g2):
+    def backward(ctx, g, _g1, _g2, _g3):
         h16, wp16, e_raw, e, mean, rstd, ln_w, table16, dlogits, count, active, n_active = ctx.saved
         sizes, fields, emb, offs, h_dtype = ctx.meta
         n = h16.shape[0]
@@ -623,7 +681,7 @@ class TiedHeadCEFn(torch.autograd.Function):
         dproj = wgrad(p_proj, h16, de_raw) if p_proj.dim() == 2 and p_proj.is_contiguous() else \
             K.gemm(h16, de_raw, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)             # [dim, F*emb]
         dh = K.gemm(de_raw, wp16, out_dtype=h_dtype)                                               # [n, dim]
-        return dh, dproj, None if d1 else dln_w, None if d2 else dln_b, dtable, None, None, None, None, None
+        return dh, dproj, None if d1 else dln_w, None if d2 else dln_b, dtable, None, None, None, None, None, None
 
 
 def tied_head_logits(hidden: Tensor, proj_w: Tensor, ln_w: Tensor, ln_b: Tensor, table: Tensor, sizes: Sequence[int],
@@ -631,7 +689,7 @@ def tied_head_logits(hidden: Tensor, proj_w: Tensor, ln_w: Tensor, ln_b: Tensor,
     """Inference-side logits (fp32 [n, V_f] per requested field); no autograd."""
     with torch.no_grad():
         h16 = K.cast_bf16(hidden.contiguous()) if hidden.dtype == F32 else hidden.contiguous()
-        e_raw = K.gemm(h16, K.cast_bf16(proj_w.contiguous()), trans_b=True, out_dtype=BF16)
+        e_raw = K.gemm(h16, K.cast_bf16(proj_w.contiguous()), trans_b=True, out_dtype=F32 if HEAD_PROJ_FP32 else BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, ln_w, ln_b, out_dtype=BF16, need_stats=False)
         table16 = K.cast_bf16(table.contiguous())
         offs = [0]

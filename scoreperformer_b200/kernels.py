@@ -415,23 +415,30 @@ def ce_rows(logits: Tensor, labels: Tensor, V: int, loss_sum: Tensor, count: Ten
 
 
 def head_ce(e_f: Tensor, table_f: Tensor, labels: Tensor, loss_sum: Tensor, count: Tensor, dlogits: Optional[Tensor] = None,
-            argmax: Optional[Tensor] = None, ignore_index: int = -100) -> None:
+            argmax: Optional[Tensor] = None, ignore_index: int = -100, token_values: Optional[Tensor] = None,
+            stats: Optional[Tensor] = None) -> None:
     """Fused tied head + cross-entropy of one field: e_f bf16 [n, 128] (strided view allowed), table_f bf16 [V, 128],
-    labels int64 [n] (strided view allowed).  loss_sum / count fp32 scalars are accumulated into."""
+    labels int64 [n] (strided view allowed).  loss_sum / count fp32 scalars are accumulated into; `stats` (fp32 [3], accumulated)
+    receives the evaluator sums (hits, |tv[argmax]-tv[label]|, expected |tv[label]-tv[v]|) with tv = `token_values` fp32 [V]."""
     _require_cuda(e_f, table_f)
     assert e_f.dtype == BF16 and table_f.dtype == BF16 and e_f.shape[1] == 128 and table_f.shape[1] == 128
     assert e_f.stride(1) == 1 and table_f.stride(1) == 1 and labels.dtype == torch.int64 and labels.dim() == 1
     n, V = e_f.shape[0], table_f.shape[0]
     if dlogits is not None:
         assert dlogits.dtype == BF16 and dlogits.shape[0] == n and dlogits.stride(1) == 1
+    if token_values is not None:
+        assert stats is not None and token_values.dtype == F32 and token_values.numel() >= V and token_values.is_contiguous()
+    if stats is not None:
+        assert stats.dtype == F32 and stats.numel() >= 3 and stats.is_contiguous()
     _call("spb_head_ce", _p(e_f), e_f.stride(0), _p(table_f), table_f.stride(0), V, _p(labels), labels.stride(0), ignore_index,
-          _p(loss_sum), _p(count), _p(dlogits), dlogits.stride(0) if dlogits is not None else 0, _p(argmax), n, _stream())
+          _p(loss_sum), _p(count), _p(dlogits), dlogits.stride(0) if dlogits is not None else 0, _p(argmax), _p(token_values),
+          _p(stats), n, _stream())
     _count()
 
 
 def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, shadow: Optional[Tensor], grad_norm: Optional[Tensor], step: Tensor, *,
                lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, max_norm: float = 0.0,
-               grad_scale: float = 1.0) -> None:
+               grad_scale: float = 1.0, lr_dev: Optional[Tensor] = None) -> None:
     """Clip-by-global-norm + AdamW + bf16 shadow refresh over flat fp32 buffers (one launch for the whole model)."""
     _require_cuda(p, g, m, v)
     assert p.dtype == F32 and g.dtype == F32 and m.dtype == F32 and v.dtype == F32 and step.dtype == torch.int64
@@ -439,7 +446,7 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, shadow: Optional[Tens
     n = p.numel()
     assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or (shadow.dtype == BF16 and shadow.numel() == n))
     _call("spb_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(shadow), n, _p(grad_norm), float(grad_scale), float(max_norm), float(lr),
-          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), _p(step), _stream())
+          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), _p(step), _p(lr_dev), _stream())
     _count()
 
 

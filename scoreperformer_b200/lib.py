@@ -41,8 +41,8 @@ SIGNATURES = {
     "spb_latent_level_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "spb_latent_level_bwd": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "spb_mmd_fwd_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "spb_head_ce": [_P, _I, _P, _I, _I, _P, _I, c_longlong, _P, _P, _P, _I, _P, _I, _P],
-    "spb_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P],
+    "spb_head_ce": [_P, _I, _P, _I, _I, _P, _I, c_longlong, _P, _P, _P, _I, _P, _P, _P, _I, _P],
+    "spb_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P],
     "spb_gemm_bf16_rowdot": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _I, _P],
     "spb_ce_rows": [_P, _I, _P, _I, _I, c_longlong, _P, _P, _P, _I, _P, _I, _P],
     "spb_clf_heads": [_P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U64, _P, _I, _P],

@@ -64,6 +64,7 @@ class LazyLogits(OrderedDict):
 class ScorePerformerLMOutput(TupleTransformerOutput):
     loss: Optional[Tensor] = None
     losses: Optional[Dict[str, Tensor]] = None
+    eval_stats: Optional[Dict[str, Tensor]] = None
 
 
 class ScorePerformerLMWrapper(LMWrapper):
@@ -74,6 +75,9 @@ class ScorePerformerLMWrapper(LMWrapper):
         # sync per field, wrappers.py:56); here it is decided once (first batch) and fields without labels contribute
         # nothing on the device.  Set to a tuple of field indices to skip the probe entirely.
         self.label_fields = None
+        # name -> fp32 [V] token values; set by ScorePerformerEvaluator.attach(): the head kernel then accumulates the evaluator's
+        # statistics while the logits are in tensor memory, and `forward` returns them as `eval_stats`
+        self.eval_token_values = None
 
     def _probe_label_fields(self, labels: Tensor):
         if self.label_fields is None:
@@ -103,13 +107,28 @@ class ScorePerformerLMWrapper(LMWrapper):
         names = list(head.embs.keys())
         fields = self._probe_label_fields(labels)
         table = head.table(table_cache)
-        loss, per_field, count = fused.TiedHeadCEFn.apply(
+        tvs = None
+        if self.eval_token_values is not None:
+            tvs = tuple(self._token_values_on(names[f], hidden.device) if f in fields else None for f in range(len(names)))
+        loss, per_field, count, stats = fused.TiedHeadCEFn.apply(
             hidden.reshape(b * t, d), head.proj_weight_kn(), head.norm.weight, head.norm.bias, table,
-            labels.reshape(b * t, -1).contiguous(), head.field_sizes, fields, head.split_dims[0], self.ignore_index)
+            labels.reshape(b * t, -1).contiguous(), head.field_sizes, fields, head.split_dims[0], self.ignore_index, tvs)
         losses = {names[f]: per_field[f] for f in fields}
         logits = LazyLogits(names, lambda: head(hidden.detach(), table=table.detach()))
         out.logits = logits
-        return ScorePerformerLMOutput(loss=loss, losses=losses, **out.__dict__)
+        res = ScorePerformerLMOutput(loss=loss, losses=losses, **out.__dict__)
+        if tvs is not None:
+            # per labelled field: (hits, labelled rows, sum |tv[argmax]-tv[label]|, sum_v p_v |tv[label]-tv[v]|)
+            res.eval_stats = {names[f]: torch.cat([stats[f, :1], count[f:f + 1], stats[f, 1:]]) for f in fields}
+        return res
+
+    def _token_values_on(self, name: str, device) -> Optional[Tensor]:
+        tv = self.eval_token_values.get(name)
+        if tv is None:
+            return None
+        if tv.device != device or tv.dtype != torch.float32 or not tv.is_contiguous():
+            tv = self.eval_token_values[name] = tv.to(device=device, dtype=torch.float32).contiguous()
+        return tv
 
 
 def _sample_fields(logits: Dict[str, Tensor], banned, filter_key_ids, filter_logits_fn, filter_kwargs, temperature):

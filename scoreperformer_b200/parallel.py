@@ -9,6 +9,15 @@ Buckets follow reverse execution order (decoder + heads -> perf encoder -> score
 because the tied tables receive gradient from all three stacks).  Each bucket is one flat fp32 buffer; gradients are
 copied in by a post-accumulate hook, the all-reduce of a bucket starts on a side stream as soon as its last gradient
 arrived, and `sync_gradients()` waits and scatters the averaged values back.
+
+The model runs backward on several streams (encoder branches, weight-gradient side streams): every hook records an event
+on the stream its gradient was produced on, and the communication stream waits for ALL events of a bucket before the
+bucket is copied and reduced.  With gradient accumulation (several backward passes per optimiser step) call
+`sync_gradients()` only after the last pass: hooks that fire again for an already complete bucket withdraw its
+in-flight reduction, which is redone on the accumulated values.
+
+`train_step.TrainStep` does not use this class: it owns flat gradient buffers and reduces their slices in place, inside
+the captured step.  This class serves a reference-style `Trainer` + `Optimizer` that keeps per-parameter `.grad`s.
 """
 from __future__ import annotations
 
@@ -54,7 +63,7 @@ class GradientBuckets:
             for p in ps:
                 views.append(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
-            self.buckets.append(dict(params=ps, flat=flat, views=views, pending=len(ps), work=None, event=None))
+            self.buckets.append(dict(params=ps, flat=flat, views=views, pending=len(ps), work=None, events=[None] * len(ps), dirty=False))
         self._owner = {id(p): (bi, pi) for bi, b in enumerate(self.buckets) for pi, p in enumerate(b["params"])}
         self._stream = torch.cuda.Stream() if (overlap and ps[0].is_cuda) else None
         self._hooks = []
@@ -67,18 +76,42 @@ class GradientBuckets:
     def _on_grad(self, p: torch.Tensor):
         bi, pi = self._owner[id(p)]
         b = self.buckets[bi]
+        if p.is_cuda:
+            ev = b["events"][pi]
+            if ev is None:
+                ev = b["events"][pi] = torch.cuda.Event()
+            ev.record()                     # on the stream that produced this gradient (the hook runs on it)
+        if b["pending"] <= 0:
+            # another backward pass of a gradient-accumulation step: the reduction in flight saw partial sums, redo it later
+            if b["work"] is not None:
+                b["work"].wait()
+                b["work"] = None
+            b["pending"] = 0
+            b["dirty"] = True
+            return
         b["pending"] -= 1
         if b["pending"] == 0:
-            torch._foreach_copy_(b["views"], [q.grad for q in b["params"]])     # one multi-tensor copy per bucket
             self._launch(b)
 
     def _launch(self, b: Dict):
+        grads = [q.grad for q in b["params"]]
         if self._stream is not None:
+            for ev in b["events"]:          # every producer stream, not just the one of the last hook
+                if ev is not None:
+                    self._stream.wait_event(ev)
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
+                torch._foreach_copy_(b["views"], grads)      # one multi-tensor copy per bucket
                 b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:
+            torch._foreach_copy_(b["views"], grads)
             b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        b["dirty"] = False
+
+    def _launch_all_streams(self, b: Dict):
+        """Late launch from sync_gradients(): backward has returned, so the engine has already joined its streams with the
+        caller's; the recorded events are waited for as well."""
+        self._launch(b)
 
     def sync_gradients(self):
         """Wait for every bucket, write the averaged gradients back into `p.grad`, re-arm for the next step."""
@@ -86,13 +119,12 @@ class GradientBuckets:
             return
         inv = 1.0 / self.world_size
         for b in self.buckets:
-            if b["pending"] != 0:        # a parameter received no gradient this step: reduce what we have
+            if b["pending"] != 0 or b["dirty"] or b["work"] is None:
+                # a parameter received no gradient this step, or gradients were accumulated over several passes: reduce what is there
                 for pi, p in enumerate(b["params"]):
                     if p.grad is None:
-                        b["views"][pi].zero_()
-                    else:
-                        b["views"][pi].copy_(p.grad)
-                self._launch(b)
+                        p.grad = torch.zeros_like(b["views"][pi])
+                self._launch_all_streams(b)
             b["work"].wait()
             if self._stream is not None:
                 torch.cuda.current_stream().wait_stream(self._stream)

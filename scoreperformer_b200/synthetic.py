@@ -78,3 +78,20 @@ def make_batch(batch_size: int, seq_len: int, seed: int = 1234, num_tokens: Opti
         "bars": bars, "beats": beats, "onsets": onsets,
         "directions": directions, "deadpan_mask": deadpan_mask,
     }
+
+
+class SyntheticTokenizer:
+    """Stand-in for the OctupleM tokenizer where only `token_values` is needed (ScorePerformerEvaluator, evaluator.py:30-35):
+    a deterministic value per token of every field -- special tokens 0, then an affine ramp whose step depends on the field."""
+
+    def __init__(self, num_tokens: Optional[Dict[str, int]] = None):
+        self.num_tokens = dict(num_tokens or PERF_SIZES)
+
+    def token_values(self, normalize: bool = False):
+        import numpy as np
+        out = {}
+        for i, (key, v) in enumerate(self.num_tokens.items()):
+            vals = np.zeros(v, dtype=np.float32)
+            vals[4:] = (np.arange(v - 4, dtype=np.float32) - 0.25 * v) * (0.5 + 0.125 * i)
+            out[key] = vals / np.abs(vals).max() if normalize else vals
+        return out

@@ -10,7 +10,14 @@ backward, `clip_grad_norm_(2.0)`, AdamW(lr 2e-4, wd 1e-6), `zero_grad`) with two
   forward GEMM reads its weight from (fused.SHADOW_ACTIVE);
 * forward + backward (the whole kernel sequence, ~1 000 launches) is captured once in a CUDA graph and replayed, because
   at ~15 ms per step the Python dispatch of the eager path (~19 ms) would otherwise be the bottleneck.  Dropout stays
-  random across replays through a device-side counter mixed into the kernels' seeds (kernels.RNG_OFFSET).
+  random across replays through a device-side counter mixed into the kernels' seeds (kernels.RNG_OFFSET); the learning rate is a
+  device scalar (`set_lr` never re-captures); one graph is kept per batch-shape signature, so a short last batch or another
+  sequence length gets its own capture instead of a shape error.
+* data parallelism (SURVEY section 8 row e): the gradient all-reduce is part of the step -- captured in the same graph -- and
+  bucketed by transformer stack: the moment a stack's backward node has finished (its weight gradients are final), that
+  stack's slice of the flat gradient buffer is handed to NCCL on the communication stream while the backward of the layers
+  below it keeps running; the remaining slices (embeddings, heads, latent levels, classifiers) follow after backward, and the
+  clip + AdamW kernel waits for all of them.  Buckets are issued in a fixed order on every rank.
 """
 from __future__ import annotations
 
@@ -19,6 +26,8 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 from torch import Tensor
+
+import os
 
 from . import fused, kernels as K
 
@@ -55,41 +64,114 @@ class TrainStep:
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)        # AdamW exp_avg
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)        # AdamW exp_avg_sq
         self.opt_step = torch.zeros(1, dtype=torch.int64, device=dev)        # device-side step number (CUDA-graph safe)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)      # device-side learning rate
         if use_graph and getattr(model, "perf_encoder", None) is not None:
             model.perf_encoder.exact_latent_shapes = False      # static segment tables: the step must not sync with the host
         self.rng_offset = torch.zeros(1, dtype=torch.int64, device=dev)
         K.RNG_OFFSET = self.rng_offset
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None                    # the graph of the current batch-shape signature
         self.static_batch: Optional[Dict[str, Tensor]] = None
         self.static_loss: Optional[Tensor] = None
         self.static_losses: Optional[Dict[str, Tensor]] = None
+        self._graphs: Dict[tuple, tuple] = {}                                # signature -> (graph, batch, loss, losses, metrics)
+        self._sig: Optional[tuple] = None
+        self.evaluator = None                                                # set_evaluator(): metrics computed inside the step
+        self.metrics: Optional[Dict[str, Tensor]] = None
+        self._shadow_stale = True                                            # bf16 weight shadow must be rebuilt from the fp32 weights
+        # gradient buckets of the data-parallel all-reduce: [lo, hi) slices of the flat buffer, one per transformer stack
+        self.overlap = self.world > 1 and os.environ.get("SPB_DDP_OVERLAP", "1") == "1"
+        self.graph_update = os.environ.get("SPB_DDP_GRAPH", "1") == "1"      # world > 1: all-reduce + AdamW inside the graph
+        self._buckets = self._stack_buckets() if self.overlap else []
+        self._bucket_of = {id(prm): i for i, (_, _, prms) in enumerate(self._buckets) for prm in prms}
+        self._ready = [False] * len(self._buckets)
+        self._next_bucket = 0
+        self._works = []
         self.launches_per_step = 0
         self._warm = 0
         self._copy_stream = None
         self._stage: Optional[Dict[str, Tensor]] = None
 
     # ------------------------------------------------------------------ pieces
+    def _stack_buckets(self):
+        """One bucket per transformer stack: the contiguous slice of the flat buffers that holds its parameters."""
+        from .modules.transformer.transformer import Transformer
+        index = {id(p): i for i, p in enumerate(self.params)}
+        buckets = []
+        for mod in self.model.modules():
+            if not isinstance(mod, Transformer):
+                continue
+            ids = sorted(index[id(p)] for p in mod.parameters() if id(p) in index)
+            if not ids or ids[-1] - ids[0] + 1 != len(ids):
+                continue                                   # not contiguous (shared parameters): stays in the tail reduction
+            lo = self.offsets[ids[0]]
+            last = self.params[ids[-1]]
+            hi = self.offsets[ids[-1]] + (last.numel() + 7) // 8 * 8
+            buckets.append((lo, hi, [self.params[i] for i in ids]))
+        # backward reaches the decoder first, the encoders after it: issue order = reverse registration order
+        return buckets[::-1]
+
+    def _on_stack_backward_done(self, params) -> None:
+        """fused.TransformerStackFn.backward calls this when every weight gradient of its stack has been written."""
+        i = next((self._bucket_of[id(p)] for p in params if id(p) in self._bucket_of), None)
+        if i is None:
+            return
+        self._ready[i] = True
+        while self._next_bucket < len(self._buckets) and self._ready[self._next_bucket]:
+            lo, hi, _ = self._buckets[self._next_bucket]
+            self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._next_bucket += 1
+
     def _forward_backward(self, batch: Dict[str, Tensor]):
         self.rng_offset.add_(1)
         self.flat_grad.zero_()
-        K.cast_bf16(self.flat_param, out=self.flat_shadow)       # ONE cast kernel refreshes every bf16 weight of the step
+        if self._shadow_stale:                                   # otherwise the previous AdamW launch has already written it
+            K.cast_bf16(self.flat_param, out=self.flat_shadow)
+            self._shadow_stale = False
         fused.DIRECT_GRAD = fused.SHADOW_ACTIVE = True
+        self._ready = [False] * len(self._buckets)
+        self._next_bucket = 0
+        self._works = []
+        fused.STACK_BACKWARD_DONE = self._on_stack_backward_done if self.overlap else None
         try:
             out = self.model(**batch)
             out.loss.backward()
         finally:
             fused.DIRECT_GRAD = fused.SHADOW_ACTIVE = False
+            fused.STACK_BACKWARD_DONE = None
+        if self.evaluator is not None:                           # trainer.py:462-464: metrics of every step
+            self.metrics = self.evaluator(batch, out)
         return out
 
     def _update(self):
         if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            # what the stack buckets have not covered, in order, then wait for everything on the current stream
+            pos = 0
+            done = sorted((lo, hi) for (lo, hi, _), r in zip(self._buckets, range(len(self._buckets))) if r < self._next_bucket)
+            for lo, hi in done + [(self.flat_grad.numel(), self.flat_grad.numel())]:
+                if lo > pos:
+                    self._works.append(dist.all_reduce(self.flat_grad[pos:lo], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                pos = max(pos, hi)
+            for w in self._works:
+                w.wait()
+            self._works = []
         norm = torch.linalg.vector_norm(self.flat_grad) if self.grad_clip is not None else None
         self.opt_step.add_(1)
-        # averaging over ranks, clipping and AdamW: one pass over the flat buffers
-        K.adamw_step(self.flat_param, self.flat_grad, self.flat_m, self.flat_v, None, norm, self.opt_step, lr=self.lr,
+        # averaging over ranks, clipping, AdamW and the bf16 weight shadow of the next step: one pass over the flat buffers
+        K.adamw_step(self.flat_param, self.flat_grad, self.flat_m, self.flat_v, self.flat_shadow, norm, self.opt_step, lr=self.lr,
                      betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, max_norm=self.grad_clip or 0.0,
-                     grad_scale=1.0 / self.world)
+                     grad_scale=1.0 / self.world, lr_dev=self.lr_dev)
+
+    def set_evaluator(self, evaluator) -> None:
+        """Compute `evaluator(batch, outputs)` inside every step, as Trainer.run_epoch does (experiments/trainer.py:462-464); the
+        metrics of the last step are in `self.metrics`.  With ScorePerformerEvaluator they are ratios of sums the head kernel
+        accumulates, so this adds a few scalar kernels to the captured graph."""
+        self.evaluator = evaluator
+        self._graphs.clear()
+        self.graph = None
+
+    def mark_weights_changed(self) -> None:
+        """Call after writing parameters from outside the step (load_state_dict, manual edits): rebuilds the bf16 shadow."""
+        self._shadow_stale = True
 
     # ------------------------------------------------------------------ input pipeline (host batches)
     def prefetch(self, batch: Dict[str, Tensor]) -> None:
@@ -114,24 +196,21 @@ class TrainStep:
         assert self._stage is not None, "call prefetch(batch) first"
         cur = torch.cuda.current_stream()
         cur.wait_event(self._copied)
-        if not self.use_graph or self._warm < 3 or self.graph is None:
+        if not self.use_graph or self._warm < 3 or not self._select_graph(self._stage):
             batch = {k: v.clone() for k, v in self._stage.items()}
             self._stage_free.record()
             return self.step(batch)
         for k, v in self._stage.items():
             self.static_batch[k].copy_(v, non_blocking=True)      # device-to-device, ~10 us
         self._stage_free.record()
-        self.graph.replay()
-        if self.world > 1:
-            self._update()
-        self.losses = self.static_losses
-        return self.static_loss
+        return self._replay()
 
     def set_lr(self, lr: float):
-        """ExponentialLR etc. (experiments/optimizers.py:121-149): the rate is baked into a captured graph, so re-capture."""
+        """ExponentialLR etc. (experiments/optimizers.py:121-149): the rate lives in a device scalar the AdamW kernel reads, so a
+        captured graph keeps replaying."""
         if lr != self.lr:
             self.lr = lr
-            self.graph = None
+            self.lr_dev.fill_(float(lr))
 
     def optimizer_state_dict(self) -> dict:
         """`torch.optim.AdamW.state_dict()`-shaped view of the flat moments, so reference checkpoints interoperate."""
@@ -154,24 +233,57 @@ class TrainStep:
             self.opt_step.fill_(int(st["step"]))
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+        self.lr_dev.fill_(float(self.lr))
+        self._graphs.clear()                                      # betas / eps / weight decay are baked into the captures
         self.graph = None
+
+    @staticmethod
+    def _signature(batch: Dict[str, Tensor]) -> tuple:
+        return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()))
+
+    def _select_graph(self, batch: Dict[str, Tensor]) -> bool:
+        """Make the graph captured for this batch's shapes current; False if there is none yet."""
+        sig = self._signature(batch)
+        if sig != self._sig:
+            entry = self._graphs.get(sig)
+            if entry is None:
+                return False
+            self.graph, self.static_batch, self.static_loss, self.static_losses, self._static_metrics = entry
+            self._sig = sig
+        return self.graph is not None
 
     def _capture(self, batch: Dict[str, Tensor]):
         self.static_batch = {k: v.clone() for k, v in batch.items()}
         self.graph = torch.cuda.CUDAGraph()
         before = K.LAUNCHES
+        in_graph = self.world == 1 or self.graph_update
         with torch.cuda.graph(self.graph):
             out = self._forward_backward(self.static_batch)
-            if self.world == 1:
+            if in_graph:
                 self._update()
+        self._update_in_graph = in_graph
         self.launches_per_step = K.LAUNCHES - before
         self.static_loss = out.loss.detach()
         self.static_losses = {k: v.detach() for k, v in out.losses.items()}
+        self._static_metrics = self.metrics
+        self._sig = self._signature(batch)
+        self._graphs[self._sig] = (self.graph, self.static_batch, self.static_loss, self.static_losses, self._static_metrics)
+
+    def _replay(self) -> Tensor:
+        self.graph.replay()
+        if not self._update_in_graph:
+            self._update()
+        self.losses = self.static_losses
+        self.metrics = self._static_metrics
+        # the static tensors are overwritten by the next replay: hand out a copy a trainer may keep (trainer.py:457-466 accumulates
+        # loss tensors and reads them later)
+        return self.static_loss.clone()
 
     # ------------------------------------------------------------------ public
     def step(self, batch: Dict[str, Tensor]) -> Tensor:
         """Run one training step on `batch` (device tensors, or pinned host tensors: they are copied in asynchronously).
-        Returns the loss tensor (device, detached)."""
+        Returns the loss tensor (device, detached; a fresh tensor every call).  Batches of a new shape signature (a short last
+        batch, another sequence length) are captured on first sight."""
         dev = self.flat_grad.device
         if not self.use_graph or self._warm < 3:
             # eager (also used to warm up lazily-initialised state before capture)
@@ -183,13 +295,9 @@ class TrainStep:
             self._warm += 1
             self.losses = {k: v.detach() for k, v in out.losses.items()}
             return out.loss.detach()
-        if self.graph is None:
+        if not self._select_graph(batch):
             torch.cuda.synchronize()
             self._capture({k: v.to(dev) for k, v in batch.items()})
         for k, v in batch.items():
             self.static_batch[k].copy_(v, non_blocking=True)
-        self.graph.replay()
-        if self.world > 1:
-            self._update()
-        self.losses = self.static_losses
-        return self.static_loss
+        return self._replay()

@@ -86,3 +86,29 @@ def test_unmask_tokens_cache_contract(setup):
     assert caches.transformer.attention[0].keys.shape == (1, T - 1, 64)
     want = render_batch(model, tokens_in[:, :T], b["masked_perf"][:, :T], enc.score_embeddings[:, :T], enc.perf_embeddings[:, :T])
     assert float((out == want).float().mean()) > 0.95
+
+
+def test_render_256_notes_token_exact_outside_near_ties():
+    """256 notes (1020 greedy decisions), teacher-forced on the reference's own prefix: every token must equal the reference's,
+    except decisions whose two largest reference logits are closer than the bf16 logit tolerance of north_star (2e-2 of the
+    decision's largest |logit|) -- a coin toss at that precision -- and those are listed, not averaged away."""
+    from scoreperformer_b200.decode import render_batch
+    g = parity.golden("render_t256.npz")
+    model = parity.build_model(dropout=False, device="cuda").eval()
+    batch = parity.make_batch(1, int(g["T"]), seed=int(g["seed"]), full_length=True, deadpan_last=False)
+    b, _ = _encoders(model, batch)
+    ref_tokens = torch.from_numpy(g["tokens_out"]).cuda()
+    tokens_in = torch.from_numpy(g["tokens_in"]).cuda()
+    score = torch.from_numpy(g["score_embeddings"]).cuda()
+    style = torch.from_numpy(g["perf_embeddings"]).cuda()
+    pred = render_batch(model, tokens_in, b["masked_perf"], score, style, mask=b["perf_mask"], teacher=ref_tokens)
+    fields = [3, 5, 10, 11]
+    T = int(g["T"])
+    gaps = torch.from_numpy(g["top2_gaps"]).view(T - 1, len(fields))          # decisions in decoding order: note-major, then field
+    tie = gaps < 2e-2 * torch.from_numpy(g["logit_scales"]).view(T - 1, len(fields))
+    diff = (pred[0, 1:, fields] != ref_tokens[0, 1:, fields]).cpu()
+    bad = [(int(t) + 1, fields[int(f)], float(gaps[t, f])) for t, f in torch.nonzero(diff) if not bool(tie[t, f])]
+    near = [(int(t) + 1, fields[int(f)], float(gaps[t, f])) for t, f in torch.nonzero(diff) if bool(tie[t, f])]
+    print(f"{int(diff.sum())} of {diff.numel()} decisions differ; {int(tie.sum())} reference decisions are near-ties; flipped near-ties: {near}")
+    assert not bad, f"tokens differ from the reference where its top-2 gap is not a near-tie: {bad}"
+    assert len(near) <= diff.numel() // 100, f"more than 1 % of the decisions flipped: {near}"

@@ -135,3 +135,30 @@ def test_gradient_buckets_gloo_world2():
                           "--master-port", "29613", script], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("DDP-OK") == 2, res.stdout[-2000:]
+
+
+def test_constructor_initialises_bit_identically_to_the_reference():
+    """parameters are registered in the reference's order, so under the same seed the constructor draws the
+    same numbers.  tests/golden/init_seed23.npz holds key order, shapes and checksums of the UNMODIFIED reference's state_dict
+    under torch.manual_seed(23) (oracle/gen_golden.py:gen_init); both directions of a strict load follow from equal key sets."""
+    import copy
+    import numpy as np
+    from tests import parity
+    from scoreperformer_b200.models import ScorePerformer
+    from scoreperformer_b200.recipes import default_model_config
+    g = parity.golden("init_seed23.npz")
+    torch.manual_seed(int(g["seed"]))
+    model = ScorePerformer.init(copy.deepcopy(default_model_config(dropout=True)))
+    sd = model.state_dict()
+    keys = list(sd.keys())
+    assert keys == [str(k) for k in g["keys"]], "state_dict keys / order differ from the reference"
+    for k, shape, s_ref, a_ref, f_ref in zip(keys, g["shapes"], g["sums"], g["abs_sums"], g["first"]):
+        t = sd[k]
+        assert "x".join(map(str, t.shape)) == str(shape), k
+        assert float(t.double().sum()) == float(s_ref) and float(t.double().abs().sum()) == float(a_ref), f"{k}: initial values differ"
+        if t.numel():
+            assert float(t.reshape(-1)[0]) == float(f_ref), k
+    # a state_dict with exactly these keys and shapes loads strictly (and the reference, having the same, accepts ours)
+    clone = ScorePerformer.init(copy.deepcopy(default_model_config(dropout=True)))
+    missing, unexpected = clone.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected

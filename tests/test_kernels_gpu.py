@@ -137,11 +137,12 @@ def test_layer_norm(k, dim, x_dtype, y_dtype, ada):
     n = 517
     x = randn(n, dim, dtype=x_dtype, scale=2.0) + 0.5
     w, b = randn(dim) * 0.2 + 1, randn(dim) * 0.1
-    gb = (randn(n, 2 * dim) * 0.3 + 0.8).to(BF16) if ada else None
+    # adaptive form: `gb` holds (gamma - 1 | beta) -- gamma lives near 1 (layers.py:38-40) and bf16 keeps the deviation
+    gb = (randn(n, 2 * dim) * 0.3 - 0.2).to(BF16) if ada else None
     xr = x.float().requires_grad_(True)
     if ada:
         gbr = gb.float().requires_grad_(True)
-        ref = gbr[:, :dim] * F.layer_norm(xr, (dim,)) + gbr[:, dim:]
+        ref = (1.0 + gbr[:, :dim]) * F.layer_norm(xr, (dim,)) + gbr[:, dim:]
     else:
         wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
         ref = F.layer_norm(xr, (dim,), wr, br)

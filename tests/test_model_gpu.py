@@ -35,9 +35,8 @@ def test_step_matches_reference_golden(model, name):
             assert cd <= 5e-3, f"{k}: cosine distance {cd}"
     for key in ("Velocity", "Tempo", "RelOnsetDev", "RelPerfDuration", "Bar", "NotesInOnset"):
         want = torch.from_numpy(g[f"logits/{key}"])
-        got = out.perf_decoder.logits[key].float().cpu()
-        err = float((got - want).abs().max() / want.abs().max())
-        assert err < parity.ACT_RTOL, f"logits/{key}: {err}"
+        err, rms = parity.logits_deviation(out.perf_decoder.logits[key].float().cpu(), want)
+        assert err < parity.LOGIT_MAX_RTOL and rms < parity.LOGIT_RMS_RTOL, f"logits/{key}: worst element {err}, rms {rms}"
 
 
 @pytest.mark.parametrize("B,T,seed", [(2, 48, 1), (4, 256, 1234), (3, 130, 7)])
@@ -130,3 +129,36 @@ def test_prefetched_host_batches_feed_the_same_steps():
         got.append(float(ts.losses["Velocity"]))
     for i in range(9):
         assert abs(got[i] - want[i % 3 + 6]) < 1e-4 * abs(got[i]), (i, got, want)
+
+
+RECIPE_IGNORE = ["Bar", "Position", "Pitch", "Duration", "TimeSig", "PositionShift", "NotesInOnset", "PositionInOnset"]
+
+
+@pytest.mark.parametrize("name", ["train_b2_t48.npz", "train_b3_t33.npz"])
+@pytest.mark.parametrize("tag,kw", [("recipe", dict(weighted_distance=True, ignore_keys=RECIPE_IGNORE)), ("plain", dict(weighted_distance=False))])
+def test_evaluator_matches_reference(model, name, tag, kw):
+    """ScorePerformerEvaluator fed by the head kernel's statistics (hits / |value - target| sums accumulated while the logits are in
+    tensor memory) against the metrics the UNMODIFIED reference evaluator produced on the same batch (evaluator.py:48-106), and
+    against its own logits-based statement.  Accuracies are ratios of small counts: one near-tie may flip."""
+    from scoreperformer_b200.models.scoreperformer.evaluator import ScorePerformerEvaluator
+    from scoreperformer_b200.synthetic import SyntheticTokenizer
+    g = parity.golden(name)
+    batch = parity.make_batch(int(g["B"]), int(g["T"]), seed=int(g["seed"]))
+    ev = ScorePerformerEvaluator(model, tokenizer=SyntheticTokenizer(), **kw)
+    try:
+        out = parity.run_product_step(model, batch, parity.z_from_golden(g))
+        assert out.perf_decoder.eval_stats is not None, "the LM wrapper did not hand back the head kernel's statistics"
+        labels = {"labels": batch["labels"].cuda()}
+        fused = ev(labels, out)
+        out.perf_decoder.eval_stats = None                      # same outputs through the materialised logits
+        plain = ev(labels, out)
+    finally:
+        model.perf_decoder.eval_token_values = None
+    want = dict(zip([str(k) for k in g[f"eval/{tag}/keys"]], g[f"eval/{tag}/vals"]))
+    assert list(fused.keys()) == list(want.keys()) == list(plain.keys())
+    rows = float((batch["labels"][:, 1:] != -100).sum()) / 4          # labelled rows per field
+    for k, w in want.items():
+        tol = 2.5 / rows + 1e-3 if k.startswith("accuracy") else 3e-2 * abs(w) + 1e-3
+        assert abs(float(fused[k]) - w) <= tol, f"{k}: head kernel {float(fused[k])} vs reference {w}"
+        assert abs(float(plain[k]) - w) <= tol, f"{k}: logits path {float(plain[k])} vs reference {w}"
+        assert abs(float(plain[k]) - float(fused[k])) <= tol, k
