@@ -36,8 +36,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
-                    help="c2 = configs[1] (64 x 512 per GPU, the headline); c4 = configs[3], the long-context variant (16 x 2048 per GPU)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 = configs[1] (64 x 512 per GPU, the headline); c4 = configs[3], the long-context variant (16 x 2048 per GPU); "
+                         "c5 = configs[4], batched KV-cached rendering of 256 scores x 1024 notes (prints bench_render.py's line)")
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default: 64 for c2, 16 for c4)")
     ap.add_argument("--seq", type=int, default=None, help="notes per sequence (default: 512 for c2, 2048 for c4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -206,7 +207,8 @@ def time_reference_gpu(batch: int, seq: int, steps: int = 3, warmup: int = 2):
 
 def workload_config(B, T, world, graph=True):
     which = "configs[1]" if (B, T) == (64, 512) else ("configs[3], long context" if (B, T) == (16, 2048) else "custom shape")
-    return {"workload": "ScorePerformer default recipe (recipes/scoreperformer/base.yaml) training step: fwd+bwd+clip+AdamW, "
+    return {"workload": "ScorePerformer default recipe (recipes/scoreperformer/base.yaml) training step: fwd+bwd+clip+AdamW + the "
+                        "recipe's evaluator metrics (trainer.py:462-464), "
                         f"bf16 tensor-core math / fp32 master weights, recipe dropouts on ({which})",
             "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world}", "cuda_graph": graph,
             "l2": "per-step activations (>3 GB) far exceed the 126 MB L2; no explicit flush needed"}
@@ -239,6 +241,11 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.config == "c5":
+        import bench_render
+        sys.argv = [sys.argv[0]]
+        bench_render.main()
+        return
 
     import torch.distributed as dist
     from scoreperformer_b200 import kernels as K
@@ -263,6 +270,13 @@ def main():
     model.perf_encoder.exact_latent_shapes = False          # static segment tables: no host sync inside the step
     model.perf_decoder.label_fields = (3, 5, 10, 11)        # MixedLM collator labels (base.yaml:64-65): no probe sync
     ts = TrainStep(model, lr=2e-4, weight_decay=1e-6, grad_clip=2.0, use_graph=not args.no_graph)
+    # the reference trainer evaluates its metrics after every training step (experiments/trainer.py:462-464, recipe settings
+    # base.yaml:195-198): the timed step does too -- the head kernel accumulates the statistics, the evaluator divides
+    from scoreperformer_b200.models.scoreperformer.evaluator import ScorePerformerEvaluator
+    from scoreperformer_b200.synthetic import SyntheticTokenizer
+    ts.set_evaluator(ScorePerformerEvaluator(
+        model, tokenizer=SyntheticTokenizer(), weighted_distance=True,
+        ignore_keys=["Bar", "Position", "Pitch", "Duration", "TimeSig", "PositionShift", "NotesInOnset", "PositionInOnset"]))
 
     B, T = args.batch, args.seq
     host_batch = {k: v.pin_memory() for k, v in make_batch(B, T, seed=1234 + rank).items()}
@@ -343,6 +357,23 @@ def main():
         K.gemm = timed_gemm
         import scoreperformer_b200.fused as fused_mod
         fused_mod.K.gemm = timed_gemm
+        # the other tensor-core kernels of the step, timed the same way: fused feed-forward forward, attention forward / backward
+        other = {"ffn_fwd": [], "attention_fwd": [], "attention_bwd": []}
+        orig_other = {name: getattr(K, name) for name in other}
+
+        def wrap(name):
+            fn = orig_other[name]
+
+            def timed_fn(*a, **kw):
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                out_ = fn(*a, **kw)
+                e_.record()
+                other[name].append((s_, e_))
+                return out_
+            return timed_fn
+        for name in other:
+            setattr(K, name, wrap(name))
         ts.use_graph = False
         # the timed step overlaps independent branches on side streams; for the per-kernel roofline every GEMM must own the GPU
         # while it is timed, so the instrumented eager steps run single-stream
@@ -351,11 +382,15 @@ def main():
             os.environ[k] = "0"
         for _ in range(3):                    # first eager passes only warm the allocator (the graph owns a private pool)
             records.clear()
+            for v_ in other.values():
+                v_.clear()
             torch.cuda._sleep(int(60e6))      # ~30 ms spin kernel: lets the CPU run ahead so event pairs see GPU time only
             ts.step(dev_batch)
             torch.cuda.synchronize()
         K.gemm = orig
         fused_mod.K.gemm = orig
+        for name, fn in orig_other.items():
+            setattr(K, name, fn)
         for k, v in branch_env.items():
             if v is None:
                 os.environ.pop(k, None)
@@ -372,7 +407,9 @@ def main():
         top_shape, (top_n, top_ms, top_fl) = max(by_shape.items(), key=lambda kv: kv[1][1])
         achieved = top_fl / (top_ms / top_n / 1e3) / 1e12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")     # DRAM bytes of this launch shape, ncu --set full capture
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if os.path.exists(tpath) and top_shape == (B * T, 2048, 256):
             with open(tpath) as f:
                 tj = json.load(f)
@@ -386,6 +423,24 @@ def main():
                     "peak_source": peaks["source"],
                     "step_algorithmic_tflops": algorithmic_flops_per_tuple(T) * B * T / (ms_step / 1e3) / 1e12,
                     "step_frac_of_peak": algorithmic_flops_per_tuple(T) * B * T / (ms_step / 1e3) / 1e12 / peaks["tflops"]}
+        # algorithmic FLOPs per launch: fused feed-forward 2*n*D*(2H + H); attention 4*B*heads*T^2*64 forward (x2.5 backward),
+        # halved under the causal mask (the decoder's 4 of the 10 layers) -- the launches are timed together, so an average
+        n_rows, Dm, Hh = B * T, 256, 1024
+        attn_full = 4.0 * B * 4 * T * T * 64
+        attn_avg = attn_full * (6 + 4 * 0.5) / 10
+        alg = {"ffn_fwd": 2.0 * n_rows * Dm * 3 * Hh, "attention_fwd": attn_avg, "attention_bwd": 2.5 * attn_avg}
+        names = {"ffn_fwd": "ffn_fwd_pair_kernel (GEMM1 -> GLU -> GEMM2 -> +residual, u / h on chip)",
+                 "attention_fwd": "attn_fwd_tc_kernel (S, P, O in TMEM)", "attention_bwd": "attn_bwd_tc_kernel (+ dQ convert)"}
+        extra = []
+        for name, evs in other.items():
+            if not evs:
+                continue
+            ms_ = sum(s_.elapsed_time(e_) for s_, e_ in evs)
+            tf = alg[name] * len(evs) / (ms_ / 1e3) / 1e12
+            extra.append({"kernel": names[name], "launches_per_step": len(evs), "avg_launch_us": ms_ / len(evs) * 1e3,
+                          "algorithmic_flops_per_launch": alg[name], "achieved": tf, "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
+                          "share_of_step": ms_ / ms_step})
+        roofline["other_tensor_kernels"] = extra
         if args.profile_kernels:
             agg = {}
             for s, e, f, shp in records:
@@ -420,8 +475,10 @@ def main():
             "cpu_baseline": cpu_baseline,
             "reference_gpu": reference_gpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        ts.close()                       # the captured graphs hold NCCL kernels: release them before the communicator goes
+        dist.barrier()
         dist.destroy_process_group()
 
 

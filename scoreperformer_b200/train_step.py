@@ -30,6 +30,7 @@ from torch import Tensor
 import os
 
 from . import fused, kernels as K
+from .utils import join_side_streams
 
 
 class TrainStep:
@@ -74,6 +75,8 @@ class TrainStep:
         self.static_loss: Optional[Tensor] = None
         self.static_losses: Optional[Dict[str, Tensor]] = None
         self._graphs: Dict[tuple, tuple] = {}                                # signature -> (graph, batch, loss, losses, metrics)
+        self._static_metrics = None
+        self._update_in_graph = True
         self._sig: Optional[tuple] = None
         self.evaluator = None                                                # set_evaluator(): metrics computed inside the step
         self.metrics: Optional[Dict[str, Tensor]] = None
@@ -115,11 +118,23 @@ class TrainStep:
         i = next((self._bucket_of[id(p)] for p in params if id(p) in self._bucket_of), None)
         if i is None:
             return
-        self._ready[i] = True
-        while self._next_bucket < len(self._buckets) and self._ready[self._next_bucket]:
+        # the stack's gradients are complete on THIS stream (its backward node ran here); a bucket that has to wait for its turn is
+        # launched later from another stack's stream, which must first wait for this point
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ready[i] = ev
+        cur = torch.cuda.current_stream()
+        while self._next_bucket < len(self._buckets) and self._ready[self._next_bucket] is not False:
             lo, hi, _ = self._buckets[self._next_bucket]
-            self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            cur.wait_event(self._ready[self._next_bucket])
+            self._works.append(self._all_reduce(self.flat_grad[lo:hi]))
             self._next_bucket += 1
+
+    def _all_reduce(self, t: Tensor):
+        if os.environ.get("SPB_DDP_SYNCOPS", "0") == "1":
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return None
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _forward_backward(self, batch: Dict[str, Tensor]):
         self.rng_offset.add_(1)
@@ -135,6 +150,7 @@ class TrainStep:
         try:
             out = self.model(**batch)
             out.loss.backward()
+            join_side_streams()       # in-place gradient writes on branch streams: order them before whoever reads flat_grad
         finally:
             fused.DIRECT_GRAD = fused.SHADOW_ACTIVE = False
             fused.STACK_BACKWARD_DONE = None
@@ -149,10 +165,11 @@ class TrainStep:
             done = sorted((lo, hi) for (lo, hi, _), r in zip(self._buckets, range(len(self._buckets))) if r < self._next_bucket)
             for lo, hi in done + [(self.flat_grad.numel(), self.flat_grad.numel())]:
                 if lo > pos:
-                    self._works.append(dist.all_reduce(self.flat_grad[pos:lo], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                    self._works.append(self._all_reduce(self.flat_grad[pos:lo]))
                 pos = max(pos, hi)
             for w in self._works:
-                w.wait()
+                if w is not None:
+                    w.wait()
             self._works = []
         norm = torch.linalg.vector_norm(self.flat_grad) if self.grad_clip is not None else None
         self.opt_step.add_(1)
@@ -168,6 +185,15 @@ class TrainStep:
         self.evaluator = evaluator
         self._graphs.clear()
         self.graph = None
+
+    def close(self) -> None:
+        """Drop the captured graphs (they hold NCCL kernels when world > 1: a process group must not be destroyed under them)."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        self.graph = None
+        self._sig = None
+        self.static_batch = self.static_loss = self.static_losses = self._static_metrics = None
+        torch.cuda.synchronize()
 
     def mark_weights_changed(self) -> None:
         """Call after writing parameters from outside the step (load_state_dict, manual edits): rebuilds the bf16 shadow."""
@@ -257,7 +283,8 @@ class TrainStep:
         self.graph = torch.cuda.CUDAGraph()
         before = K.LAUNCHES
         in_graph = self.world == 1 or self.graph_update
-        with torch.cuda.graph(self.graph):
+        # thread-local capture mode: NCCL's watchdog thread polls CUDA events of earlier collectives while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
             out = self._forward_backward(self.static_batch)
             if in_graph:
                 self._update()

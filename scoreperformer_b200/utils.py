@@ -52,6 +52,21 @@ import contextlib as _contextlib
 import os as _os
 
 _SIDE_STREAMS = {}
+_TOUCHED = set()          # side streams that have run work since the last join_side_streams()
+
+
+def join_side_streams() -> None:
+    """Make the current stream wait for every side stream used since the last call.  Autograd replays each node on the stream
+    of its forward, and nodes that write gradients in place (fused.DIRECT_GRAD) hand nothing back for the engine to order: the
+    consumer of the gradient buffers (all-reduce, clip + AdamW) must wait for those streams itself."""
+    if not _TOUCHED:
+        return
+    import torch
+    cur = torch.cuda.current_stream()
+    for s in list(_TOUCHED):
+        if s != cur:
+            cur.wait_stream(s)
+    _TOUCHED.clear()
 
 
 class SideBranch:
@@ -83,6 +98,7 @@ class SideBranch:
             if t is not None and t.is_cuda:
                 t.record_stream(self.side)
         self.used = True
+        _TOUCHED.add(self.side)
         with self.torch.cuda.stream(self.side):
             yield
 

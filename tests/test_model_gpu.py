@@ -162,3 +162,17 @@ def test_evaluator_matches_reference(model, name, tag, kw):
         assert abs(float(fused[k]) - w) <= tol, f"{k}: head kernel {float(fused[k])} vs reference {w}"
         assert abs(float(plain[k]) - w) <= tol, f"{k}: logits path {float(plain[k])} vs reference {w}"
         assert abs(float(plain[k]) - float(fused[k])) <= tol, k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box (gpurun --gpus 2)")
+def test_train_step_nccl_world2():
+    """Data-parallel TrainStep over NCCL: parameters stay identical across ranks, equal the single-process result on the same data,
+    and the bucketed all-reduce captured inside the step graph equals one all-reduce after backward (tests/ddp_nccl_worker.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "ddp_nccl_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0 and res.stdout.count("DDP-NCCL-OK") == 2, res.stdout[-3000:] + res.stderr[-3000:]
