@@ -281,7 +281,11 @@ def main():
     B, T = args.batch, args.seq
     host_batch = {k: v.pin_memory() for k, v in make_batch(B, T, seed=1234 + rank).items()}
     dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host_batch.values())
+    # what crosses the host-device link per step: the collated batch in its natural width (uint16 tokens, int32 segment ids,
+    # uint8 directions, lengths); masked tokens, labels and masks are rebuilt on the device (data/packed.py, csrc/collate.cu)
+    from scoreperformer_b200.data.packed import pack_batch, packed_bytes
+    packed_host = pack_batch(host_batch, check=True)
+    h2d_bytes = packed_bytes(packed_host)
 
     def barrier():
         if world > 1:
@@ -325,11 +329,11 @@ def main():
     # copy of step i+1 is issued (side stream) before the host waits for step i's loss, the way a prefetching input pipeline
     # feeds a trainer, so the H2D transfer overlaps compute instead of serialising with it.
     def e2e_step():
-        loss = ts.step_prefetched()                          # waits for this step's H2D copy, then runs the step
-        ts.prefetch(host_batch)                              # next step's pinned host -> device copy, overlapped
+        loss = ts.step_prefetched()                          # waits for this step's H2D copy, expands it on the device, runs the step
+        ts.prefetch_packed(packed_host)                      # next step's pinned host -> device copy, overlapped
         return float(loss)                                   # D2H read of the step's result (sync)
 
-    ts.prefetch(host_batch)
+    ts.prefetch_packed(packed_host)
     e2e_step()
     ms_e2e = timed(args.steps, e2e_step)
 

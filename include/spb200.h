@@ -73,6 +73,16 @@ int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p,
 int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p, uint64_t seed,
                 const uint64_t* rng_offset, spb_stream_t stream);
 
+/* Device side of the collator (data/collators/performance.py:239-255 MixedLM mask_sequence, score_performance.py:186-234): expands a
+ * packed batch -- uint16 tokens, int32 segment ids [3, n] (bars | beats | onsets), uint8 directions, int32 lengths -- into the int64
+ * tensors and bool masks the model consumes, and derives masked tokens / labels from the performance tokens.  ignore_dims /
+ * ignore_ids are bit sets (mask_ignore_token_dims / mask_ignore_token_ids, ids < 32).  Optional groups are NULL in and out. */
+int spb_unpack_batch(const uint16_t* perf, const uint16_t* score, const int32_t* segs, const uint8_t* dirs, const int32_t* perf_len,
+                     const int32_t* score_len, int64_t* o_perf, int64_t* o_masked, int64_t* o_labels, int64_t* o_score, int64_t* o_segs,
+                     int64_t* o_dirs, uint8_t* o_perf_mask, uint8_t* o_score_mask, int B, int T, int Fp, int Fs, int Fd,
+                     uint32_t ignore_dims, uint32_t ignore_ids, int mask_token, long long label_pad, int label_pad_ignored_dims,
+                     spb_stream_t stream);
+
 /* Fused feed-forward sub-layer forward: out = resid + W2 . dropout(value * silu(gate)), [value | gate] = xn W1^T + b1
  * (modules/transformer/feedforward.py:13-22,35-64 inside the pre-norm residual of transformer.py:139-232).  One tcgen05 kernel:
  * the [n, 2*hidden] pre-activation and the [n, hidden] activation stay in TMEM / shared memory.  xn bf16 [n, dim]; w1 bf16

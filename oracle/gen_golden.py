@@ -162,6 +162,30 @@ def gen_init(name, seed=23):
     print(name, len(keys), "tensors")
 
 
+def gen_collator(name, seed=11):
+    """MixedLM masking of the UNMODIFIED collator (data/collators/performance.py:239-255) with the recipe's settings
+    (base.yaml:62-65) on a seeded token tensor that contains every special token and padded tails."""
+    ref_shim.install_stubs()
+    from scoreperformer.data.collators.performance import MixedLMPerformanceCollator
+    g = torch.Generator().manual_seed(seed)
+    B, T, F = 5, 37, 12
+    seq = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in (260, 132, 92, 132, 133, 125, 26, 69, 16, 16, 165, 85)], dim=-1)
+    seq[torch.rand(B, T, F, generator=g) < 0.15] = 2          # sprinkle SOS / EOS / MASK / PAD
+    seq[torch.rand(B, T, F, generator=g) < 0.05] = 3
+    seq[torch.rand(B, T, F, generator=g) < 0.05] = 1
+    lengths = torch.tensor([37, 30, 1, 36, 18])
+    seq = seq * (torch.arange(T)[None] < lengths[:, None])[..., None]
+    out = {"seq": seq.numpy(), "lengths": lengths.numpy()}
+    for tag, kw in (("recipe", dict(mask_ignore_token_ids=[0, 1, 2, 3], mask_ignore_token_dims=[0, 1, 2, 4, 6, 7, 8, 9])),
+                    ("all_dims", dict(mask_ignore_token_ids=[0, 3], mask_ignore_token_dims=[], label_pad_ignored_dims=False)),
+                    ("keep_labels", dict(mask_ignore_token_ids=[0, 1, 2, 3], mask_ignore_token_dims=[0, 5], label_pad_ignored_dims=False))):
+        col = MixedLMPerformanceCollator(**kw)
+        masked, labels = col.mask_sequence(seq)
+        out[f"{tag}/masked"], out[f"{tag}/labels"] = masked.numpy(), labels.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), **out)
+    print(name, "ok")
+
+
 def gen_render(name, T, seed):
     """Eval-mode encoders + cached greedy unmask_tokens for one score (generators.py:230-240).  Every greedy decision is recorded
     together with the gap between its two largest logits, so a test can demand exact tokens wherever the decision is not a
@@ -234,3 +258,4 @@ if __name__ == "__main__":
     gen_render("render_t24.npz", 24, seed=5)
     gen_render("render_t256.npz", 256, seed=9)
     gen_init("init_seed23.npz", seed=23)
+    gen_collator("collator_mixlm.npz")

@@ -150,6 +150,22 @@ def layer_norm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, w: Optiona
     return (dx, dx16) if want_dx16 else dx
 
 
+# ----------------------------------------------------------------------------- collator (device side)
+def unpack_batch(perf, score, segs, dirs, perf_len, score_len, o_perf, o_masked, o_labels, o_score, o_segs, o_dirs, o_perf_mask,
+                 o_score_mask, B: int, T: int, Fp: int, Fs: int, Fd: int, ignore_dims: int, ignore_ids: int, mask_token: int,
+                 label_pad: int, label_pad_ignored_dims: bool) -> None:
+    """Packed batch -> int64 model inputs + MixedLM masking, one launch (csrc/collate.cu; data/packed.py builds the arguments)."""
+    _require_cuda(perf, o_perf)
+    assert perf.dtype == torch.uint16 and perf_len.dtype == torch.int32 and o_perf.dtype == torch.int64
+    assert score is None or score.dtype == torch.uint16
+    assert segs is None or (segs.dtype == torch.int32 and segs.is_contiguous())
+    assert dirs is None or dirs.dtype == torch.uint8
+    _call("spb_unpack_batch", _p(perf), _p(score), _p(segs), _p(dirs), _p(perf_len), _p(score_len), _p(o_perf), _p(o_masked),
+          _p(o_labels), _p(o_score), _p(o_segs), _p(o_dirs), _p(o_perf_mask), _p(o_score_mask), B, T, Fp, Fs, Fd, int(ignore_dims),
+          int(ignore_ids), int(mask_token), int(label_pad), int(bool(label_pad_ignored_dims)), _stream())
+    _count()
+
+
 # ----------------------------------------------------------------------------- GLU
 def glu_fwd(u: Tensor, dropout_p: float, seed: int) -> Tensor:
     _require_cuda(u)

@@ -93,6 +93,9 @@ class TrainStep:
         self._warm = 0
         self._copy_stream = None
         self._stage: Optional[Dict[str, Tensor]] = None
+        self._pstage: Optional[Dict[str, Tensor]] = None
+        self._pspec = None
+        self._packed_pending = False
 
     # ------------------------------------------------------------------ pieces
     def _stack_buckets(self):
@@ -217,8 +220,48 @@ class TrainStep:
                 self._stage[k].copy_(v, non_blocking=True)
             self._copied.record()
 
+    def prefetch_packed(self, packed: Dict[str, Tensor], spec=None) -> None:
+        """Like `prefetch`, for a batch packed by `data.pack_batch` (uint16 tokens, int32 segments, uint8 directions, lengths: 65
+        bytes per note-tuple instead of 466): the compact tensors are copied on the side stream and `step_prefetched()` expands
+        them -- MixedLM masking included -- with one kernel straight into the step's input tensors."""
+        from .data.packed import PackedBatchSpec
+        dev = self.flat_grad.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copied = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        if self._pstage is None or any(k not in self._pstage or self._pstage[k].shape != v.shape for k, v in packed.items()):
+            self._pstage = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in packed.items()}
+        self._pspec = spec or PackedBatchSpec()
+        self._copy_stream.wait_event(self._stage_free)
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in packed.items():
+                self._pstage[k].copy_(v, non_blocking=True)
+            self._copied.record()
+        self._packed_pending = True
+
+    def _step_prefetched_packed(self) -> Tensor:
+        from .data.packed import unpack_batch
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copied)
+        self._packed_pending = False
+        if self.use_graph and self._warm >= 3 and self.graph is not None:
+            # expand straight into the captured step's input tensors (shape changes fall through to a fresh capture below)
+            try:
+                unpack_batch(self._pstage, self._pspec, out=self.static_batch)
+                self._stage_free.record()
+                return self._replay()
+            except AssertionError:
+                pass
+        batch = unpack_batch(self._pstage, self._pspec)
+        self._stage_free.record()
+        return self.step(batch)
+
     def step_prefetched(self) -> Tensor:
-        """One training step on the batch handed to the last `prefetch()` call."""
+        """One training step on the batch handed to the last `prefetch()` / `prefetch_packed()` call."""
+        if self._packed_pending:
+            return self._step_prefetched_packed()
         assert self._stage is not None, "call prefetch(batch) first"
         cur = torch.cuda.current_stream()
         cur.wait_event(self._copied)

@@ -162,3 +162,28 @@ def test_constructor_initialises_bit_identically_to_the_reference():
     clone = ScorePerformer.init(copy.deepcopy(default_model_config(dropout=True)))
     missing, unexpected = clone.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
+
+
+def test_mixlm_masking_statement_matches_reference_collator():
+    """data/packed.mixlm_mask_sequence == MixedLMPerformanceCollator.mask_sequence of the unmodified reference (golden vectors for
+    three settings, oracle/gen_golden.py:gen_collator); pack_batch keeps exactly the information the collator output carries."""
+    from tests import parity
+    from scoreperformer_b200.data import PackedBatchSpec, mixlm_mask_sequence, pack_batch
+    from scoreperformer_b200.data.packed import packed_bytes
+    from scoreperformer_b200.synthetic import make_batch
+    g = parity.golden("collator_mixlm.npz")
+    seq = torch.from_numpy(g["seq"])
+    specs = {"recipe": PackedBatchSpec(),
+             "all_dims": PackedBatchSpec(mask_ignore_token_ids=(0, 3), mask_ignore_token_dims=(), label_pad_ignored_dims=False),
+             "keep_labels": PackedBatchSpec(mask_ignore_token_dims=(0, 5), label_pad_ignored_dims=False)}
+    for tag, spec in specs.items():
+        masked, labels = mixlm_mask_sequence(seq, spec)
+        assert torch.equal(masked, torch.from_numpy(g[f"{tag}/masked"])) and torch.equal(labels, torch.from_numpy(g[f"{tag}/labels"])), tag
+    batch = make_batch(4, 64, seed=3)
+    packed = pack_batch(batch, check=True, pin=False)
+    assert packed_bytes(packed) < 0.15 * sum(v.numel() * v.element_size() for v in batch.values())
+    bad = dict(batch)
+    bad["perf_mask"] = batch["perf_mask"].clone()
+    bad["perf_mask"][0, 3] = False                       # a hole: not a prefix mask
+    with pytest.raises(ValueError):
+        pack_batch(bad, pin=False)

@@ -538,3 +538,37 @@ def test_table_build_matches_module_arithmetic():
     out.backward(g)
     for p_, want in zip(embs.parameters(), ref_grads):
         assert rel_err(p_.grad, want) < 1e-4
+
+
+# ------------------------------------------------------------------ device-side collator
+def test_unpack_batch_matches_reference_collator(k):
+    """spb_unpack_batch: (1) the MixedLM masking is bit-exact against MixedLMPerformanceCollator.mask_sequence of the unmodified
+    reference (golden vectors, three settings, ragged lengths, every special token); (2) pack -> copy -> unpack reproduces the
+    int64 batch of the shapes the model consumes, bit for bit, including writing into preallocated (static-graph) tensors."""
+    import numpy as np
+    from tests import parity
+    from scoreperformer_b200.data import PackedBatchSpec, pack_batch, unpack_batch
+    g = parity.golden("collator_mixlm.npz")
+    seq = torch.from_numpy(g["seq"])
+    lengths = torch.from_numpy(g["lengths"]).to(torch.int32)
+    specs = {"recipe": PackedBatchSpec(),
+             "all_dims": PackedBatchSpec(mask_ignore_token_ids=(0, 3), mask_ignore_token_dims=(), label_pad_ignored_dims=False),
+             "keep_labels": PackedBatchSpec(mask_ignore_token_dims=(0, 5), label_pad_ignored_dims=False)}
+    for tag, spec in specs.items():
+        packed = {"perf": seq.to(torch.int32).to(torch.uint16).cuda(), "perf_len": lengths.cuda()}
+        out = unpack_batch(packed, spec)
+        assert torch.equal(out["perf"].cpu(), seq), tag
+        assert torch.equal(out["masked_perf"].cpu(), torch.from_numpy(g[f"{tag}/masked"])), tag
+        assert torch.equal(out["labels"].cpu(), torch.from_numpy(g[f"{tag}/labels"])), tag
+        assert torch.equal(out["perf_mask"].cpu(), torch.arange(seq.shape[1])[None] < lengths[:, None]), tag
+    for B, T in ((3, 33), (64, 512)):
+        batch = parity.make_batch(B, T, seed=21)
+        packed = {kk: v.cuda() for kk, v in pack_batch(batch, check=True).items()}
+        got = unpack_batch(packed)
+        assert set(got) == set(batch)
+        for name, want in batch.items():
+            assert got[name].dtype == want.dtype and torch.equal(got[name].cpu(), want), name
+        static = {kk: torch.zeros_like(v, device="cuda") for kk, v in batch.items()}
+        unpack_batch(packed, out=static)
+        for name, want in batch.items():
+            assert torch.equal(static[name].cpu(), want), name
