@@ -73,6 +73,17 @@ int spb_glu_fwd(const void* u, void* h, int n_rows, int hidden, float dropout_p,
 int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_rows, int hidden, float dropout_p, uint64_t seed,
                 const uint64_t* rng_offset, spb_stream_t stream);
 
+/* One new position of B scores through a whole AdaLN decoder stack in ONE persistent kernel (cache path of
+ * modules/transformer/transformer.py:161-186,219-221; attention.py:139-197; feedforward.py:13-64; layers.py:31-47): phases separated
+ * by a grid barrier, weights streamed from L2 once per step, the KV cache appended and read in place.  ptrs = HOST array of device
+ * pointers, 7 per layer: wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048], w2 bf16
+ * [256,1024], kv cache bf16 [B, cap, 128].  w_ada / b_ada: (gamma-1 | beta) rows of the 2*depth+1 AdaLN linears.  pos_dev: device
+ * int64 position.  Scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; barrier uint32.
+ * hid_out fp32 [depth, B, 256] (may be NULL) = inputs of the attention layers; out fp32 [B,256]. dim 256, 4 heads x 64, hidden 1024. */
+int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada, const void* const* ptrs,
+                          int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap, void* gb, void* qkv, void* o,
+                          void* hmid, float* xres, float* hid_out, float* out, unsigned* barrier, float eps, spb_stream_t stream);
+
 /* Device side of the collator (data/collators/performance.py:239-255 MixedLM mask_sequence, score_performance.py:186-234): expands a
  * packed batch -- uint16 tokens, int32 segment ids [3, n] (bars | beats | onsets), uint8 directions, int32 lengths -- into the int64
  * tensors and bool masks the model consumes, and derives masked tokens / labels from the performance tokens.  ignore_dims /

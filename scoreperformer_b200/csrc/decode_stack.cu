@@ -1,0 +1,469 @@
+// One new position through the whole decoder stack in ONE persistent kernel (north_star item 6).
+//
+// Reference semantics: the cache path of Transformer.forward (modules/transformer/transformer.py:161-186,219-221) for B scores
+// that advance in lockstep -- per layer AdaLN -> q|k|v -> append k|v to the cache -> MQA attention of the new query over the
+// cache with the ALiBi bias (attend.py:58-126, attention.py:139-197) -> out-projection + residual -> AdaLN -> GLU feed-forward
+// + residual (feedforward.py:13-64), then the final AdaLN (layers.py:31-47).
+//
+// A note-step is ~2 GFLOP on [B <= 256, 256] activations against 7.6 MB of bf16 weights: as ~45 separate launches it is pure
+// launch / dependency latency (8 us per kernel, 0.5 ms per note).  Here every SM takes a slice of every phase -- weights stream
+// from L2 once per step over the whole chip, the KV cache is read once -- and the phases are separated by a grid barrier
+// (one atomic counter; all CTAs are co-resident: grid <= #SMs, one CTA per SM):
+//   phase 0        gb = style W_ada^T + b          (gamma-1 | beta) of all 2*depth+1 AdaLNs, bf16 scratch
+//   per layer  A   qkv  = AdaLN(x) Wqkv^T                                 32x32 tiles, mma.sync m16n8k16 (M is tiny: tcgen05's
+//              B   cache[pos] = k|v ;  o = softmax(q K^T s - slope|i-j|) V   128-row tiles would idle 3/4 of the tensor core)
+//              C   x   += mask * (o Wo^T)
+//              D   h    = GLU(AdaLN(x) W1^T + b1)
+//              E   x   += h W2^T                     split-K x4, fp32 atomics into the residual stream
+//   final          out  = AdaLN(x)
+// Algorithmic HBM/L2 bytes per note-step: B * pos * 4 layers * 256 B of KV cache (the roofline term) + 7.6 MB of
+// weights out of L2.
+#include "common.cuh"
+
+namespace {
+
+constexpr int DS_D = 256, DS_H = 4, DS_DH = 64, DS_HID = 1024, DS_QKV = DS_H * DS_DH + 2 * DS_DH;      // 384
+constexpr int DS_MAX_DEPTH = 8;
+constexpr int DS_THREADS = 256;
+constexpr int DS_TM = 32, DS_TN = 32;            // CTA tile
+constexpr int DS_LDA = DS_D + 8;                 // padded smem row (bf16 elements): conflict-free fragment loads
+constexpr int DS_MAX_KEYS = 2048;
+
+struct DecodeStackParams {
+    int B, depth, S, cap;                        // scores, layers, style width, cache capacity (rows per score)
+    const float* x_in;                           // [B, 256] stream input of the new position
+    const float* style;                          // [B, S]
+    const __nv_bfloat16* w_ada;                  // [(2*depth+1) * 512, S]
+    const float* b_ada;                          // [(2*depth+1) * 512]  (gamma - 1 | beta)
+    const __nv_bfloat16* wqkv[DS_MAX_DEPTH];     // [384, 256]
+    const __nv_bfloat16* wo[DS_MAX_DEPTH];       // [256, 256]
+    const float* logslopes[DS_MAX_DEPTH];        // [4]
+    const __nv_bfloat16* w1[DS_MAX_DEPTH];       // [2048, 256] value rows | gate rows
+    const float* b1[DS_MAX_DEPTH];               // [2048]
+    const __nv_bfloat16* w2[DS_MAX_DEPTH];       // [256, 1024]
+    __nv_bfloat16* kv[DS_MAX_DEPTH];             // [B, cap, 128] k | v
+    const uint8_t* key_mask;                     // [B, cap] or null
+    const long long* pos_dev;                    // device scalar: index of the new position
+    // scratch
+    __nv_bfloat16* gb;                           // [B, (2*depth+1) * 512]
+    __nv_bfloat16* qkv;                          // [B, 384]
+    __nv_bfloat16* o;                            // [B, 256]
+    __nv_bfloat16* hmid;                         // [B, 1024]
+    float* xres;                                 // [B, 256] residual stream
+    float* hid_out;                              // [depth, B, 256] inputs of the attention layers (cache contract), or null
+    float* out;                                  // [B, 256]
+    unsigned* barrier;                           // zeroed by the host before the launch
+    float eps;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * gridDim.x;
+        unsigned seen;
+        long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen < target && clock64() - t0 > 4000000000ll) {
+                printf("spb200: decode_stack grid barrier timed out (block %d, epoch %u, seen %u)\n", blockIdx.x, epoch, seen);
+                __trap();
+            }
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[4] of this warp's m16n8 piece of a 32 x 32 CTA tile: rows r0 + 16*(warp&1).., columns of W  n0 + 8*(warp>>1)..
+// A: smem bf16 [32][lda] (k contiguous);  W: global bf16 [N][ldw] (k contiguous), rows n_row0.. are this tile's columns
+__device__ __forceinline__ void tile_mma(float (&acc)[4], const __nv_bfloat16* sA, int lda, const __nv_bfloat16* __restrict__ W, int ldw,
+                                         int n_row0, int K, int warp, int lane) {
+    const int g = lane >> 2, tig = lane & 3;
+    const __nv_bfloat16* a_lo = sA + (size_t)((warp & 1) * 16 + g) * lda + tig * 2;
+    const __nv_bfloat16* a_hi = a_lo + 8 * lda;
+    const __nv_bfloat16* wr = W + (size_t)(n_row0 + (warp >> 1) * 8 + g) * ldw + tig * 2;
+#pragma unroll 4
+    for (int k = 0; k < K; k += 16) {
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(a_lo + k), a1 = *reinterpret_cast<const uint32_t*>(a_hi + k);
+        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(a_lo + k + 8), a3 = *reinterpret_cast<const uint32_t*>(a_hi + k + 8);
+        const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wr + k)), b1 = __ldg(reinterpret_cast<const uint32_t*>(wr + k + 8));
+        mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+    }
+}
+
+// AdaLN of 32 rows of the fp32 residual stream -> bf16 smem tile [32][DS_LDA]; one warp per 4 rows (rows beyond B are zeroed)
+__device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres, const __nv_bfloat16* gb, int ld_gb, int norm_idx, int row0,
+                                            int B, float eps, int warp, int lane) {
+    for (int rr = warp; rr < DS_TM; rr += DS_THREADS / 32) {
+        const int row = row0 + rr;
+        __nv_bfloat16* dst = sA + (size_t)rr * DS_LDA + lane * 8;
+        if (row >= B) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        const float4 v0 = *reinterpret_cast<const float4*>(xres + (size_t)row * DS_D + lane * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(xres + (size_t)row * DS_D + lane * 8 + 4);
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+        const float mean = warp_sum(s) * (1.f / DS_D);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] -= mean; q += v[j] * v[j]; }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / DS_D) + eps);
+        const __nv_bfloat16* gr = gb + (size_t)row * ld_gb + norm_idx * 2 * DS_D + lane * 8;
+        const uint4 gu = *reinterpret_cast<const uint4*>(gr), bu = *reinterpret_cast<const uint4*>(gr + DS_D);
+        const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z), g3 = unpack_bf16x2(gu.w);
+        const float2 b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y), b2 = unpack_bf16x2(bu.z), b3 = unpack_bf16x2(bu.w);
+        const float gm[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y}, bt[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = v[j] * rstd * (1.f + gm[j]) + bt[j];        // gb holds gamma - 1 (rowops.cu)
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    }
+}
+
+// copy 32 rows x K bf16 columns (k0..k0+K of a [B, ld] matrix) into the smem tile
+__device__ __forceinline__ void stage_rows(__nv_bfloat16* sA, const __nv_bfloat16* src, int ld, int k0, int K, int row0, int B) {
+    const int per_row = K / 8;
+    for (int i = threadIdx.x; i < DS_TM * per_row; i += DS_THREADS) {
+        const int rr = i / per_row, c = (i - rr * per_row) * 8;
+        const int row = row0 + rr;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row < B) v = *reinterpret_cast<const uint4*>(src + (size_t)row * ld + k0 + c);
+        *reinterpret_cast<uint4*>(sA + (size_t)rr * DS_LDA + c) = v;
+    }
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 1)
+decode_stack_kernel(DecodeStackParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);                          // [32][DS_LDA]
+    float* sP = reinterpret_cast<float*>(smem_raw + DS_TM * DS_LDA * 2);                      // [8 warps][cap] attention scores
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int B = p.B, n_norms = 2 * p.depth + 1, ld_gb = n_norms * 2 * DS_D;
+    const int row_blocks = (B + DS_TM - 1) / DS_TM;
+    const int pos = (int)*p.pos_dev;
+    unsigned epoch = 0;
+
+    // ---- phase 0: gb = style W_ada^T + b_ada for every norm; the residual stream starts as the input
+    {
+        const int col_blocks = ld_gb / DS_TN;
+        for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+            const int rb = t / col_blocks, cb = t - rb * col_blocks;
+            __syncthreads();
+            for (int i = threadIdx.x; i < DS_TM * p.S; i += DS_THREADS) {        // style rows -> bf16 tile (S <= 256)
+                const int rr = i / p.S, c = i - rr * p.S;
+                const int row = rb * DS_TM + rr;
+                sA[(size_t)rr * DS_LDA + c] = __float2bfloat16_rn(row < B ? p.style[(size_t)row * p.S + c] : 0.f);
+            }
+            __syncthreads();
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            tile_mma(acc, sA, DS_LDA, p.w_ada, p.S, cb * DS_TN, p.S, warp, lane);
+            const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
+            const float bb0 = p.b_ada[col], bb1 = p.b_ada[col + 1];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
+                if (row < B)
+                    *reinterpret_cast<uint32_t*>(p.gb + (size_t)row * ld_gb + col) = pack_bf16x2(acc[2 * hf] + bb0, acc[2 * hf + 1] + bb1);
+            }
+        }
+        for (int i = blockIdx.x * DS_THREADS + threadIdx.x; i < B * DS_D / 4; i += gridDim.x * DS_THREADS)
+            reinterpret_cast<float4*>(p.xres)[i] = reinterpret_cast<const float4*>(p.x_in)[i];
+    }
+    grid_barrier(p.barrier, epoch);
+
+    for (int l = 0; l < p.depth; ++l) {
+        // ---- A: qkv = AdaLN(x) Wqkv^T  (and the cache contract's copy of the layer input)
+        if (p.hid_out != nullptr)
+            for (int i = blockIdx.x * DS_THREADS + threadIdx.x; i < B * DS_D / 4; i += gridDim.x * DS_THREADS)
+                reinterpret_cast<float4*>(p.hid_out + (size_t)l * B * DS_D)[i] = reinterpret_cast<const float4*>(p.xres)[i];
+        {
+            const int col_blocks = DS_QKV / DS_TN;
+            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+                const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                __syncthreads();
+                stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l, rb * DS_TM, B, p.eps, warp, lane);
+                __syncthreads();
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                tile_mma(acc, sA, DS_LDA, p.wqkv[l], DS_D, cb * DS_TN, DS_D, warp, lane);
+                const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
+                    if (row < B) *reinterpret_cast<uint32_t*>(p.qkv + (size_t)row * DS_QKV + col) = pack_bf16x2(acc[2 * hf], acc[2 * hf + 1]);
+                }
+            }
+        }
+        grid_barrier(p.barrier, epoch);
+
+        // ---- B: append k|v, attention of the new query over the cache.  Two scores per CTA at a time: warps 0-3 / 4-7 = heads.
+        {
+            const int n_keys = min(p.cap, pos + 1);
+            const float scale = rsqrtf((float)DS_DH);
+            for (int pair = blockIdx.x; pair * 2 < B; pair += gridDim.x) {
+                const int b = pair * 2 + (warp >> 2), h = warp & 3;
+                __syncthreads();
+                if (b < B) {
+                    __nv_bfloat16* kvb = p.kv[l] + (size_t)b * p.cap * 128;
+                    const int lw = threadIdx.x & 127;
+                    if (lw < 16 && pos < p.cap)
+                        reinterpret_cast<uint4*>(kvb + (size_t)pos * 128)[lw] = reinterpret_cast<const uint4*>(p.qkv + (size_t)b * DS_QKV + DS_H * DS_DH)[lw];
+                }
+                __syncthreads();
+                if (b >= B) continue;
+                const __nv_bfloat16* kvb = p.kv[l] + (size_t)b * p.cap * 128;
+                float* pr = sP + (size_t)warp * p.cap;
+                const float slope = __expf(p.logslopes[l][h]);
+                float qv[DS_DH];
+                {
+                    const __nv_bfloat16* qr = p.qkv + (size_t)b * DS_QKV + h * DS_DH;
+#pragma unroll
+                    for (int c = 0; c < DS_DH / 8; ++c) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(qr + c * 8);
+                        const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+                        qv[c * 8 + 0] = a.x; qv[c * 8 + 1] = a.y; qv[c * 8 + 2] = b2.x; qv[c * 8 + 3] = b2.y;
+                        qv[c * 8 + 4] = c2.x; qv[c * 8 + 5] = c2.y; qv[c * 8 + 6] = d.x; qv[c * 8 + 7] = d.y;
+                    }
+                }
+                float mx = -INFINITY;
+                for (int j = lane; j < n_keys; j += 32) {
+                    const bool ok = p.key_mask == nullptr || p.key_mask[(size_t)b * p.cap + j];
+                    float s = -INFINITY;
+                    if (ok) {
+                        const __nv_bfloat16* kr = kvb + (size_t)j * 128;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < DS_DH / 8; ++c) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
+                            const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+                            acc += qv[c * 8] * a.x + qv[c * 8 + 1] * a.y + qv[c * 8 + 2] * b2.x + qv[c * 8 + 3] * b2.y + qv[c * 8 + 4] * c2.x +
+                                   qv[c * 8 + 5] * c2.y + qv[c * 8 + 6] * d.x + qv[c * 8 + 7] * d.y;
+                        }
+                        s = acc * scale - slope * (float)(pos - j);
+                    }
+                    pr[j] = s;
+                    mx = fmaxf(mx, s);
+                }
+                mx = warp_max(mx);
+                const float m_use = mx == -INFINITY ? 0.f : mx;
+                float sum = 0.f;
+                for (int j = lane; j < n_keys; j += 32) {
+                    const float e = __expf(pr[j] - m_use);
+                    pr[j] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                __syncwarp();
+                const float inv = sum > 0.f ? 1.f / sum : 0.f;
+                const int grp = lane >> 3, sub = lane & 7;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = 0.f;
+                const __nv_bfloat16* vbase = kvb + DS_DH + sub * 8;
+                for (int j = grp; j < n_keys; j += 4) {
+                    const float p0 = pr[j];
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128);
+                    const float2 a0 = unpack_bf16x2(u0.x), a1 = unpack_bf16x2(u0.y), a2 = unpack_bf16x2(u0.z), a3 = unpack_bf16x2(u0.w);
+                    o[0] += p0 * a0.x; o[1] += p0 * a0.y; o[2] += p0 * a1.x; o[3] += p0 * a1.y;
+                    o[4] += p0 * a2.x; o[5] += p0 * a2.y; o[6] += p0 * a3.x; o[7] += p0 * a3.y;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+                    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+                }
+                if (grp == 0)
+                    *reinterpret_cast<uint4*>(p.o + (size_t)b * DS_D + h * DS_DH + sub * 8) =
+                        make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
+                                   pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
+            }
+        }
+        grid_barrier(p.barrier, epoch);
+
+        // ---- C: x += mask[b, pos] * (o Wo^T)
+        {
+            const int col_blocks = DS_D / DS_TN;
+            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+                const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                __syncthreads();
+                stage_rows(sA, p.o, DS_D, 0, DS_D, rb * DS_TM, B);
+                __syncthreads();
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                tile_mma(acc, sA, DS_LDA, p.wo[l], DS_D, cb * DS_TN, DS_D, warp, lane);
+                const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
+                    if (row < B) {
+                        const bool keep = p.key_mask == nullptr || pos >= p.cap || p.key_mask[(size_t)row * p.cap + pos];
+                        if (keep) {
+                            float2* xr = reinterpret_cast<float2*>(p.xres + (size_t)row * DS_D + col);
+                            float2 v = *xr;
+                            v.x += acc[2 * hf];
+                            v.y += acc[2 * hf + 1];
+                            *xr = v;
+                        }
+                    }
+                }
+            }
+        }
+        grid_barrier(p.barrier, epoch);
+
+        // ---- D: h = GLU(AdaLN(x) W1^T + b1): a tile is 32 rows x 16 hidden units (16 value + 16 gate columns)
+        {
+            const int col_blocks = DS_HID / 16;
+            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+                const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                __syncthreads();
+                stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
+                __syncthreads();
+                // warps 0-3 (n-pieces 0,1 of the tile) take the value columns, warps 4-7 the matching gate columns
+                const int piece = (warp >> 1) & 1, is_gate = warp >> 2;
+                const int wrow0 = (is_gate ? DS_HID : 0) + cb * 16 + piece * 8;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                {
+                    const __nv_bfloat16* a_lo = sA + (size_t)((warp & 1) * 16 + g) * DS_LDA + tig * 2;
+                    const __nv_bfloat16* a_hi = a_lo + 8 * DS_LDA;
+                    const __nv_bfloat16* wr = p.w1[l] + (size_t)(wrow0 + g) * DS_D + tig * 2;
+#pragma unroll 4
+                    for (int k = 0; k < DS_D; k += 16) {
+                        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(a_lo + k), a1 = *reinterpret_cast<const uint32_t*>(a_hi + k);
+                        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(a_lo + k + 8), a3 = *reinterpret_cast<const uint32_t*>(a_hi + k + 8);
+                        const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wr + k)), b1 = __ldg(reinterpret_cast<const uint32_t*>(wr + k + 8));
+                        mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+                    }
+                }
+                const int wcol = wrow0 + tig * 2;
+                acc[0] += p.b1[l][wcol]; acc[1] += p.b1[l][wcol + 1]; acc[2] += p.b1[l][wcol]; acc[3] += p.b1[l][wcol + 1];
+                // value and gate of the same (row, hidden) live in warps w and w + 4: exchange through smem (reuse the score area)
+                float* ex = sP;                      // [4 value warps][32 lanes][4]
+                __syncthreads();
+                if (is_gate) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ex[((warp - 4) * 32 + lane) * 4 + e] = acc[e];
+                }
+                __syncthreads();
+                if (!is_gate) {
+                    float hv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float gt = ex[(warp * 32 + lane) * 4 + e];
+                        hv[e] = acc[e] * gt / (1.f + __expf(-gt));
+                    }
+                    const int hcol = cb * 16 + piece * 8 + tig * 2;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
+                        if (row < B) *reinterpret_cast<uint32_t*>(p.hmid + (size_t)row * DS_HID + hcol) = pack_bf16x2(hv[2 * hf], hv[2 * hf + 1]);
+                    }
+                }
+            }
+        }
+        grid_barrier(p.barrier, epoch);
+
+        // ---- E: x += h W2^T, split-K x4 (K = 256 each), fp32 atomics into the residual stream
+        {
+            const int col_blocks = DS_D / DS_TN, splits = DS_HID / DS_D;
+            for (int t = blockIdx.x; t < row_blocks * col_blocks * splits; t += gridDim.x) {
+                const int sp = t / (row_blocks * col_blocks), rem = t - sp * row_blocks * col_blocks;
+                const int rb = rem / col_blocks, cb = rem - rb * col_blocks;
+                __syncthreads();
+                stage_rows(sA, p.hmid, DS_HID, sp * DS_D, DS_D, rb * DS_TM, B);
+                __syncthreads();
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                tile_mma(acc, sA, DS_LDA, p.w2[l] + sp * DS_D, DS_HID, cb * DS_TN, DS_D, warp, lane);
+                const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
+                    if (row < B) {
+                        atomicAdd(p.xres + (size_t)row * DS_D + col, acc[2 * hf]);
+                        atomicAdd(p.xres + (size_t)row * DS_D + col + 1, acc[2 * hf + 1]);
+                    }
+                }
+            }
+        }
+        grid_barrier(p.barrier, epoch);
+    }
+
+    // ---- final AdaLN -> fp32 out, one warp per row
+    for (int row = blockIdx.x * (DS_THREADS / 32) + warp; row < B; row += gridDim.x * (DS_THREADS / 32)) {
+        const float4 v0 = *reinterpret_cast<const float4*>(p.xres + (size_t)row * DS_D + lane * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(p.xres + (size_t)row * DS_D + lane * 8 + 4);
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+        const float mean = warp_sum(s) * (1.f / DS_D);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] -= mean; q += v[j] * v[j]; }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / DS_D) + p.eps);
+        const __nv_bfloat16* gr = p.gb + (size_t)row * ld_gb + (2 * p.depth) * 2 * DS_D + lane * 8;
+        const uint4 gu = *reinterpret_cast<const uint4*>(gr), bu = *reinterpret_cast<const uint4*>(gr + DS_D);
+        const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z), g3 = unpack_bf16x2(gu.w);
+        const float2 b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y), b2 = unpack_bf16x2(bu.z), b3 = unpack_bf16x2(bu.w);
+        const float gm[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y}, bt[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = v[j] * rstd * (1.f + gm[j]) + bt[j];
+        *reinterpret_cast<float4*>(p.out + (size_t)row * DS_D + lane * 8) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(p.out + (size_t)row * DS_D + lane * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+}
+
+}  // namespace
+
+// One new position through an AdaLN decoder stack (see the header of this file).  `ptrs` is a HOST array of device pointers:
+// per layer l (7 entries at 7*l): wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048],
+// w2 bf16 [256,1024], kv cache bf16 [B, cap, 128].  w_ada bf16 [(2*depth+1)*512, S] / b_ada fp32 hold (gamma-1 | beta) rows per
+// norm.  scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; `barrier` one uint32.
+// hid_out (fp32 [depth, B, 256], may be NULL) receives the inputs of the attention layers (the reference's cache contract).
+extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada,
+                                     const void* const* ptrs, int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap,
+                                     void* gb, void* qkv, void* o, void* hmid, float* xres, float* hid_out, float* out, unsigned* barrier,
+                                     float eps, cudaStream_t stream) {
+    if (B <= 0) return SPB_OK;
+    SPB_CHECK_ARG(x_in && style && w_ada && b_ada && ptrs && pos_dev && gb && qkv && o && hmid && xres && out && barrier,
+                  "spb_decode_stack_step: null pointer");
+    SPB_CHECK_ARG(depth >= 1 && depth <= DS_MAX_DEPTH, "spb_decode_stack_step: depth must be in 1..%d", DS_MAX_DEPTH);
+    SPB_CHECK_ARG(S % 16 == 0 && S >= 16 && S <= DS_D, "spb_decode_stack_step: style width must be a multiple of 16 in [16, 256], got %d", S);
+    SPB_CHECK_ARG(cap >= 1 && cap <= DS_MAX_KEYS, "spb_decode_stack_step: cache capacity must be in 1..%d", DS_MAX_KEYS);
+    DecodeStackParams p;
+    p.B = B; p.depth = depth; p.S = S; p.cap = cap;
+    p.x_in = x_in; p.style = style;
+    p.w_ada = reinterpret_cast<const __nv_bfloat16*>(w_ada); p.b_ada = b_ada;
+    for (int l = 0; l < depth; ++l) {
+        p.wqkv[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l]);
+        p.wo[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l + 1]);
+        p.logslopes[l] = reinterpret_cast<const float*>(ptrs[7 * l + 2]);
+        p.w1[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l + 3]);
+        p.b1[l] = reinterpret_cast<const float*>(ptrs[7 * l + 4]);
+        p.w2[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l + 5]);
+        p.kv[l] = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ptrs[7 * l + 6]));
+        SPB_CHECK_ARG(p.wqkv[l] && p.wo[l] && p.logslopes[l] && p.w1[l] && p.b1[l] && p.w2[l] && p.kv[l], "spb_decode_stack_step: null layer pointer");
+    }
+    p.key_mask = key_mask; p.pos_dev = pos_dev;
+    p.gb = reinterpret_cast<__nv_bfloat16*>(gb); p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv);
+    p.o = reinterpret_cast<__nv_bfloat16*>(o); p.hmid = reinterpret_cast<__nv_bfloat16*>(hmid);
+    p.xres = xres; p.hid_out = hid_out; p.out = out; p.barrier = barrier; p.eps = eps;
+    const int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 4 * 32 * 4 * 4;
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
+    decode_stack_kernel<<<spb_num_sms(), DS_THREADS, smem, stream>>>(p);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}

@@ -166,6 +166,13 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     field_idx = torch.tensor(list(fields), dtype=torch.int64, device=dev)
     neg_inf = -float("inf")
 
+    # the whole decoder stack of a note-step is ONE persistent kernel when the stack has the recipe's shape (csrc/decode_stack.cu);
+    # SPB_DECODE=legacy keeps the launch-per-operator path (also the fallback for other shapes)
+    plan = None
+    style_f = style.float().contiguous()
+    if K.decode_stack_ok(sw.depth, sw.D, sw.H, sw.layers[0]["w2"].shape[1], sw.ada, style_f.shape[-1], T):
+        plan = K.DecodeStackPlan(sw.layers, sw.w_ada, sw.b_ada, kv_caches, B, style_f.shape[-1])
+
     def step():
         nxt = pos_t + 1
         # decoder position i: full tuple of note i, masked tuple / context / style of note i+1 (wrappers.py:409-431)
@@ -177,7 +184,10 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
         K.layer_norm_fwd(te, en_w, en_b, out=cat2[:, :dec.dim], need_stats=False)
         cat2[:, dec.dim:].copy_(ctx16.index_select(1, nxt).reshape(B, -1))
         x = K.gemm(cat2, wc16, bias=bc, out_dtype=F32)
-        hid = _stack_step(sw, x, style.index_select(1, nxt).reshape(B, -1), kv_caches, km, 0, pos_dev=pos_t)
+        if plan is not None:
+            hid = plan.step(x, style_f.index_select(1, nxt).reshape(B, -1), km, pos_t)
+        else:
+            hid = _stack_step(sw, x, style.index_select(1, nxt).reshape(B, -1), kv_caches, km, 0, pos_dev=pos_t)
         # tied head for the masked fields only (wrappers.py:364-380)
         e_raw = K.gemm(K.cast_bf16(hid), whead16, trans_b=True, out_dtype=BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)

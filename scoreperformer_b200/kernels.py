@@ -150,6 +150,50 @@ def layer_norm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, w: Optiona
     return (dx, dx16) if want_dx16 else dx
 
 
+# ----------------------------------------------------------------------------- persistent decode step
+class DecodeStackPlan:
+    """Pointer table + scratch of `spb_decode_stack_step` for one (stack, batch, cache) -- built once per decode session."""
+
+    def __init__(self, layers, w_ada: Tensor, b_ada: Tensor, kv_caches, B: int, style_dim: int, keep_hiddens: bool = False):
+        import ctypes
+        dev = w_ada.device
+        self.depth, self.B, self.S, self.cap = len(layers), B, style_dim, kv_caches[0].shape[1]
+        self.w_ada, self.b_ada = w_ada, b_ada
+        self._keep = [layers, kv_caches]                       # keep the tensors alive as long as the pointers are used
+        ptrs = []
+        for w, kv in zip(layers, kv_caches):
+            assert kv.dtype == BF16 and kv.is_contiguous() and kv.shape == (B, self.cap, 128)
+            for t in (w["wqkv"], w["wo"], w["ls"], w["w1"], w["b1"], w["w2"], kv):
+                assert t.is_contiguous()
+                ptrs.append(t.data_ptr())
+        self.ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        n_norms = 2 * self.depth + 1
+        self.gb = torch.empty((B, n_norms * 512), dtype=BF16, device=dev)
+        self.qkv = torch.empty((B, 384), dtype=BF16, device=dev)
+        self.o = torch.empty((B, 256), dtype=BF16, device=dev)
+        self.hmid = torch.empty((B, 1024), dtype=BF16, device=dev)
+        self.xres = torch.empty((B, 256), dtype=F32, device=dev)
+        self.hid = torch.empty((self.depth, B, 256), dtype=F32, device=dev) if keep_hiddens else None
+        self.out = torch.empty((B, 256), dtype=F32, device=dev)
+        self.barrier = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step(self, x: Tensor, style: Tensor, key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5) -> Tensor:
+        assert x.dtype == F32 and x.is_contiguous() and x.shape == (self.B, 256)
+        assert style.dtype == F32 and style.is_contiguous() and style.shape == (self.B, self.S)
+        assert pos_dev.dtype == torch.int64 and pos_dev.is_cuda
+        assert key_mask is None or (key_mask.is_contiguous() and key_mask.shape == (self.B, self.cap))
+        _call("spb_decode_stack_step", _p(x), _p(style), self.S, _p(self.w_ada), _p(self.b_ada), self.ptrs, self.depth, _p(key_mask),
+              _p(pos_dev), self.B, self.cap, _p(self.gb), _p(self.qkv), _p(self.o), _p(self.hmid), _p(self.xres), _p(self.hid),
+              _p(self.out), _p(self.barrier), float(eps), _stream())
+        _count()
+        return self.out
+
+
+def decode_stack_ok(depth: int, dim: int, heads: int, hidden: int, ada: bool, style_dim: int, cap: int) -> bool:
+    return (ada and dim == 256 and heads == 4 and hidden == 1024 and 1 <= depth <= 8 and style_dim % 16 == 0 and 16 <= style_dim <= 256
+            and cap <= 2048 and _os.environ.get("SPB_DECODE", "fused") == "fused")
+
+
 # ----------------------------------------------------------------------------- collator (device side)
 def unpack_batch(perf, score, segs, dirs, perf_len, score_len, o_perf, o_masked, o_labels, o_score, o_segs, o_dirs, o_perf_mask,
                  o_score_mask, B: int, T: int, Fp: int, Fs: int, Fd: int, ignore_dims: int, ignore_ids: int, mask_token: int,

@@ -112,3 +112,25 @@ def test_render_256_notes_token_exact_outside_near_ties():
     print(f"{int(diff.sum())} of {diff.numel()} decisions differ; {int(tie.sum())} reference decisions are near-ties; flipped near-ties: {near}")
     assert not bad, f"tokens differ from the reference where its top-2 gap is not a near-tie: {bad}"
     assert len(near) <= diff.numel() // 100, f"more than 1 % of the decisions flipped: {near}"
+
+
+@pytest.mark.parametrize("B,T", [(5, 40), (64, 130)])
+def test_persistent_decode_stack_matches_operator_path(monkeypatch, B, T):
+    """csrc/decode_stack.cu (one persistent kernel per note-step for the whole decoder stack) against the launch-per-operator
+    path it replaces, on the same weights / caches: identical tokens except near-ties, and hidden states within bf16 noise."""
+    from scoreperformer_b200.decode import render_batch
+    model = parity.build_model(dropout=False, device="cuda").eval()
+    batch = parity.make_batch(B, T, seed=31, deadpan_last=False)
+    b, enc = _encoders(model, batch)
+    tokens = b["masked_perf"].clone()
+    tokens[:, 0] = b["perf"][:, 0]
+    outs = {}
+    for mode in ("legacy", "fused"):
+        monkeypatch.setenv("SPB_DECODE", mode)
+        outs[mode] = render_batch(model, tokens, b["masked_perf"], enc.score_embeddings, enc.perf_embeddings, mask=b["perf_mask"],
+                                  teacher=b["perf"], use_graph=(mode == "fused"))
+    fields = [3, 5, 10, 11]
+    valid = b["perf_mask"][:, 1:, None].expand(-1, -1, len(fields))
+    same = (outs["fused"][:, 1:, fields] == outs["legacy"][:, 1:, fields])[valid]
+    assert float(same.float().mean()) > 0.97, float(same.float().mean())
+    assert int((outs["fused"] == 1).sum()) == int((tokens[:, 0] == 1).sum())        # every MASK after note 0 was filled
