@@ -63,7 +63,7 @@ def main():
         "config": {"workload": f"configs[4]: {B} scores x {T} notes, fields (3,5,10,11) rendered note by note", "scores": B, "notes": T},
         "seconds": dt, "encoder_seconds": t_enc, "gpu_launches": K.LAUNCHES, "filled_mask_tokens": int((out != tokens).sum()),
         "roofline": {"bound": "hbm", "achieved": kv_bytes / dt / 1e9, "peak": 6450.6, "unit": "GB/s", "frac": kv_bytes / dt / 1e9 / 6450.6,
-                     "note": "algorithmic KV-cache reads only; one note-step (~45 small launches, positions device-side) is captured in a CUDA graph and replayed; a persistent single-kernel decode step is the next step"},
+                     "note": "algorithmic KV-cache reads only (SURVEY 8(d)); a note-step is ~15 launches captured in a CUDA graph: the embedding front (8), ONE persistent kernel for the 4-layer decoder stack (grid-barrier phases, csrc/decode_stack.cu), head projection + LayerNorm (3) and ONE head + sampling kernel"},
         "cpu_baseline": {"value": (n - 1) / dt_cpu, "unit": "notes/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"oracle port of unmask_tokens, batch 1, cached, {n} notes"}}))
 

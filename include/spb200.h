@@ -84,6 +84,13 @@ int spb_decode_stack_step(const float* x_in, const float* style, int S, const vo
                           int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap, void* gb, void* qkv, void* o,
                           void* hmid, float* xres, float* hid_out, float* out, unsigned* barrier, float eps, spb_stream_t stream);
 
+/* Tied heads of the rendered fields + sampling in one launch (modules/sampling.py:28-59, wrappers.py:358-397): per listed field
+ * (host int arrays: field index, first table row, vocabulary <= 256, top-k <= 32; k = 1 is greedy) logits = e_f . table_f^T stay in
+ * registers, tokens [0, n_banned) are never emitted, and the drawn token is written to tokens[b, *pos_dev + 1, field] (int64 [B,T,F]). */
+int spb_sample_fields(const void* e, int ld_e, const void* table, const int* fields, const int* offsets, const int* vocab, const int* topk,
+                      int n_fields, int n_banned, float temperature, uint64_t seed, const long long* pos_dev, long long* tokens, int B,
+                      int T, int F, spb_stream_t stream);
+
 /* Device side of the collator (data/collators/performance.py:239-255 MixedLM mask_sequence, score_performance.py:186-234): expands a
  * packed batch -- uint16 tokens, int32 segment ids [3, n] (bars | beats | onsets), uint8 directions, int32 lengths -- into the int64
  * tensors and bool masks the model consumes, and derives masked tokens / labels from the performance tokens.  ignore_dims /

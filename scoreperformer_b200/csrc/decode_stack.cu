@@ -100,6 +100,30 @@ __device__ __forceinline__ void tile_mma(float (&acc)[4], const __nv_bfloat16* s
     }
 }
 
+// The same product with the weight fragments fetched up front: a tile's 2 * KSTEPS 32-bit loads leave together BEFORE the
+// activation tile is staged, so one L2 round trip (not KSTEPS / 4 of them) sits on the tile's critical path.
+template <int KSTEPS>
+__device__ __forceinline__ void load_w(uint32_t (&bf)[2 * KSTEPS], const __nv_bfloat16* __restrict__ W, int ldw, int n_row, int lane) {
+    const __nv_bfloat16* wr = W + (size_t)(n_row + (lane >> 2)) * ldw + (lane & 3) * 2;
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) {
+        bf[2 * k] = __ldg(reinterpret_cast<const uint32_t*>(wr + 16 * k));
+        bf[2 * k + 1] = __ldg(reinterpret_cast<const uint32_t*>(wr + 16 * k + 8));
+    }
+}
+template <int KSTEPS>
+__device__ __forceinline__ void mma_pre(float (&acc)[4], const __nv_bfloat16* sA, int lda, const uint32_t (&bf)[2 * KSTEPS], int warp, int lane) {
+    const int g = lane >> 2, tig = lane & 3;
+    const __nv_bfloat16* a_lo = sA + (size_t)((warp & 1) * 16 + g) * lda + tig * 2;
+    const __nv_bfloat16* a_hi = a_lo + 8 * lda;
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) {
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(a_lo + 16 * k), a1 = *reinterpret_cast<const uint32_t*>(a_hi + 16 * k);
+        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(a_lo + 16 * k + 8), a3 = *reinterpret_cast<const uint32_t*>(a_hi + 16 * k + 8);
+        mma_bf16_16816(acc, a0, a1, a2, a3, bf[2 * k], bf[2 * k + 1]);
+    }
+}
+
 // AdaLN of 32 rows of the fp32 residual stream -> bf16 smem tile [32][DS_LDA]; one warp per 4 rows (rows beyond B are zeroed)
 __device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres, const __nv_bfloat16* gb, int ld_gb, int norm_idx, int row0,
                                             int B, float eps, int warp, int lane) {
@@ -194,11 +218,13 @@ decode_stack_kernel(DecodeStackParams p) {
             const int col_blocks = DS_QKV / DS_TN;
             for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
                 const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                uint32_t bf[32];
+                load_w<16>(bf, p.wqkv[l], DS_D, cb * DS_TN + (warp >> 1) * 8, lane);
                 __syncthreads();
                 stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l, rb * DS_TM, B, p.eps, warp, lane);
                 __syncthreads();
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                tile_mma(acc, sA, DS_LDA, p.wqkv[l], DS_D, cb * DS_TN, DS_D, warp, lane);
+                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
                 const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -209,86 +235,155 @@ decode_stack_kernel(DecodeStackParams p) {
         }
         grid_barrier(p.barrier, epoch);
 
-        // ---- B: append k|v, attention of the new query over the cache.  Two scores per CTA at a time: warps 0-3 / 4-7 = heads.
+        // ---- B: append k|v, attention of the new query over the cache.  Two scores per CTA at a time (warps 0-3 / 4-7).  MQA: the
+        // four heads share K and V, so the four warps of a score split the KEYS and each evaluates all four heads on its quarter
+        // -- every cache row is fetched once, and a warp walks a quarter of the sequential load -> use -> load chain.
         {
             const int n_keys = min(p.cap, pos + 1);
             const float scale = rsqrtf((float)DS_DH);
+            float* sS = sP;                                                   // [2 scores][4 heads][cap] scores / numerators
+            float* sRed = sP + (size_t)(DS_THREADS / 32) * p.cap;             // [2][4 warps][4 heads] maxima, then [2][4][4] sums
+            float* sO = sRed + 64;                                            // [2][4 warps][4 heads][64] partial outputs
+            constexpr int UNR = 8;
+            const int bl = warp >> 2, wq = warp & 3;
+            const int grp = lane >> 3, sub = lane & 7;
+            const int per_warp = ((n_keys + 3) / 4 + 3) & ~3;                 // keys per warp, a multiple of 4
+            const int k_lo = wq * per_warp, k_hi = min(n_keys, k_lo + per_warp);
             for (int pair = blockIdx.x; pair * 2 < B; pair += gridDim.x) {
-                const int b = pair * 2 + (warp >> 2), h = warp & 3;
+                const int b = pair * 2 + bl;
+                const bool live = b < B;
                 __syncthreads();
-                if (b < B) {
-                    __nv_bfloat16* kvb = p.kv[l] + (size_t)b * p.cap * 128;
+                if (live) {
+                    __nv_bfloat16* kvw = p.kv[l] + (size_t)b * p.cap * 128;
                     const int lw = threadIdx.x & 127;
                     if (lw < 16 && pos < p.cap)
-                        reinterpret_cast<uint4*>(kvb + (size_t)pos * 128)[lw] = reinterpret_cast<const uint4*>(p.qkv + (size_t)b * DS_QKV + DS_H * DS_DH)[lw];
+                        reinterpret_cast<uint4*>(kvw + (size_t)pos * 128)[lw] = reinterpret_cast<const uint4*>(p.qkv + (size_t)b * DS_QKV + DS_H * DS_DH)[lw];
                 }
                 __syncthreads();
-                if (b >= B) continue;
-                const __nv_bfloat16* kvb = p.kv[l] + (size_t)b * p.cap * 128;
-                float* pr = sP + (size_t)warp * p.cap;
-                const float slope = __expf(p.logslopes[l][h]);
-                float qv[DS_DH];
-                {
-                    const __nv_bfloat16* qr = p.qkv + (size_t)b * DS_QKV + h * DS_DH;
+                const __nv_bfloat16* kvb = p.kv[l] + (size_t)(live ? b : 0) * p.cap * 128;
+                float* ss = sS + (size_t)bl * 4 * p.cap;
+                float qs[4][8];
 #pragma unroll
-                    for (int c = 0; c < DS_DH / 8; ++c) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(qr + c * 8);
-                        const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-                        qv[c * 8 + 0] = a.x; qv[c * 8 + 1] = a.y; qv[c * 8 + 2] = b2.x; qv[c * 8 + 3] = b2.y;
-                        qv[c * 8 + 4] = c2.x; qv[c * 8 + 5] = c2.y; qv[c * 8 + 6] = d.x; qv[c * 8 + 7] = d.y;
-                    }
+                for (int h = 0; h < 4; ++h) {
+                    const uint4 u = live ? *reinterpret_cast<const uint4*>(p.qkv + (size_t)b * DS_QKV + h * DS_DH + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+                    const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+                    qs[h][0] = a.x * scale; qs[h][1] = a.y * scale; qs[h][2] = b2.x * scale; qs[h][3] = b2.y * scale;
+                    qs[h][4] = c2.x * scale; qs[h][5] = c2.y * scale; qs[h][6] = d.x * scale; qs[h][7] = d.y * scale;
                 }
-                float mx = -INFINITY;
-                for (int j = lane; j < n_keys; j += 32) {
-                    const bool ok = p.key_mask == nullptr || p.key_mask[(size_t)b * p.cap + j];
-                    float s = -INFINITY;
-                    if (ok) {
-                        const __nv_bfloat16* kr = kvb + (size_t)j * 128;
-                        float acc = 0.f;
+                float slope[4];
 #pragma unroll
-                        for (int c = 0; c < DS_DH / 8; ++c) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
-                            const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-                            acc += qv[c * 8] * a.x + qv[c * 8 + 1] * a.y + qv[c * 8 + 2] * b2.x + qv[c * 8 + 3] * b2.y + qv[c * 8 + 4] * c2.x +
-                                   qv[c * 8 + 5] * c2.y + qv[c * 8 + 6] * d.x + qv[c * 8 + 7] * d.y;
+                for (int h = 0; h < 4; ++h) slope[h] = __expf(p.logslopes[l][h]);
+                float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (live) {
+                    for (int base = k_lo; base < k_hi; base += 4 * UNR) {          // warp-uniform trip count: the body shuffles
+                        uint4 kq[UNR];
+#pragma unroll
+                        for (int u_ = 0; u_ < UNR; ++u_) {
+                            const int j = base + grp + 4 * u_;
+                            kq[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(kvb + (size_t)j * 128 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
                         }
-                        s = acc * scale - slope * (float)(pos - j);
+#pragma unroll
+                        for (int u_ = 0; u_ < UNR; ++u_) {
+                            const int j = base + grp + 4 * u_;
+                            const float2 a = unpack_bf16x2(kq[u_].x), b2 = unpack_bf16x2(kq[u_].y), c2 = unpack_bf16x2(kq[u_].z), d = unpack_bf16x2(kq[u_].w);
+                            float acc[4];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                acc[h] = qs[h][0] * a.x + qs[h][1] * a.y + qs[h][2] * b2.x + qs[h][3] * b2.y + qs[h][4] * c2.x + qs[h][5] * c2.y +
+                                         qs[h][6] * d.x + qs[h][7] * d.y;
+                                acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+                                acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
+                                acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 4);
+                            }
+                            if (j < k_hi) {
+                                const bool ok = p.key_mask == nullptr || p.key_mask[(size_t)b * p.cap + j];
+                                const float dist = (float)(pos - j);
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const float sc = ok ? acc[h] - slope[h] * dist : -INFINITY;
+                                    if (sub == h) ss[(size_t)h * p.cap + j] = sc;
+                                    mx[h] = fmaxf(mx[h], sc);
+                                }
+                            }
+                        }
                     }
-                    pr[j] = s;
-                    mx = fmaxf(mx, s);
-                }
-                mx = warp_max(mx);
-                const float m_use = mx == -INFINITY ? 0.f : mx;
-                float sum = 0.f;
-                for (int j = lane; j < n_keys; j += 32) {
-                    const float e = __expf(pr[j] - m_use);
-                    pr[j] = e;
-                    sum += e;
-                }
-                sum = warp_sum(sum);
-                __syncwarp();
-                const float inv = sum > 0.f ? 1.f / sum : 0.f;
-                const int grp = lane >> 3, sub = lane & 7;
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = 0.f;
-                const __nv_bfloat16* vbase = kvb + DS_DH + sub * 8;
-                for (int j = grp; j < n_keys; j += 4) {
-                    const float p0 = pr[j];
-                    const uint4 u0 = *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128);
-                    const float2 a0 = unpack_bf16x2(u0.x), a1 = unpack_bf16x2(u0.y), a2 = unpack_bf16x2(u0.z), a3 = unpack_bf16x2(u0.w);
-                    o[0] += p0 * a0.x; o[1] += p0 * a0.y; o[2] += p0 * a1.x; o[3] += p0 * a1.y;
-                    o[4] += p0 * a2.x; o[5] += p0 * a2.y; o[6] += p0 * a3.x; o[7] += p0 * a3.y;
                 }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
-                    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+                for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
+                if (lane < 4) sRed[(bl * 4 + wq) * 4 + lane] = mx[lane];
+                __syncthreads();
+                float m_use[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float m = fmaxf(fmaxf(sRed[(bl * 4 + 0) * 4 + h], sRed[(bl * 4 + 1) * 4 + h]),
+                                          fmaxf(sRed[(bl * 4 + 2) * 4 + h], sRed[(bl * 4 + 3) * 4 + h]));
+                    m_use[h] = m == -INFINITY ? 0.f : m;
                 }
-                if (grp == 0)
-                    *reinterpret_cast<uint4*>(p.o + (size_t)b * DS_D + h * DS_DH + sub * 8) =
-                        make_uint4(pack_bf16x2(o[0] * inv, o[1] * inv), pack_bf16x2(o[2] * inv, o[3] * inv),
-                                   pack_bf16x2(o[4] * inv, o[5] * inv), pack_bf16x2(o[6] * inv, o[7] * inv));
+                __syncthreads();                              // everyone has read the maxima: the slots are reused for the sums
+                float o[4][8], sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[h][e] = 0.f;
+                if (live) {
+                    const __nv_bfloat16* vbase = kvb + DS_DH + sub * 8;
+                    for (int base = k_lo; base < k_hi; base += 4 * UNR) {
+                        uint4 vq[UNR];
+#pragma unroll
+                        for (int u_ = 0; u_ < UNR; ++u_) {
+                            const int j = base + grp + 4 * u_;
+                            vq[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                        for (int u_ = 0; u_ < UNR; ++u_) {
+                            const int j = base + grp + 4 * u_;
+                            if (j < k_hi) {
+                                const float2 a0 = unpack_bf16x2(vq[u_].x), a1 = unpack_bf16x2(vq[u_].y), a2 = unpack_bf16x2(vq[u_].z), a3 = unpack_bf16x2(vq[u_].w);
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const float e = __expf(ss[(size_t)h * p.cap + j] - m_use[h]);
+                                    sum[h] += e;
+                                    o[h][0] += e * a0.x; o[h][1] += e * a0.y; o[h][2] += e * a1.x; o[h][3] += e * a1.y;
+                                    o[h][4] += e * a2.x; o[h][5] += e * a2.y; o[h][6] += e * a3.x; o[h][7] += e * a3.y;
+                                }
+                            }
+                        }
+                    }
+                }
+                // the four key groups of the warp meet through shuffles, the four warps of the score through shared memory
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 8);
+                    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 16);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        o[h][e] += __shfl_xor_sync(0xffffffffu, o[h][e], 8);
+                        o[h][e] += __shfl_xor_sync(0xffffffffu, o[h][e], 16);
+                    }
+                }
+                if (grp == 0) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sO[((size_t)(bl * 4 + wq) * 4 + h) * 64 + sub * 8 + e] = o[h][e];
+                    if (sub == 0)
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) sRed[(bl * 4 + wq) * 4 + h] = sum[h];      // every lane of a group holds the same sums
+                }
+                __syncthreads();
+                if (live) {
+                    // warp wq finishes head wq: 64 dims, two per lane
+                    const int h = wq;
+                    const float tot = sRed[(bl * 4 + 0) * 4 + h] + sRed[(bl * 4 + 1) * 4 + h] + sRed[(bl * 4 + 2) * 4 + h] + sRed[(bl * 4 + 3) * 4 + h];
+                    const float inv = tot > 0.f ? 1.f / tot : 0.f;
+                    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+                    for (int w2 = 0; w2 < 4; ++w2) {
+                        r0 += sO[((size_t)(bl * 4 + w2) * 4 + h) * 64 + lane * 2];
+                        r1 += sO[((size_t)(bl * 4 + w2) * 4 + h) * 64 + lane * 2 + 1];
+                    }
+                    *reinterpret_cast<uint32_t*>(p.o + (size_t)b * DS_D + h * DS_DH + lane * 2) = pack_bf16x2(r0 * inv, r1 * inv);
+                }
             }
         }
         grid_barrier(p.barrier, epoch);
@@ -298,11 +393,13 @@ decode_stack_kernel(DecodeStackParams p) {
             const int col_blocks = DS_D / DS_TN;
             for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
                 const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                uint32_t bf[32];
+                load_w<16>(bf, p.wo[l], DS_D, cb * DS_TN + (warp >> 1) * 8, lane);
                 __syncthreads();
                 stage_rows(sA, p.o, DS_D, 0, DS_D, rb * DS_TM, B);
                 __syncthreads();
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                tile_mma(acc, sA, DS_LDA, p.wo[l], DS_D, cb * DS_TN, DS_D, warp, lane);
+                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
                 const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -324,28 +421,26 @@ decode_stack_kernel(DecodeStackParams p) {
 
         // ---- D: h = GLU(AdaLN(x) W1^T + b1): a tile is 32 rows x 16 hidden units (16 value + 16 gate columns)
         {
-            const int col_blocks = DS_HID / 16;
-            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+            // every CTA takes a contiguous run of tiles (column blocks fastest): the AdaLN'd rows are staged once per run
+            const int col_blocks = DS_HID / 16, total = row_blocks * col_blocks;
+            const int per_cta = (total + gridDim.x - 1) / gridDim.x;
+            const int t_lo = blockIdx.x * per_cta, t_hi = min(total, t_lo + per_cta);
+            int staged_rb = -1;
+            for (int t = t_lo; t < t_hi; ++t) {
                 const int rb = t / col_blocks, cb = t - rb * col_blocks;
-                __syncthreads();
-                stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
-                __syncthreads();
                 // warps 0-3 (n-pieces 0,1 of the tile) take the value columns, warps 4-7 the matching gate columns
                 const int piece = (warp >> 1) & 1, is_gate = warp >> 2;
                 const int wrow0 = (is_gate ? DS_HID : 0) + cb * 16 + piece * 8;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                {
-                    const __nv_bfloat16* a_lo = sA + (size_t)((warp & 1) * 16 + g) * DS_LDA + tig * 2;
-                    const __nv_bfloat16* a_hi = a_lo + 8 * DS_LDA;
-                    const __nv_bfloat16* wr = p.w1[l] + (size_t)(wrow0 + g) * DS_D + tig * 2;
-#pragma unroll 4
-                    for (int k = 0; k < DS_D; k += 16) {
-                        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(a_lo + k), a1 = *reinterpret_cast<const uint32_t*>(a_hi + k);
-                        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(a_lo + k + 8), a3 = *reinterpret_cast<const uint32_t*>(a_hi + k + 8);
-                        const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wr + k)), b1 = __ldg(reinterpret_cast<const uint32_t*>(wr + k + 8));
-                        mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
-                    }
+                uint32_t bf[32];
+                load_w<16>(bf, p.w1[l], DS_D, wrow0, lane);
+                if (rb != staged_rb) {
+                    __syncthreads();
+                    stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
+                    staged_rb = rb;
                 }
+                __syncthreads();
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
                 const int wcol = wrow0 + tig * 2;
                 acc[0] += p.b1[l][wcol]; acc[1] += p.b1[l][wcol + 1]; acc[2] += p.b1[l][wcol]; acc[3] += p.b1[l][wcol + 1];
                 // value and gate of the same (row, hidden) live in warps w and w + 4: exchange through smem (reuse the score area)
@@ -380,11 +475,13 @@ decode_stack_kernel(DecodeStackParams p) {
             for (int t = blockIdx.x; t < row_blocks * col_blocks * splits; t += gridDim.x) {
                 const int sp = t / (row_blocks * col_blocks), rem = t - sp * row_blocks * col_blocks;
                 const int rb = rem / col_blocks, cb = rem - rb * col_blocks;
+                uint32_t bf[32];
+                load_w<16>(bf, p.w2[l] + sp * DS_D, DS_HID, cb * DS_TN + (warp >> 1) * 8, lane);
                 __syncthreads();
                 stage_rows(sA, p.hmid, DS_HID, sp * DS_D, DS_D, rb * DS_TM, B);
                 __syncthreads();
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                tile_mma(acc, sA, DS_LDA, p.w2[l] + sp * DS_D, DS_HID, cb * DS_TN, DS_D, warp, lane);
+                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
                 const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -460,10 +557,135 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     p.gb = reinterpret_cast<__nv_bfloat16*>(gb); p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv);
     p.o = reinterpret_cast<__nv_bfloat16*>(o); p.hmid = reinterpret_cast<__nv_bfloat16*>(hmid);
     p.xres = xres; p.hid_out = hid_out; p.out = out; p.barrier = barrier; p.eps = eps;
-    const int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 4 * 32 * 4 * 4;
+    const int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4;
     SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
     decode_stack_kernel<<<spb_num_sms(), DS_THREADS, smem, stream>>>(p);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// ============================================================================================================================
+// Tied output heads of the rendered fields + token sampling in one launch (modules/sampling.py:28-59 top-k filtering, softmax at
+// a temperature, one draw; models/scoreperformer/wrappers.py:358-397: PAD and MASK are never emitted).  One CTA per score, one
+// warp per field: logits = e_f . table_f^T stay in registers (V <= 256: up to 8 per lane), the k largest are peeled off by k
+// warp-wide arg-max rounds (k = 1 is greedy decoding: the lowest index wins ties, like torch.argmax), the draw uses a counter
+// based hash of (seed, position, score, field), and the token goes straight into tokens[b, pos + 1, field].
+namespace {
+
+constexpr int SF_MAX_FIELDS = 8;
+
+struct SampleParams {
+    const __nv_bfloat16* e;       // [B, ld_e] normalised head projection (all fields)
+    int ld_e;
+    const __nv_bfloat16* table;   // [sum V, 128]
+    int n_fields;
+    int field[SF_MAX_FIELDS], offset[SF_MAX_FIELDS], V[SF_MAX_FIELDS], k[SF_MAX_FIELDS];
+    int n_banned;                 // tokens [0, n_banned) are never emitted
+    float inv_temperature;
+    uint64_t seed;
+    const long long* pos_dev;
+    long long* tokens;            // [B, T, F]
+    int T, F;
+};
+
+__global__ void __launch_bounds__(32 * SF_MAX_FIELDS)
+sample_fields_kernel(SampleParams p) {
+    __shared__ float s_e[SF_MAX_FIELDS][128];
+    const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w >= p.n_fields) return;
+    const int f = p.field[w], V = p.V[w], k = p.k[w];
+    const long long pos = *p.pos_dev;
+    {
+        const uint2 u = *reinterpret_cast<const uint2*>(p.e + (size_t)b * p.ld_e + f * 128 + lane * 4);
+        const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+        s_e[w][lane * 4] = a.x; s_e[w][lane * 4 + 1] = a.y; s_e[w][lane * 4 + 2] = c.x; s_e[w][lane * 4 + 3] = c.y;
+    }
+    __syncwarp();
+    float lg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int v = lane + 32 * i;
+        float acc = -INFINITY;
+        if (v < V && v >= p.n_banned) {
+            const __nv_bfloat16* tr = p.table + (size_t)(p.offset[w] + v) * 128;
+            acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const uint4 u = *reinterpret_cast<const uint4*>(tr + c * 8);
+                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                const float* ev = &s_e[w][c * 8];
+                acc += ev[0] * a0.x + ev[1] * a0.y + ev[2] * a1.x + ev[3] * a1.y + ev[4] * a2.x + ev[5] * a2.y + ev[6] * a3.x + ev[7] * a3.y;
+            }
+        }
+        lg[i] = acc;
+    }
+    // k rounds of warp arg-max: round t leaves its winner (value, token) in lane t
+    float top_val = -INFINITY;
+    int top_idx = 0;
+    for (int t = 0; t < k; ++t) {
+        float best = -INFINITY;
+        int best_i = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int v = lane + 32 * i;
+            if (lg[i] > best) { best = lg[i]; best_i = v; }      // ascending v within a lane: the lowest index wins ties
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+        }
+        if (lane == t) { top_val = best; top_idx = best_i; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lane + 32 * i == best_i) lg[i] = -INFINITY;
+    }
+    int token = __shfl_sync(0xffffffffu, top_idx, 0);
+    if (k > 1) {
+        // softmax over the k kept logits at the temperature, then one draw by inverse cdf
+        const float m = __shfl_sync(0xffffffffu, top_val, 0);
+        float pr = (lane < k && top_val > -INFINITY) ? __expf((top_val - m) * p.inv_temperature) : 0.f;
+        float cdf = pr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, cdf, o);
+            if (lane >= o) cdf += up;
+        }
+        const float total = __shfl_sync(0xffffffffu, cdf, 31);
+        const uint32_t r = spb_hash32(p.seed + (uint64_t)pos * 0x9E3779B97F4A7C15ull, (uint64_t)b * SF_MAX_FIELDS + (uint64_t)w);
+        const float u01 = (float)(r >> 8) * (1.f / 16777216.f) * total;
+        const unsigned ge = __ballot_sync(0xffffffffu, lane < k && cdf > u01);
+        const int pick = ge != 0 ? __ffs(ge) - 1 : k - 1;
+        token = __shfl_sync(0xffffffffu, top_idx, pick);
+    }
+    if (lane == 0 && pos + 1 < p.T) p.tokens[((size_t)b * p.T + (size_t)(pos + 1)) * p.F + f] = token;
+}
+
+}  // namespace
+
+// e bf16 [B, ld_e] (LayerNorm'ed head projection, 128 columns per field), table bf16 [sum V, 128]; for each of the n_fields listed
+// fields (field index, first table row, vocabulary, k of the top-k filter; k = 1: greedy) one token is written to
+// tokens[b, *pos_dev + 1, field] (int64 [B, T, F]).  V <= 256, k <= 32, at most 8 fields.
+extern "C" int spb_sample_fields(const void* e, int ld_e, const void* table, const int* fields, const int* offsets, const int* vocab,
+                                 const int* topk, int n_fields, int n_banned, float temperature, uint64_t seed, const long long* pos_dev,
+                                 long long* tokens, int B, int T, int F, cudaStream_t stream) {
+    if (B <= 0 || n_fields <= 0) return SPB_OK;
+    SPB_CHECK_ARG(e && table && fields && offsets && vocab && topk && pos_dev && tokens, "spb_sample_fields: null pointer");
+    SPB_CHECK_ARG(n_fields <= SF_MAX_FIELDS && ld_e % 4 == 0 && temperature > 0.f, "spb_sample_fields: at most %d fields, ld_e %% 4 == 0, temperature > 0", SF_MAX_FIELDS);
+    SampleParams p;
+    p.e = reinterpret_cast<const __nv_bfloat16*>(e); p.ld_e = ld_e;
+    p.table = reinterpret_cast<const __nv_bfloat16*>(table);
+    p.n_fields = n_fields;
+    for (int i = 0; i < n_fields; ++i) {
+        SPB_CHECK_ARG(vocab[i] >= 1 && vocab[i] <= 256 && topk[i] >= 1 && topk[i] <= 32 && fields[i] >= 0 && fields[i] < F,
+                      "spb_sample_fields: field %d needs V <= 256 and 1 <= k <= 32 (V %d, k %d)", fields[i], vocab[i], topk[i]);
+        p.field[i] = fields[i]; p.offset[i] = offsets[i]; p.V[i] = vocab[i]; p.k[i] = topk[i] < vocab[i] ? topk[i] : vocab[i];
+    }
+    p.n_banned = n_banned; p.inv_temperature = 1.f / temperature; p.seed = seed; p.pos_dev = pos_dev;
+    p.tokens = tokens; p.T = T; p.F = F;
+    sample_fields_kernel<<<B, 32 * n_fields, 0, stream>>>(p);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

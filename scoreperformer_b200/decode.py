@@ -173,6 +173,11 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     if K.decode_stack_ok(sw.depth, sw.D, sw.H, sw.layers[0]["w2"].shape[1], sw.ada, style_f.shape[-1], T):
         plan = K.DecodeStackPlan(sw.layers, sw.w_ada, sw.b_ada, kv_caches, B, style_f.shape[-1])
 
+    ks = [top_k if top_k is not None else -(-sizes[f] // 10) for f in fields]
+    fused_sampling = (generator is None and emb == 128 and len(fields) <= 8 and all(sizes[f] <= 256 for f in fields)
+                      and all(1 <= k <= 32 for k in ks) and K._os.environ.get("SPB_DECODE", "fused") == "fused")
+    seed = K.seed_from_torch() if any(k > 1 for k in ks) else 0
+
     def step():
         nxt = pos_t + 1
         # decoder position i: full tuple of note i, masked tuple / context / style of note i+1 (wrappers.py:409-431)
@@ -191,22 +196,28 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
         # tied head for the masked fields only (wrappers.py:364-380)
         e_raw = K.gemm(K.cast_bf16(hid), whead16, trans_b=True, out_dtype=BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)
-        toks = []
-        for f in fields:
-            lg = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + sizes[f]], out_dtype=F32)
-            lg[:, :2] = neg_inf                                             # PAD / MASK are never emitted
-            k = top_k if top_k is not None else -(-sizes[f] // 10)
-            if k == 1:
-                tok = lg.argmax(dim=-1)
-            else:
-                val, ind = torch.topk(lg, k)
-                probs = torch.softmax(val / temperature, dim=-1)
-                tok = ind.gather(1, torch.multinomial(probs, 1, generator=generator)).squeeze(1)
-            toks.append(tok)
-        # out[:, i+1, fields] = toks
-        out_rows = out.view(B, T * F)
-        dst = nxt * F + field_idx                                           # [n_fields] flat column indices
-        out_rows.index_copy_(1, dst, torch.stack(toks, dim=1))
+        if fused_sampling:
+            # heads of the rendered fields, PAD / MASK ban, top-k filter, draw and token write: one launch
+            K.sample_fields(e, table16, fields, [offs[f] for f in fields], [sizes[f] for f in fields],
+                            [top_k if top_k is not None else -(-sizes[f] // 10) for f in fields], out, pos_t,
+                            temperature=temperature, seed=seed)
+        else:
+            toks = []
+            for f in fields:
+                lg = K.gemm(e[:, f * emb:(f + 1) * emb], table16[offs[f]:offs[f] + sizes[f]], out_dtype=F32)
+                lg[:, :2] = neg_inf                                             # PAD / MASK are never emitted
+                k = top_k if top_k is not None else -(-sizes[f] // 10)
+                if k == 1:
+                    tok = lg.argmax(dim=-1)
+                else:
+                    val, ind = torch.topk(lg, k)
+                    probs = torch.softmax(val / temperature, dim=-1)
+                    tok = ind.gather(1, torch.multinomial(probs, 1, generator=generator)).squeeze(1)
+                toks.append(tok)
+            # out[:, i+1, fields] = toks
+            out_rows = out.view(B, T * F)
+            dst = nxt * F + field_idx                                           # [n_fields] flat column indices
+            out_rows.index_copy_(1, dst, torch.stack(toks, dim=1))
         pos_t.add_(1)
 
     n_steps = T - 1

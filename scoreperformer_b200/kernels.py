@@ -189,6 +189,21 @@ class DecodeStackPlan:
         return self.out
 
 
+def sample_fields(e: Tensor, table16: Tensor, fields: Sequence[int], offsets: Sequence[int], vocab: Sequence[int], topk: Sequence[int],
+                  tokens: Tensor, pos_dev: Tensor, temperature: float = 1.0, seed: int = 0, n_banned: int = 2) -> None:
+    """Heads of `fields` + top-k sampling (k = 1: greedy) + write of tokens[:, pos + 1, field], one launch (csrc/decode_stack.cu)."""
+    import ctypes
+    _require_cuda(e, table16, tokens)
+    assert e.dtype == BF16 and e.stride(1) == 1 and table16.dtype == BF16 and table16.is_contiguous() and table16.shape[1] == 128
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and tokens.dim() == 3 and pos_dev.dtype == torch.int64
+    n = len(fields)
+    arr = lambda xs: (ctypes.c_int * n)(*[int(x) for x in xs])
+    B, T, F = tokens.shape
+    _call("spb_sample_fields", _p(e), e.stride(0), _p(table16), arr(fields), arr(offsets), arr(vocab), arr(topk), n, int(n_banned),
+          float(temperature), int(seed), _p(pos_dev), _p(tokens), B, T, F, _stream())
+    _count()
+
+
 def decode_stack_ok(depth: int, dim: int, heads: int, hidden: int, ada: bool, style_dim: int, cap: int) -> bool:
     return (ada and dim == 256 and heads == 4 and hidden == 1024 and 1 <= depth <= 8 and style_dim % 16 == 0 and 16 <= style_dim <= 256
             and cap <= 2048 and _os.environ.get("SPB_DECODE", "fused") == "fused")

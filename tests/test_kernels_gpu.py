@@ -572,3 +572,44 @@ def test_unpack_batch_matches_reference_collator(k):
         unpack_batch(packed, out=static)
         for name, want in batch.items():
             assert torch.equal(static[name].cpu(), want), name
+
+
+# ------------------------------------------------------------------ heads + sampling of the rendered fields
+def test_sample_fields_greedy_and_topk(k):
+    """spb_sample_fields: k = 1 is torch.argmax of the fp32 statement of the tied head (PAD / MASK banned); k > 1 only ever draws
+    from the k largest logits, every one of them, with frequencies that follow the softmax at the temperature."""
+    torch.manual_seed(12)
+    B, T, F_ = 64, 6, 12
+    sizes = [260, 132, 92, 132, 133, 125, 26, 69, 16, 16, 165, 85]
+    offs = [0]
+    for v in sizes[:-1]:
+        offs.append(offs[-1] + v)
+    fields = [3, 5, 10, 11]
+    table = randn(sum(sizes), 128, dtype=BF16, scale=0.3)
+    e = randn(B, F_ * 128, dtype=BF16)
+    tokens = torch.zeros(B, T, F_, dtype=torch.int64, device="cuda")
+    pos = torch.tensor([2], device="cuda")
+    logits = {f: e[:, f * 128:(f + 1) * 128].float() @ table[offs[f]:offs[f] + sizes[f]].float().t() for f in fields}
+    for f in fields:
+        logits[f][:, :2] = -float("inf")
+    k.sample_fields(e, table, fields, [offs[f] for f in fields], [sizes[f] for f in fields], [1] * 4, tokens, pos)
+    for f in fields:
+        top2 = logits[f].topk(2, dim=-1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-3                    # bf16 products summed in a different order: skip numerical ties
+        assert torch.equal(tokens[clear, 3, f], logits[f].argmax(-1)[clear]), f
+    assert int(tokens[:, :3].abs().sum()) == 0 and int(tokens[:, 4:].abs().sum()) == 0
+    untouched = [f for f in range(F_) if f not in fields]
+    assert int(tokens[:, 3, untouched].abs().sum()) == 0
+    # top-k sampling: one row repeated, many seeds
+    kk, temp, n_draw = 5, 0.7, 4096
+    e1 = e[:1].repeat(n_draw, 1).contiguous()
+    tok = torch.zeros(n_draw, T, F_, dtype=torch.int64, device="cuda")
+    for rep in range(4):
+        k.sample_fields(e1, table, fields, [offs[f] for f in fields], [sizes[f] for f in fields], [kk] * 4, tok, pos, temperature=temp, seed=1000 + rep)
+        for f in fields:
+            val, ind = logits[f][0].topk(kk)
+            drawn = tok[:, 3, f]
+            assert bool(torch.isin(drawn, ind).all()), f
+            want = torch.softmax(val / temp, -1)
+            got = torch.stack([(drawn == i).float().mean() for i in ind])
+            assert float((got - want).abs().max()) < 0.04, (f, got.tolist(), want.tolist())
