@@ -12,6 +12,7 @@ Two entry points over the same kernels:
 """
 from __future__ import annotations
 
+import math
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -120,6 +121,15 @@ def cached_stack_step(tr, x: Tensor, mask: Optional[Tensor], style: Optional[Ten
 def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor, style: Tensor, mask: Optional[Tensor] = None,
                  fields: Sequence[int] = (3, 5, 10, 11), temperature: float = 1.0, top_k: Optional[int] = 1,
                  generator: Optional[torch.Generator] = None, teacher: Optional[Tensor] = None, use_graph: bool = True) -> Tensor:
+    """`render_decoder` on the performance decoder of a ScorePerformer model."""
+    return render_decoder(model.perf_decoder.model, perf, masked_perf, score_hidden, style, mask=mask, fields=fields,
+                          temperature=temperature, top_k=top_k, generator=generator, teacher=teacher, use_graph=use_graph)
+
+
+@torch.no_grad()
+def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor, style: Tensor, mask: Optional[Tensor] = None,
+                   fields: Sequence[int] = (3, 5, 10, 11), temperature: float = 1.0, top_k: Optional[int] = 1,
+                   generator: Optional[torch.Generator] = None, teacher: Optional[Tensor] = None, use_graph: bool = True) -> Tensor:
     """Fill `fields` of every note >= 1 of `perf` [B, T, F], note by note, for all B scores in lockstep.
 
     perf / masked_perf: int64 [B, T, F]; score_hidden fp32 [B, T, D]; style fp32 [B, T, S]; mask bool [B, T].
@@ -130,7 +140,6 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     `use_graph`: capture one note-step in a CUDA graph and replay it (positions are device-side); sampling with a custom
     `generator` runs eagerly.
     """
-    dec = model.perf_decoder.model
     te_mod, head = dec.token_emb, dec.lm_head
     B, T, F = perf.shape
     dev = perf.device
@@ -240,3 +249,168 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
         graph.replay()
     K.LAUNCHES += per_step * (n_steps - 2)       # ... each replay launches every recorded kernel
     return out
+
+
+# ----------------------------------------------------------------------------- reference-signature entry points
+# `unmask_tokens` / `generate` of the LM wrappers (models/scoreperformer/wrappers.py:200-307, 324-407 of the reference) keep their
+# argument lists and their cache contract, so inference/generators.py works unchanged -- but they are adapters over this file:
+# a whole window goes through `render_batch`'s device-resident loop whenever the request is expressible there (any batch size,
+# top-k / greedy sampling, no incoming caches, no per-key bans); everything else runs the general stepper below, which advances
+# one note per iteration through the cached stack step (persistent kernel) and samples on the host side of the logits.
+def _sampling_plan(filter_logits_fn, filter_kwargs, sizes: Sequence[int], fields: Sequence[int]):
+    """k per field if the filter is the reference's `top_k` (sampling.py:28-33), else None (host sampling)."""
+    from .modules import sampling
+    if filter_logits_fn is not sampling.top_k:
+        return None
+    kw = dict(filter_kwargs or {})
+    if set(kw) - {"k", "thres"}:
+        return None
+    ks = [int(kw["k"]) if kw.get("k") is not None else math.ceil((1 - kw.get("thres", 0.9)) * sizes[f]) for f in fields]
+    return ks if all(1 <= k <= 32 for k in ks) else None
+
+
+def _draw(logits: Dict[str, Tensor], banned: Sequence[int], filter_key_ids, filter_logits_fn, filter_kwargs, temperature: float) -> Tensor:
+    """One token per field from fp32 logits [B, V]: bans, the caller's filter, softmax at the temperature, a draw."""
+    from .modules.sampling import filter_logits_and_sample
+    cols = []
+    for key, lg in logits.items():
+        lg = lg.clone()
+        lg[:, list(banned)] = -float("inf")
+        extra = (filter_key_ids or {}).get(key)
+        if extra is not None:
+            lg[:, extra] = -float("inf")
+        cols.append(filter_logits_and_sample(lg, filter_logits_fn, filter_kwargs=filter_kwargs, temperature=temperature))
+    return torch.cat(cols, dim=-1)
+
+
+def _masked_columns(tokens: Tensor, mask_token_id: int):
+    """(note indices that contain a MASK, bool [F] of the masked fields) -- the same fields at every note of the window, as the
+    collator produces them; raises otherwise."""
+    hit = tokens == mask_token_id
+    notes = torch.nonzero(hit.any(dim=2).any(dim=0)).flatten()
+    cols = hit.any(dim=1).any(dim=0)
+    return notes, cols, hit
+
+
+@torch.inference_mode()
+def unmask_mixlm(wrapper, tokens: Tensor, tokens_masked: Tensor, temperature: float, filter_logits_fn, filter_kwargs, filter_key_ids,
+                 caches, return_caches: bool, **kwargs):
+    """MixedLM rendering with the reference's signature (wrappers.py:324-407): fill the MASKed fields of `tokens` note by note;
+    position i of the decoder sees the full tuple of note i and the masked tuple of note i+1."""
+    dec = wrapper.model
+    was_training = dec.training
+    dec.eval()
+    squeeze = tokens.dim() == 2
+    if squeeze:
+        tokens, tokens_masked = tokens[None], tokens_masked[None]
+    out = tokens.clone()
+    mask = kwargs.pop("mask", None)
+    notes, cols, hit = _masked_columns(out, wrapper.mask_token_id)
+    fields = torch.nonzero(cols).flatten().tolist()
+    sizes = dec.token_emb.field_sizes
+    ks = _sampling_plan(filter_logits_fn, filter_kwargs, sizes, fields)
+    context, style = kwargs.get("context"), kwargs.get("style_embeddings")
+    T = out.shape[1]
+    contiguous_tail = notes.numel() > 0 and int(notes[0]) >= 1 and torch.equal(notes, torch.arange(int(notes[0]), T, device=notes.device))
+    uniform = bool(hit[:, notes][..., cols].all()) if notes.numel() else False
+    fast = (ks is not None and caches is None and not return_caches and not filter_key_ids and contiguous_tail and int(notes[0]) == 1
+            and uniform and context is not None and style is not None and len(set(ks)) == 1 and set(kwargs) <= {"context", "style_embeddings"})
+    if fast:
+        res = render_decoder(dec, out, tokens_masked, context, style, mask=mask, fields=fields, temperature=temperature, top_k=ks[0])
+    else:
+        res, caches = _unmask_stepwise(wrapper, out, tokens_masked, mask, notes, hit, temperature, filter_logits_fn, filter_kwargs,
+                                       filter_key_ids, caches, kwargs)
+    dec.train(was_training)
+    res = res[0] if squeeze else res
+    return (res, caches) if return_caches else res
+
+
+def _unmask_stepwise(wrapper, out, tokens_masked, mask, notes, hit, temperature, filter_logits_fn, filter_kwargs, filter_key_ids, caches, kwargs):
+    """General stepper: one cached forward per note (the wrapper's own `forward` slices context / style / masks the way training
+    does), logits of the note's masked fields from the tied head, host-side filter + draw."""
+    names = list(wrapper.model.lm_head.embs.keys())
+    if mask is None:
+        mask = torch.ones(out.shape[:2], dtype=torch.bool, device=out.device)
+    for idx in notes.tolist():
+        keys = torch.nonzero(hit[0, idx]).flatten().tolist()
+        step = wrapper(out[:, :idx + 1], seq_masked=tokens_masked[:, :idx + 1], mask=mask[:, :idx + 1], return_embeddings=True,
+                       return_caches=True, caches=caches, **kwargs)
+        caches = step.caches
+        logits = wrapper.model.lm_head(step.hidden_state[:, idx - 1], keys=keys)
+        out[:, idx, keys] = _draw(logits, (wrapper.pad_token_id, wrapper.mask_token_id), filter_key_ids, filter_logits_fn, filter_kwargs,
+                                  temperature)
+    return out, caches
+
+
+@torch.inference_mode()
+def unmask_mlm(wrapper, tokens: Tensor, single_run: bool, temperature: float, filter_logits_fn, filter_kwargs, filter_key_ids, **kwargs):
+    """Masked-LM unmasking (wrappers.py:131-198 of the reference): every MASK at once from one forward (`single_run`, arg-max),
+    or note by note re-running the (uncached, bidirectional) model."""
+    dec = wrapper.model
+    was_training = dec.training
+    dec.eval()
+    squeeze = tokens.dim() == 2
+    out = (tokens[None] if squeeze else tokens).clone()
+    mask = kwargs.pop("mask", None)
+    if mask is None:
+        mask = torch.ones(out.shape[:2], dtype=torch.bool, device=out.device)
+    notes, _, hit = _masked_columns(out, wrapper.mask_token_id)
+    if single_run:
+        logits = dec(out, mask=mask, **kwargs).logits
+        best = torch.stack([lg.argmax(dim=-1) for lg in logits.values()], dim=-1)
+        out = torch.where(hit, best, out)
+    else:
+        for idx in notes.tolist():
+            keys = torch.nonzero(hit[0, idx]).flatten().tolist()
+            step = wrapper(out[:, :idx + 1], mask=mask[:, :idx + 1], return_embeddings=True, **kwargs)
+            logits = dec.lm_head(step.hidden_state[:, idx - 1], keys=keys)
+            out[:, idx, keys] = _draw(logits, range(wrapper.num_special_tokens), filter_key_ids, filter_logits_fn, filter_kwargs, temperature)
+    dec.train(was_training)
+    return out[0] if squeeze else out
+
+
+@torch.inference_mode()
+def generate_ar(wrapper, start_tokens: Tensor, seq_len: int, max_bar, temperature: float, filter_logits_fn, filter_kwargs, caches,
+                return_caches: bool, tokenizer, fix_errors: bool, **kwargs):
+    """Causal-LM continuation (wrappers.py:200-307 of the reference): append one sampled tuple per step through the cached stack
+    step until `seq_len`, EOS, or a bar beyond `max_bar`.  With a tokenizer and `fix_errors` the bar never decreases and the
+    tempo / time signature are held inside a bar."""
+    dec = wrapper.model
+    was_training = dec.training
+    dec.eval()
+    squeeze = start_tokens.dim() == 2
+    out = start_tokens[None] if squeeze else start_tokens
+    t0 = out.shape[1]
+    mask = kwargs.pop("mask", None)
+    if mask is None:
+        mask = torch.ones(out.shape[:2], dtype=torch.bool, device=out.device)
+    col = getattr(tokenizer, "vocab_types_idx", None) if fix_errors else None
+    for _ in range(t0, seq_len + 1):
+        window, wmask = out[:, -wrapper.max_seq_len:], mask[:, -wrapper.max_seq_len:]
+        step = wrapper(window, mask=wmask, caches=caches, return_embeddings=True, return_caches=True, **kwargs)
+        caches = step.caches
+        logits = dec.lm_head(step.hidden_state[:, -1])
+        last = out[:, -1]
+        new, bar_tok = [], None
+        for key, lg in logits.items():
+            if col is not None and key == "Bar":
+                lg = lg.clone()
+                lg[:, 4:int(last[0, col["Bar"]])] = -float("inf")           # bars only move forward
+            held = col is not None and (key == "TimeSig" or (key == "Tempo" and bar_tok is not None and bool((bar_tok == last[:, col["Bar"]]).all())))
+            tok = last[:, col[key]][:, None] if held else _draw({key: lg}, (0, 1), None, filter_logits_fn, filter_kwargs, temperature)
+            if key == "Bar":
+                bar_tok = tok[:, 0]
+            new.append(tok)
+        out = torch.cat([out, torch.cat(new, dim=-1)[:, None]], dim=1)
+        mask = torch.nn.functional.pad(mask, (0, 1), value=True)
+        if wrapper.eos_token_id is not None:
+            if bool((out[:, -1, 0] == wrapper.eos_token_id).any()):
+                out[:, -1, 1:] = wrapper.pad_token_id
+                break
+        elif max_bar is not None and bool((out[:, -1, 0] > max_bar).any()):
+            out = out[:, :-1]
+            break
+    out = out[:, t0:]
+    dec.train(was_training)
+    out = out[0] if squeeze else out
+    return (out, caches) if return_caches else out

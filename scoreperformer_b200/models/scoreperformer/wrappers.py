@@ -6,18 +6,16 @@ Rendering: `unmask_tokens` / `generate` keep the reference's argument lists and 
 """
 from __future__ import annotations
 
-import warnings
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Callable, Dict, Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch import Tensor
 
 from ... import fused
-from ...modules.sampling import filter_logits_and_sample, top_k
+from ...modules.sampling import top_k
 from ...utils import ExplicitEnum, exists
 from .embeddings import TupleTokenTiedLMHead
 from .transformer import TupleTransformer, TupleTransformerCaches, TupleTransformerOutput
@@ -131,59 +129,17 @@ class ScorePerformerLMWrapper(LMWrapper):
         return tv
 
 
-def _sample_fields(logits: Dict[str, Tensor], banned, filter_key_ids, filter_logits_fn, filter_kwargs, temperature):
-    samples = []
-    for key, lg in logits.items():
-        for tok in banned:
-            lg[:, tok] = -float("Inf")
-        ids = filter_key_ids.get(key, None)
-        if ids is not None:
-            lg[:, ids] = -float("Inf")
-        samples.append(filter_logits_and_sample(lg, filter_logits_fn, filter_kwargs=filter_kwargs, temperature=temperature))
-    return torch.cat(samples, dim=-1)[None]
-
-
 class ScorePerformerMLMWrapper(ScorePerformerLMWrapper):
     def __init__(self, model: TupleTransformer, mask_token_id: int = 1, num_special_tokens: int = 4, ignore_index: int = -100):
         super().__init__(model=model, ignore_index=ignore_index)
         self.mask_token_id = mask_token_id
         self.num_special_tokens = num_special_tokens
 
-    @torch.inference_mode()
     def unmask_tokens(self, tokens: Tensor, single_run: bool = True, temperature: float = 1., filter_logits_fn: Callable = top_k,
                       filter_kwargs=None, filter_key_ids=None, disable_tqdm: bool = False, **kwargs):
-        assert callable(filter_logits_fn)
-        was_training = self.model.training
-        if was_training:
-            self.model.eval()
-        num_dims = len(tokens.shape)
-        if num_dims == 2:
-            tokens = tokens[None, :]
-        out = tokens.clone().detach()
-        mask = kwargs.pop("mask", None)
-        if mask is None:
-            mask = torch.full_like(out[..., 0], True, dtype=torch.bool, device=out.device)
-        filter_key_ids = filter_key_ids or dict()
-        unmask_mask = out == self.mask_token_id
-        if single_run:
-            warnings.warn("`single_run` unmasking with sampling is not yet implemented, using argmax.")
-            outputs = self.model(out, mask=mask, **kwargs)
-            samples = torch.cat([torch.argmax(l, dim=-1, keepdim=True) for l in outputs.logits.values()], dim=-1)
-            out[unmask_mask] = samples[unmask_mask]
-        else:
-            unmask_ids = torch.where(torch.any(unmask_mask, dim=2))[1]
-            for idx in unmask_ids.tolist():
-                type_mask = unmask_mask[:, idx][0]
-                logits_keys = torch.where(type_mask)[0].tolist()
-                outputs = self(out[:, :idx + 1], mask=mask[:, :idx + 1], return_embeddings=True, **kwargs)
-                logits = self.model.lm_head(outputs.hidden_state[:, idx - 1], keys=logits_keys)
-                out[:, idx, type_mask] = _sample_fields(logits, range(self.num_special_tokens), filter_key_ids, filter_logits_fn,
-                                                        filter_kwargs, temperature)
-        if num_dims == 2:
-            out = out.squeeze(0)
-        if was_training:
-            self.model.train(was_training)
-        return out
+        """Reference signature (wrappers.py:131-198); the work is decode.unmask_mlm."""
+        from ... import decode
+        return decode.unmask_mlm(self, tokens, single_run, temperature, filter_logits_fn, filter_kwargs, filter_key_ids, **kwargs)
 
 
 class ScorePerformerARWrapper(ScorePerformerLMWrapper):
@@ -194,62 +150,13 @@ class ScorePerformerARWrapper(ScorePerformerLMWrapper):
         self.eos_token_id = eos_token_id
         self.num_special_tokens = num_special_tokens
 
-    @torch.inference_mode()
     def generate(self, start_tokens: Tensor, seq_len: int, max_bar: Optional[int] = None, temperature: float = 1.,
                  filter_logits_fn: Callable = top_k, filter_kwargs=None, caches: Optional[TupleTransformerCaches] = None,
                  return_caches: bool = False, tokenizer=None, fix_errors: bool = True, disable_tqdm: bool = False, **kwargs):
-        assert callable(filter_logits_fn)
-        was_training = self.model.training
-        if was_training:
-            self.model.eval()
-        num_dims = len(start_tokens.shape)
-        if num_dims == 2:
-            start_tokens = start_tokens[None, :]
-        b, t = start_tokens.shape[:2]
-        out = start_tokens
-        mask = kwargs.pop("mask", None)
-        if mask is None:
-            mask = torch.full_like(out[..., 0], True, dtype=torch.bool, device=out.device)
-        for _ in range(t, seq_len + 1):
-            x = out[:, -self.max_seq_len:]
-            mask = mask[:, -self.max_seq_len:]
-            outputs = self(x, mask=mask, caches=caches, return_embeddings=True, return_caches=True, **kwargs)
-            logits = self.model.lm_head(outputs.hidden_state[:, -1])
-            caches = outputs.caches
-            samples = {}
-            for key, logits_i in logits.items():
-                do_sample = True
-                if fix_errors and exists(tokenizer):
-                    if key == "Bar":
-                        last_bar = out[:, -1, tokenizer.vocab_types_idx["Bar"]]
-                        logits_i[:, 4:last_bar] = -float("Inf")
-                    same_bar = samples.get("Bar", -1) == out[:, -1, tokenizer.vocab_types_idx["Bar"]]
-                    if (key == "Tempo" and same_bar) or key == "TimeSig":
-                        sample = out[:, -1, tokenizer.vocab_types_idx[key]][None]
-                        do_sample = False
-                if do_sample:
-                    logits_i[:, :2] = -float("Inf")
-                    sample = filter_logits_and_sample(logits_i, filter_logits_fn, filter_kwargs=filter_kwargs, temperature=temperature)
-                samples[key] = sample
-            samples = torch.cat(list(samples.values()), dim=-1)[None]
-            out = torch.cat((out, samples), dim=1)
-            mask = F.pad(mask, (0, 1), value=True)
-            if exists(self.eos_token_id):
-                if (out[..., -1, 0] == self.eos_token_id).any(dim=-1):
-                    out[:, -1, 1:] = self.pad_token_id
-                    break
-            elif exists(max_bar):
-                if (out[..., -1, 0] > max_bar).any(dim=-1):
-                    out = out[:, :-1, :]
-                    break
-        out = out[:, t:]
-        if num_dims == 2:
-            out = out.squeeze(0)
-        if was_training:
-            self.model.train(was_training)
-        if return_caches:
-            return out, caches
-        return out
+        """Reference signature (wrappers.py:200-307); the work is decode.generate_ar (cached stack steps)."""
+        from ... import decode
+        return decode.generate_ar(self, start_tokens, seq_len, max_bar, temperature, filter_logits_fn, filter_kwargs, caches,
+                                  return_caches, tokenizer, fix_errors, **kwargs)
 
     def forward(self, seq: Tensor, labels: Optional[Tensor] = None, **kwargs):
         seq = seq[:, :-1]
@@ -274,43 +181,15 @@ class ScorePerformerMixedLMWrapper(ScorePerformerLMWrapper):
         self.mask_token_id = mask_token_id
         self.num_special_tokens = num_special_tokens
 
-    @torch.inference_mode()
     def unmask_tokens(self, tokens: Tensor, tokens_masked, temperature: float = 1., filter_logits_fn: Callable = top_k,
                       filter_kwargs=None, filter_key_ids=None, caches: Optional[TupleTransformerCaches] = None,
                       return_caches: bool = False, disable_tqdm: bool = False, **kwargs):
-        """Note-by-note unmasking with hidden/KV caches (wrappers.py:324-407); batch-1 like the reference.
-        The batched, device-resident renderer is scoreperformer_b200.decode.render_batch."""
-        assert callable(filter_logits_fn)
-        was_training = self.model.training
-        if was_training:
-            self.model.eval()
-        num_dims = len(tokens.shape)
-        if num_dims == 2:
-            tokens = tokens[None, :]
-            tokens_masked = tokens_masked[None, :]
-        out = tokens.clone().detach()
-        mask = kwargs.pop("mask", None)
-        if mask is None:
-            mask = torch.full_like(out[..., 0], True, dtype=torch.bool, device=out.device)
-        filter_key_ids = filter_key_ids or dict()
-        unmask_mask = out == self.mask_token_id
-        unmask_ids = torch.where(torch.any(unmask_mask, dim=2))[1]
-        for idx in unmask_ids.tolist():
-            type_mask = unmask_mask[:, idx][0]
-            logits_keys = torch.where(type_mask)[0].tolist()
-            outputs = self(out[:, :idx + 1], seq_masked=tokens_masked[:, :idx + 1], mask=mask[:, :idx + 1], return_embeddings=True,
-                           return_caches=True, caches=caches, **kwargs)
-            caches = outputs.caches
-            logits = self.model.lm_head(outputs.hidden_state[:, idx - 1], keys=logits_keys)
-            out[:, idx, type_mask] = _sample_fields(logits, (self.pad_token_id, self.mask_token_id), filter_key_ids, filter_logits_fn,
-                                                    filter_kwargs, temperature)
-        if num_dims == 2:
-            out = out.squeeze(0)
-        if was_training:
-            self.model.train(was_training)
-        if return_caches:
-            return out, caches
-        return out
+        """Reference signature and cache contract (wrappers.py:324-407).  A whole window with top-k / greedy sampling and no incoming
+        caches runs in decode.render_decoder's device-resident loop (any batch size: one persistent kernel per note for the
+        stack, one for heads + sampling); anything else takes decode's general cached stepper."""
+        from ... import decode
+        return decode.unmask_mixlm(self, tokens, tokens_masked, temperature, filter_logits_fn, filter_kwargs, filter_key_ids, caches,
+                                   return_caches, **kwargs)
 
     def forward(self, seq: Tensor, labels: Optional[Tensor] = None, **kwargs):
         seq = seq[:, :-1]

@@ -134,3 +134,23 @@ def test_persistent_decode_stack_matches_operator_path(monkeypatch, B, T):
     same = (outs["fused"][:, 1:, fields] == outs["legacy"][:, 1:, fields])[valid]
     assert float(same.float().mean()) > 0.97, float(same.float().mean())
     assert int((outs["fused"] == 1).sum()) == int((tokens[:, 0] == 1).sum())        # every MASK after note 0 was filled
+
+
+def test_unmask_tokens_adapter_runs_the_batched_renderer(setup):
+    """`ScorePerformerMixedLMWrapper.unmask_tokens` with the reference's argument list, a batch of 3 and greedy top-k: the request is
+    expressible in the device-resident loop, so the adapter must return exactly what render_batch returns; with a filter the
+    loop does not know (top_p) it falls back to the general stepper and still fills every MASK."""
+    g, model, batch = setup
+    from scoreperformer_b200.decode import render_batch
+    from scoreperformer_b200.modules.sampling import top_k, top_p
+    b, enc = _encoders(model, batch)
+    tokens_in = torch.from_numpy(g["tokens_in"]).cuda()
+    rep = lambda t: t.repeat(3, *([1] * (t.dim() - 1)))
+    got = model.perf_decoder.unmask_tokens(rep(tokens_in), rep(b["masked_perf"]), filter_logits_fn=top_k, filter_kwargs={"k": 1},
+                                           disable_tqdm=True, context=rep(enc.score_embeddings), style_embeddings=rep(enc.perf_embeddings))
+    want = render_batch(model, rep(tokens_in), rep(b["masked_perf"]), rep(enc.score_embeddings), rep(enc.perf_embeddings))
+    assert torch.equal(got, want)
+    torch.manual_seed(3)
+    got_p = model.perf_decoder.unmask_tokens(tokens_in[:, :9], b["masked_perf"][:, :9], filter_logits_fn=top_p, filter_kwargs={"thres": 0.5},
+                                             disable_tqdm=True, context=enc.score_embeddings[:, :9], style_embeddings=enc.perf_embeddings[:, :9])
+    assert int((got_p == 1).sum()) == int((tokens_in[:, 0] == 1).sum()) and got_p.shape == tokens_in[:, :9].shape
