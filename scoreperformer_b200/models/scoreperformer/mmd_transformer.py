@@ -160,6 +160,8 @@ class MMDTupleTransformer(TupleTransformer):
         # When False the segment tables are sized T + 4 (static, no host sync); when True one `.max()` sync per forward
         # trims `latents` to the reference's exact [B, max_id + 1, z] shape.
         self.exact_latent_shapes = True
+        self.slot_capacity = None          # rows of every segment table in sync-free mode (None: T + 4)
+        self.segment_overflow = None       # device counter of note-tuples whose segment id did not fit (sync-free mode)
 
     @staticmethod
     def _get_segments(aggregate_mode: str, bars=None, beats=None, onsets=None):
@@ -204,7 +206,17 @@ class MMDTupleTransformer(TupleTransformer):
             maxima = torch.stack([s.max() if s is not None else s_zero(hidden) for s in segs]).tolist()   # one host sync
             slots = [2 if s is None else int(m) + 1 for s, m in zip(segs, maxima)]
         else:
-            slots = [2 if s is None else t + 4 for s in segs]
+            # sync-free mode (CUDA-graph capture): every segment table has `slot_capacity` rows (default T + 4).  Ids count musical
+            # time, not notes, so a very sparse window can exceed that; the pooling kernel skips such ids.  They are counted here on
+            # the device (`segment_overflow`, read it with TrainStep.segment_overflow_count() or int(...)) so that a run can
+            # notice and raise `slot_capacity` (or fall back to exact shapes) instead of diverging silently.
+            cap = self.slot_capacity if self.slot_capacity is not None else t + 4
+            slots = [2 if s is None else cap for s in segs]
+            over = [((s >= cap) & mask).sum() for s in segs if s is not None]
+            if over:
+                if self.segment_overflow is None or self.segment_overflow.device != hidden.device:
+                    self.segment_overflow = torch.zeros((), dtype=torch.int64, device=hidden.device)
+                self.segment_overflow += torch.stack(over).sum()
         wb = []
         for m in self.aggregate_mode:
             wb += [self.vae_head[m].linear.weight, self.vae_head[m].linear.bias]

@@ -198,6 +198,14 @@ class TrainStep:
         self.static_batch = self.static_loss = self.static_losses = self._static_metrics = None
         torch.cuda.synchronize()
 
+    def segment_overflow_count(self) -> int:
+        """Note-tuples (accumulated over all steps so far) whose bar / beat / onset id exceeded the static segment tables of the
+        sync-free mode -- they were left out of their level's pooling.  Non-zero means: raise
+        `model.perf_encoder.slot_capacity` (and re-capture) or train with use_graph=False.  Reading it synchronises."""
+        enc = getattr(self.model, "perf_encoder", None)
+        c = getattr(enc, "segment_overflow", None)
+        return 0 if c is None else int(c)
+
     def mark_weights_changed(self) -> None:
         """Call after writing parameters from outside the step (load_state_dict, manual edits): rebuilds the bf16 shadow."""
         self._shadow_stale = True

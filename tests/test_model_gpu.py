@@ -176,3 +176,24 @@ def test_train_step_nccl_world2():
            "--master-port", "29517", os.path.join(root, "tests", "ddp_nccl_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0 and res.stdout.count("DDP-NCCL-OK") == 2, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_static_segment_tables_report_overflow():
+    """in sync-free mode ids beyond the static table are skipped by the pooling kernel -- that must be visible.  A batch
+    whose beat ids run past T + 4 raises the device counter; the default synthetic batch does not."""
+    from scoreperformer_b200.train_step import TrainStep
+    m = parity.build_model(dropout=False, device="cuda").train()
+    ts = TrainStep(m, lr=0.0, use_graph=False)
+    m.perf_encoder.exact_latent_shapes = False
+    batch = {k: v.cuda() for k, v in parity.make_batch(2, 48, seed=2).items()}
+    ts.step(batch)
+    assert ts.segment_overflow_count() == 0
+    sparse = dict(batch)
+    sparse["beats"] = batch["beats"] * 3                 # fewer than one note per beat: ids run ahead of the note count
+    ts.step(sparse)
+    want = int(((sparse["beats"] >= 48 + 4) & batch["perf_mask"]).sum())
+    assert want > 0 and ts.segment_overflow_count() == want
+    m.perf_encoder.slot_capacity = int(sparse["beats"].max()) + 1
+    m.perf_encoder.segment_overflow.zero_()
+    ts.step(sparse)
+    assert ts.segment_overflow_count() == 0
