@@ -410,14 +410,15 @@ def main():
             a[1] += s_.elapsed_time(e_)
         top_shape, (top_n, top_ms, top_fl) = max(by_shape.items(), key=lambda kv: kv[1][1])
         achieved = top_fl / (top_ms / top_n / 1e3) / 1e12
+        # DRAM bytes of the dominant launch shape from the committed `ncu --set full` capture (profiles/r02_gemm_traffic.json); null
+        # if the dominant shape of this run is not the captured one
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")     # DRAM bytes of this launch shape, ncu --set full capture
-        if not os.path.exists(tpath):
-            tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-        if os.path.exists(tpath) and top_shape == (B * T, 2048, 256):
+        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+        if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            if tuple(tj.get("shape_MNK", ())) == tuple(top_shape):
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roofline = {"bound": "tensor",
                     "kernel": f"gemm_bf16_kernel (tcgen05/TMEM/TMA), dominant launch M,N,K={top_shape} x{top_n} per step",
                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],

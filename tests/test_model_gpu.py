@@ -189,7 +189,7 @@ def test_static_segment_tables_report_overflow():
     ts.step(batch)
     assert ts.segment_overflow_count() == 0
     sparse = dict(batch)
-    sparse["beats"] = batch["beats"] * 3                 # fewer than one note per beat: ids run ahead of the note count
+    sparse["beats"] = batch["beats"] * 8                 # far fewer than one note per beat: ids run ahead of the note count
     ts.step(sparse)
     want = int(((sparse["beats"] >= 48 + 4) & batch["perf_mask"]).sum())
     assert want > 0 and ts.segment_overflow_count() == want
