@@ -111,6 +111,16 @@ int spb_ffn_fwd(const void* xn, int ld_xn, const void* w1, const float* b1, cons
                 int ld_out, void* u_save, void* h_save, int n_rows, int dim, int hidden, float dropout_p, uint64_t seed,
                 const uint64_t* rng_offset, spb_stream_t stream);
 
+/* Fused feed-forward sub-layer backward, data path (the autograd of feedforward.py:13-22,35-64): dh = dy W2 stays on chip,
+ * du = GLU'(u) . mask . dh is written once (du may be u itself: in place), dxn = du W1, db1 += column sums of du.  One tcgen05
+ * kernel of CTA pairs.  dy bf16 [n, dim]; w2t bf16 [hidden, dim] = the out-projection weight TRANSPOSED (spb_transpose_bf16);
+ * w1 bf16 [2*hidden, dim]; u bf16 [n, 2*hidden] as saved by spb_ffn_fwd; db1 fp32 [2*hidden] or NULL; dxn bf16 [n, ld_dxn].
+ * The weight gradients (du^T xn, dy^T h) remain spb_gemm_bf16 calls.  Dropout arguments as given to spb_ffn_fwd. */
+int spb_ffn_bwd(const void* dy, int ld_dy, const void* w2t, const void* w1, const void* u, void* du, float* db1, void* dxn, int ld_dxn,
+                int n_rows, int dim, int hidden, float dropout_p, uint64_t seed, const uint64_t* rng_offset, spb_stream_t stream);
+/* dst[c, r] = src[r, c], bf16, src [rows, cols] contiguous. */
+int spb_transpose_bf16(const void* src, void* dst, int rows, int cols, spb_stream_t stream);
+
 /* Computed per-field tables W_f = index rows {discrete ids} + MLP(token_values) (modules/transformer/embeddings.py:124-143,199-211),
  * all fields in one launch.  ptrs is a HOST array of device pointers, 7 per field for the forward (index_weight [V,128], token_values
  * [V], discrete mask [V] fp32 0/1, W0 [128], b0 [128], W1 [128,128], b1 [128]) and 12 per field for the backward (+ the five gradient

@@ -447,13 +447,23 @@ class TransformerStackFn(torch.autograd.Function):
             p_w1, p_b1, p_w2 = params[base + PARAMS_PER_ATTN + 2:base + PARAMS_PER_ATTN + 5]
             with side(g16, rec_f["h"]):
                 grads[base + PARAMS_PER_ATTN + 4] = wgrad(p_w2, g16, rec_f["h"])
-            dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
             db1, d_b1 = take(p_b1)
-            du = K.glu_bwd(dh, rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
+            if K.ffn_bwd_fused_ok(D, spec.ff_inner):
+                # one kernel: dh = dy W2 (on chip) -> GLU' . mask -> du (written over u) -> dxn = du W1, db1 += colsum(du)
+                if rec_f["u"] is None:
+                    raise RuntimeError("TransformerStackFn: second backward through the same graph (the saved pre-activations were "
+                                       "overwritten in place by the first)")
+                dxn, du = K.ffn_bwd(g16, K.transpose_bf16(rec_f["w2_16"]), rec_f["w1_16"], rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
+                rec_f["u"] = None
+            else:
+                dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)
+                du = K.glu_bwd(dh, rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
+                dxn = None
             grads[base + PARAMS_PER_ATTN + 3] = None if d_b1 else db1
             with side(du, rec_f["xn"]):
                 grads[base + PARAMS_PER_ATTN + 2] = wgrad(p_w1, du, rec_f["xn"])
-            dxn = K.gemm(du, rec_f["w1_16"], trans_b=True, out_dtype=BF16)
+            if dxn is None:
+                dxn = K.gemm(du, rec_f["w1_16"], trans_b=True, out_dtype=BF16)
             g, g16 = norm_bwd(2 * l + 1, dxn, rec_f, g)
             # ---- attention backward:  x_out = x + mask * Wo attn(Wqkv LN(x))
             p_q, p_k, p_v, p_o, p_ls = params[base + 2:base + 7]

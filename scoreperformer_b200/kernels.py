@@ -257,8 +257,43 @@ def ffn_fwd(xn: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, resid: Optional[Tens
     return out, u, h
 
 
+def transpose_bf16(w: Tensor) -> Tensor:
+    """w^T as a contiguous bf16 matrix (the out-projection weight in the layout spb_ffn_bwd streams)."""
+    _require_cuda(w)
+    assert w.dtype == BF16 and w.is_contiguous() and w.dim() == 2
+    out = torch.empty((w.shape[1], w.shape[0]), dtype=BF16, device=w.device)
+    _call("spb_transpose_bf16", _p(w), _p(out), w.shape[0], w.shape[1], _stream())
+    _count()
+    return out
+
+
+def ffn_bwd(dy: Tensor, w2t: Tensor, w1: Tensor, u: Tensor, db1: Optional[Tensor], dropout_p: float, seed: int,
+            in_place: bool = True):
+    """Fused feed-forward backward, data path (one tcgen05 kernel): dy bf16 [n, 256], w2t bf16 [1024, 256] (W2 transposed),
+    w1 bf16 [2048, 256], u bf16 [n, 2048] as saved by ffn_fwd.  Returns (dxn bf16 [n, 256], du bf16 [n, 2048]); with `in_place`
+    du overwrites u.  db1 fp32 [2048] is accumulated into."""
+    _require_cuda(dy, w2t, w1, u)
+    n, dim = dy.shape
+    hidden = w2t.shape[0]
+    assert dy.dtype == BF16 and dy.stride(1) == 1 and u.dtype == BF16 and u.is_contiguous() and u.shape == (n, 2 * hidden)
+    assert w1.dtype == BF16 and w2t.dtype == BF16 and w1.is_contiguous() and w2t.is_contiguous()
+    assert w1.shape == (2 * hidden, dim) and w2t.shape == (hidden, dim)
+    if db1 is not None:
+        assert db1.dtype == F32 and db1.is_contiguous() and db1.numel() == 2 * hidden
+    du = u if in_place else torch.empty_like(u)
+    dxn = torch.empty((n, dim), dtype=BF16, device=dy.device)
+    _call("spb_ffn_bwd", _p(dy), dy.stride(0), _p(w2t), _p(w1), _p(u), _p(du), _p(db1), _p(dxn), dxn.stride(0), n, dim, hidden,
+          float(dropout_p), seed, _p(RNG_OFFSET), _stream())
+    _count()
+    return dxn, du
+
+
 def ffn_fused_ok(dim: int, hidden: int) -> bool:
     return dim == 256 and hidden == 1024 and _os.environ.get("SPB_FFN", "fused") == "fused"
+
+
+def ffn_bwd_fused_ok(dim: int, hidden: int) -> bool:
+    return dim == 256 and hidden == 1024 and _os.environ.get("SPB_FFN_BWD", "fused") == "fused"
 
 
 def glu_bwd(dh: Tensor, u: Tensor, dbias: Optional[Tensor], dropout_p: float, seed: int) -> Tensor:

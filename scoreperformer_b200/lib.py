@@ -15,7 +15,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libspb200.so")
-SOURCES = ["api.cu", "collate.cu", "decode_stack.cu", "gemm.cu", "ffn.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "latents.cu", "heads.cu", "head_ce.cu", "tables.cu", "optim.cu"]
+SOURCES = ["api.cu", "collate.cu", "decode_stack.cu", "gemm.cu", "ffn.cu", "ffn_bwd.cu", "rowops.cu", "embed_scatter.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "latents.cu", "heads.cu", "head_ce.cu", "tables.cu", "optim.cu"]
 
 _P, _I, _F, _L, _U64 = c_void_p, c_int, c_float, c_int64, c_uint64
 _U32 = ctypes.c_uint32
@@ -32,6 +32,8 @@ SIGNATURES = {
     "spb_decode_stack_step": [_P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P],
     "spb_unpack_batch": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _U32, _U32, _I, c_longlong, _I, _P],
     "spb_ffn_fwd": [_P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _F, _U64, _P, _P],
+    "spb_ffn_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _U64, _P, _P],
+    "spb_transpose_bf16": [_P, _P, _I, _I, _P],
     "spb_glu_bwd": [_P, _P, _P, _P, _I, _I, _F, _U64, _P, _P],
     "spb_table_build_fwd": [_P, _I, _P, _P, _P],
     "spb_table_build_bwd": [_P, _I, _P, _P, _P],

@@ -225,6 +225,41 @@ def test_ffn_fused_forward(k, n):
     assert rel_err(outd, resid + hd.float() @ w2.float().t()) < 1e-2
 
 
+@pytest.mark.parametrize("n", [256, 333, 4099, 32768])
+@pytest.mark.parametrize("p_drop", [0.0, 0.25])
+def test_ffn_fused_backward(k, n, p_drop):
+    """spb_ffn_bwd (one tcgen05 kernel: dh on chip, du in place, dxn, bias gradient) against autograd of the fp32 statement of
+    feedforward.py:13-22,56-64 with the kernel's own dropout mask, and against the unfused chain (gemm -> glu_bwd -> gemm)."""
+    torch.manual_seed(13)
+    D, H = 256, 1024
+    dy = randn(n, D, dtype=BF16)
+    u = randn(n, 2 * H, dtype=BF16)
+    w1, w2 = randn(2 * H, D, dtype=BF16, scale=D ** -0.5), randn(D, H, dtype=BF16, scale=H ** -0.5)
+    w2t = k.transpose_bf16(w2)
+    assert torch.equal(w2t, w2.t().contiguous())
+    keep = (k.glu_fwd(u, p_drop, 77) != 0) | (u[:, :H].float() * F.silu(u[:, H:].float()) == 0)     # the mask function of the forward
+    ur = u.float().requires_grad_(True)
+    a, g = ur.chunk(2, dim=-1)
+    hr = a * F.silu(g) * keep / (1 - p_drop)
+    hr.backward(dy.float() @ w2.float())
+    du_ref = ur.grad
+    db, db2 = torch.zeros(2 * H, device="cuda"), torch.zeros(2 * H, device="cuda")
+    dxn, du = k.ffn_bwd(dy, w2t, w1, u, db, p_drop, 77, in_place=False)
+    assert rel_err(du, du_ref) < 1e-2
+    assert rel_err(dxn, du_ref @ w1.float()) < 1e-2
+    assert rel_err(db, du_ref.sum(dim=0)) < 1e-2
+    # the chain it replaces: same mask, same numbers up to the bf16 rounding of dh the fused kernel does not do
+    dh = k.gemm(dy, w2, trans_b=True, out_dtype=BF16)
+    du2 = k.glu_bwd(dh, u, db2, p_drop, 77)
+    assert torch.equal(du == 0, du2 == 0) and rel_err(du, du2) < 1e-2
+    assert rel_err(dxn, k.gemm(du2, w1, trans_b=True, out_dtype=BF16)) < 1e-2 and rel_err(db, db2) < 1e-2
+    # in place: du over u, bias gradient accumulated on top of what is there
+    u2 = u.clone()
+    dxn3, du3 = k.ffn_bwd(dy, w2t, w1, u2, db, p_drop, 77)
+    assert du3.data_ptr() == u2.data_ptr() and torch.equal(du3, du) and torch.equal(dxn3, dxn)
+    assert rel_err(db, 2 * db2) < 1e-2
+
+
 # ------------------------------------------------------------------ tuple embedding
 @pytest.mark.parametrize("F_", [12, 10])
 def test_embed_ln(k, F_):
