@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel launch table of one step")
+    ap.add_argument("--timeline", default=None,
+                    help="warm up, then record the kernels of 3 steps with torch.profiler (CUPTI) into this CSV "
+                         "(name, stream, start_us, dur_us) and exit -- a diagnostic, never a bench value")
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (use with ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -316,6 +319,22 @@ def main():
         ts.step(dev_batch)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        return
+
+    if args.timeline:
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                ts.step(dev_batch)
+            torch.cuda.synchronize()
+        with open(args.timeline, "w") as f:
+            f.write("name,stream,start_us,dur_us\n")
+            for ev in prof.events():
+                if ev.device_type == torch.autograd.DeviceType.CUDA:
+                    name = ev.name.replace(",", ";")[:100]
+                    f.write(f"{name},{getattr(ev, 'device_index', 0)}:{getattr(ev, 'stream', getattr(ev, 'device_resource_id', 0))},"
+                            f"{ev.time_range.start:.3f},{ev.time_range.end - ev.time_range.start:.3f}\n")
         return
 
     sampler = ClockSampler(local_rank)

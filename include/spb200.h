@@ -118,8 +118,9 @@ int spb_ffn_fwd(const void* xn, int ld_xn, const void* w1, const float* b1, cons
  * The weight gradients (du^T xn, dy^T h) remain spb_gemm_bf16 calls.  Dropout arguments as given to spb_ffn_fwd. */
 int spb_ffn_bwd(const void* dy, int ld_dy, const void* w2t, const void* w1, const void* u, void* du, float* db1, void* dxn, int ld_dxn,
                 int n_rows, int dim, int hidden, float dropout_p, uint64_t seed, const uint64_t* rng_offset, spb_stream_t stream);
-/* dst[c, r] = src[r, c], bf16, src [rows, cols] contiguous. */
-int spb_transpose_bf16(const void* src, void* dst, int rows, int cols, spb_stream_t stream);
+/* dst[z][c, r] = srcs[z][r, c] for n_mats (<= 16) contiguous bf16 matrices [rows, cols]; srcs is a HOST array of device pointers,
+ * dst one buffer [n_mats, cols, rows] (all out-projection weights of a stack in one launch). */
+int spb_transpose_bf16(const void* const* srcs, int n_mats, void* dst, int rows, int cols, spb_stream_t stream);
 
 /* Computed per-field tables W_f = index rows {discrete ids} + MLP(token_values) (modules/transformer/embeddings.py:124-143,199-211),
  * all fields in one launch.  ptrs is a HOST array of device pointers, 7 per field for the forward (index_weight [V,128], token_values

@@ -372,10 +372,16 @@ ffn_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
-// dst[c, r] = src[r, c] for a bf16 matrix (the once-per-step W2 -> W2T of the kernel above)
+// dst_z[c, r] = src_z[r, c] for up to 16 bf16 matrices of one shape (the once-per-step W2 -> W2T of the kernel above, all layers
+// of a stack in one launch); dst_z = dst + z * rows * cols
+struct TransposeBatch {
+    const __nv_bfloat16* src[16];
+};
 __global__ void __launch_bounds__(256)
-transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
+transpose_bf16_kernel(TransposeBatch b, __nv_bfloat16* __restrict__ dst_all, int rows, int cols) {
     __shared__ __nv_bfloat16 tile[64][66];
+    const __nv_bfloat16* __restrict__ src = b.src[blockIdx.z];
+    __nv_bfloat16* __restrict__ dst = dst_all + (size_t)blockIdx.z * rows * cols;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int r = i >> 6, c = i & 63;
@@ -390,11 +396,13 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __re
 
 }  // namespace
 
-extern "C" int spb_transpose_bf16(const void* src, void* dst, int rows, int cols, cudaStream_t stream) {
-    if (rows <= 0 || cols <= 0) return SPB_OK;
-    SPB_CHECK_ARG(src && dst, "spb_transpose_bf16: null pointer");
-    dim3 grid(ceil_div(cols, 64), ceil_div(rows, 64));
-    transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), rows, cols);
+extern "C" int spb_transpose_bf16(const void* const* srcs, int n_mats, void* dst, int rows, int cols, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0 || n_mats <= 0) return SPB_OK;
+    SPB_CHECK_ARG(srcs && dst && n_mats <= 16, "spb_transpose_bf16: 1..16 matrices per call (got %d)", n_mats);
+    TransposeBatch b;
+    for (int i = 0; i < 16; ++i) b.src[i] = reinterpret_cast<const __nv_bfloat16*>(srcs[i < n_mats ? i : 0]);
+    dim3 grid(ceil_div(cols, 64), ceil_div(rows, 64), n_mats);
+    transpose_bf16_kernel<<<grid, 256, 0, stream>>>(b, reinterpret_cast<__nv_bfloat16*>(dst), rows, cols);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

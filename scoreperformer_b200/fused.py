@@ -430,16 +430,20 @@ class TransformerStackFn(torch.autograd.Function):
             grads[j], grads[j + 1] = (None if d1 else dw), (None if d2 else db)
             return res if want16 else (res, None)
 
-        # weight-gradient GEMMs feed nothing downstream in this backward: they run on a side stream of their own (one per calling
-        # stream) and fill the gaps of the activation-gradient chain; joined before the gradients are handed to autograd
+        # weight-gradient GEMMs feed nothing downstream in this backward, so they CAN run on a side stream of their own (one per
+        # calling stream), joined before the gradients are handed to autograd.  Off by default since round 2: every large kernel
+        # of the chain is persistent and owns all SMs, so the branch only delays the chain (measured 10.54 vs 10.16 ms per C2 step)
         wb = None
-        if g_out.is_cuda and os.environ.get("SPB_WGRAD_BRANCH", "1") == "1":
+        if g_out.is_cuda and os.environ.get("SPB_WGRAD_BRANCH", "0") == "1":
             for i in range(3):                                     # small fixed pool, created on the first (eager) call
                 SideBranch(g_out.device, slot=("wgrad", i))
             wb = SideBranch(g_out.device, slot=("wgrad", (torch.cuda.current_stream().cuda_stream >> 6) % 3))
         side = (lambda *ts: wb.run(*ts)) if wb is not None else (lambda *ts: contextlib.nullcontext())
 
         g, g16 = norm_bwd(2 * spec.depth, K.cast_bf16(g_out.contiguous().view(N, D)), ctx.final, None)
+        w2t_all = None
+        if K.ffn_bwd_fused_ok(D, spec.ff_inner):       # out-projection weights of every layer, transposed in one launch
+            w2t_all = K.transpose_bf16([ctx.layers[l][1]["w2_16"] for l in range(spec.depth)])
         for l in reversed(range(spec.depth)):
             base = l * (PARAMS_PER_ATTN + PARAMS_PER_FF)
             rec_a, rec_f = ctx.layers[l]
@@ -453,7 +457,7 @@ class TransformerStackFn(torch.autograd.Function):
                 if rec_f["u"] is None:
                     raise RuntimeError("TransformerStackFn: second backward through the same graph (the saved pre-activations were "
                                        "overwritten in place by the first)")
-                dxn, du = K.ffn_bwd(g16, K.transpose_bf16(rec_f["w2_16"]), rec_f["w1_16"], rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
+                dxn, du = K.ffn_bwd(g16, w2t_all[l], rec_f["w1_16"], rec_f["u"], db1, p_ff, ctx.seeds[2 * l + 1])
                 rec_f["u"] = None
             else:
                 dh = K.gemm(g16, rec_f["w2_16"], trans_b=True, out_dtype=BF16)

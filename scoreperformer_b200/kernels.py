@@ -257,14 +257,20 @@ def ffn_fwd(xn: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, resid: Optional[Tens
     return out, u, h
 
 
-def transpose_bf16(w: Tensor) -> Tensor:
-    """w^T as a contiguous bf16 matrix (the out-projection weight in the layout spb_ffn_bwd streams)."""
-    _require_cuda(w)
-    assert w.dtype == BF16 and w.is_contiguous() and w.dim() == 2
-    out = torch.empty((w.shape[1], w.shape[0]), dtype=BF16, device=w.device)
-    _call("spb_transpose_bf16", _p(w), _p(out), w.shape[0], w.shape[1], _stream())
-    _count()
-    return out
+def transpose_bf16(ws) -> Tensor:
+    """w^T as a contiguous bf16 matrix -- or, for a list of up to 16 same-shaped matrices, [len, cols, rows] in one launch
+    (the out-projection weights of a stack in the layout spb_ffn_bwd streams)."""
+    single = isinstance(ws, Tensor)
+    mats = [ws] if single else list(ws)
+    _require_cuda(*mats)
+    rows, cols = mats[0].shape
+    assert all(w.dtype == BF16 and w.is_contiguous() and w.shape == (rows, cols) for w in mats)
+    out = torch.empty((len(mats), cols, rows), dtype=BF16, device=mats[0].device)
+    for i in range(0, len(mats), 16):
+        part = mats[i:i + 16]
+        _call("spb_transpose_bf16", _ptr_array(part), len(part), _p(out[i]), rows, cols, _stream())
+        _count()
+    return out[0] if single else out
 
 
 def ffn_bwd(dy: Tensor, w2t: Tensor, w1: Tensor, u: Tensor, db1: Optional[Tensor], dropout_p: float, seed: int,
