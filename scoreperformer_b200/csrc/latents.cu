@@ -207,67 +207,85 @@ seg_latent_bwd_kernel(float* __restrict__ dlat, const float* __restrict__ dlat_d
 }
 
 // d_hidden[b,t,:] += mask * dpooled[b, seg, :256] ; d_style[b,t,:w_style] += dpooled[b, seg, 256:256+w_style]
-// (style inputs were stored already masked, and their own mask is applied again when they were produced)
-__global__ void seg_scatter_grad_kernel(const float* __restrict__ dpooled, const int64_t* __restrict__ segments,
-                                        const uint8_t* __restrict__ mask, float* __restrict__ d_hidden, float* __restrict__ d_style,
-                                        int ld_style, int B, int T, int S, int d_hidden_dim, int d_total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * T * d_total) return;
-    const int c = (int)(i % d_total);
-    const int64_t tok = i / d_total;
-    const int b = (int)(tok / T);
-    long long id = segments != nullptr ? segments[tok] : (mask[tok] ? 1 : 0);
-    if (id < 0 || id >= S) return;
-    const float g = dpooled[((size_t)b * S + id) * MAX_D + c];
-    if (c < d_hidden_dim) {
-        if (mask[tok]) d_hidden[tok * d_hidden_dim + c] += g;
-    } else {
-        d_style[tok * ld_style + (c - d_hidden_dim)] += g;
+// (style inputs were stored already masked, and their own mask is applied again when they were produced).
+// One warp per note-tuple, 16-byte read-modify-writes (d_hidden_dim, w_style and ld_style are multiples of 4): the kernel is a
+// stream over d_hidden, nothing else.
+__global__ void __launch_bounds__(256)
+seg_scatter_grad_kernel(const float* __restrict__ dpooled, const int64_t* __restrict__ segments, const uint8_t* __restrict__ mask,
+                        float* __restrict__ d_hidden, float* __restrict__ d_style, int ld_style, int B, int T, int S, int d_hidden_dim,
+                        int d_total) {
+    const int lane = threadIdx.x & 31;
+    const int n_tok = B * T;
+    const int q_hidden = d_hidden_dim >> 2, q_total = d_total >> 2;
+    for (int tok = blockIdx.x * 8 + (threadIdx.x >> 5); tok < n_tok; tok += gridDim.x * 8) {
+        const bool live = mask[tok] != 0;
+        const long long id = segments != nullptr ? segments[tok] : (live ? 1 : 0);
+        if (id < 0 || id >= S) continue;
+        const float4* src = reinterpret_cast<const float4*>(dpooled + ((size_t)(tok / T) * S + id) * MAX_D);
+        float4* dh = reinterpret_cast<float4*>(d_hidden + (size_t)tok * d_hidden_dim);
+        float4* ds = reinterpret_cast<float4*>(d_style + (size_t)tok * ld_style);
+        for (int c = lane; c < q_total; c += 32) {
+            float4* dst = c < q_hidden ? (live ? dh + c : nullptr) : ds + (c - q_hidden);
+            if (dst == nullptr) continue;
+            const float4 g = __ldg(src + c);
+            float4 v = *dst;
+            v.x += g.x; v.y += g.y; v.z += g.z; v.w += g.w;
+            *dst = v;
+        }
     }
 }
 
-// C[m, n] += A[K, m]^T B[K, n] in fp32 (tiny m*n, long K): blocks split K, 256 threads tile the outputs.
+// C[m, n] += A[K, m]^T B[K, n] in fp32 (tiny m <= MR, n <= 512, long K): blocks split K; thread t owns columns t and t + 256 for
+// ALL rows, so a k step costs two conflict-free B loads and MR / 4 broadcast float4 loads of A for 2 * MR FMAs.
+template <int MR>
 __global__ void __launch_bounds__(256)
 small_gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb, float* __restrict__ C, int ldc, int K,
                      int m, int n, int k_per_block) {
-    extern __shared__ float sm[];
-    float* sA = sm;                       // [KT][m]
-    float* sB = sm + 32 * m;              // [KT][n]
+    extern __shared__ __align__(16) float sm[];
+    float* sA = sm;                       // [32][MR], rows >= m zero
+    float* sB = sm + 32 * MR;             // [32][512]
     const int k0 = blockIdx.x * k_per_block, k1 = min(K, k0 + k_per_block);
-    const int outs = m * n;
-    constexpr int MAXO = 40;              // outputs per thread (m*n <= 10240)
-    float acc[MAXO];
+    const int c0 = threadIdx.x, c1 = threadIdx.x + 256;
+    float acc0[MR], acc1[MR];
 #pragma unroll
-    for (int i = 0; i < MAXO; ++i) acc[i] = 0.f;
+    for (int r = 0; r < MR; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
     for (int kk = k0; kk < k1; kk += 32) {
         const int kt = min(32, k1 - kk);
         __syncthreads();
         // A = dlatents: rows of empty / padded segments are exactly zero (most rows in the sync-free [B, T+4] layout), and a
         // chunk of 32 all-zero rows contributes nothing
         int live = 0;
-        for (int i = threadIdx.x; i < kt * m; i += 256) {
-            const float a = A[(size_t)(kk + i / m) * lda + i % m];
+        for (int i = threadIdx.x; i < 32 * MR; i += 256) {
+            const int k = i / MR, r = i % MR;
+            const float a = (k < kt && r < m) ? A[(size_t)(kk + k) * lda + r] : 0.f;
             sA[i] = a;
             live |= (a != 0.f);
         }
         if (!__syncthreads_or(live)) continue;
-        for (int i = threadIdx.x; i < kt * n; i += 256) sB[i] = Bm[(size_t)(kk + i / n) * ldb + i % n];
+        for (int k = 0; k < kt; ++k) {
+            sB[k * 512 + c0] = c0 < n ? Bm[(size_t)(kk + k) * ldb + c0] : 0.f;
+            sB[k * 512 + c1] = c1 < n ? Bm[(size_t)(kk + k) * ldb + c1] : 0.f;
+        }
         __syncthreads();
+        for (int k = 0; k < kt; ++k) {
+            const float b0 = sB[k * 512 + c0], b1 = sB[k * 512 + c1];
+            const float4* a4 = reinterpret_cast<const float4*>(sA + k * MR);
 #pragma unroll
-        for (int i = 0; i < MAXO; ++i) {
-            const int o = threadIdx.x + i * 256;
-            if (o < outs) {
-                const int r = o / n, c = o % n;
-                float s = 0.f;
-                for (int k = 0; k < kt; ++k) s += sA[k * m + r] * sB[k * n + c];
-                acc[i] += s;
+            for (int r = 0; r < MR; r += 4) {
+                const float4 a = a4[r >> 2];
+                acc0[r] = fmaf(a.x, b0, acc0[r]);         acc1[r] = fmaf(a.x, b1, acc1[r]);
+                acc0[r + 1] = fmaf(a.y, b0, acc0[r + 1]); acc1[r + 1] = fmaf(a.y, b1, acc1[r + 1]);
+                acc0[r + 2] = fmaf(a.z, b0, acc0[r + 2]); acc1[r + 2] = fmaf(a.z, b1, acc1[r + 2]);
+                acc0[r + 3] = fmaf(a.w, b0, acc0[r + 3]); acc1[r + 3] = fmaf(a.w, b1, acc1[r + 3]);
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < MAXO; ++i) {
-        const int o = threadIdx.x + i * 256;
-        if (o < outs && acc[i] != 0.f) atomicAdd(C + (size_t)(o / n) * ldc + o % n, acc[i]);
+    for (int r = 0; r < MR; ++r) {
+        if (r < m) {
+            if (c0 < n && acc0[r] != 0.f) atomicAdd(C + (size_t)r * ldc + c0, acc0[r]);
+            if (c1 < n && acc1[r] != 0.f) atomicAdd(C + (size_t)r * ldc + c1, acc1[r]);
+        }
     }
 }
 
@@ -413,13 +431,27 @@ extern "C" int spb_latent_level_bwd(float* d_style, int ld_style, int col0, cons
     const int K = B * S;
     int k_per_block = ceil_div(K, 2 * spb_num_sms());
     if (k_per_block < 32) k_per_block = 32;
-    const size_t smem = (size_t)32 * (z + d_total) * sizeof(float);
-    small_gemm_tn_kernel<<<ceil_div(K, k_per_block), 256, smem, stream>>>(dlat, z, pooled, MAX_D, dW, d_total, K, z, d_total, k_per_block);
+#define SMALL_GEMM_CASE(MR)                                                                                                          \
+    {                                                                                                                                \
+        constexpr int smem = 32 * (MR + 512) * (int)sizeof(float);                                                                   \
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(small_gemm_tn_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
+        small_gemm_tn_kernel<MR><<<ceil_div(K, k_per_block), 256, smem, stream>>>(dlat, z, pooled, MAX_D, dW, d_total, K, z, d_total, \
+                                                                                  k_per_block);                                      \
+    }
+    if (z <= 4) SMALL_GEMM_CASE(4)
+    else if (z <= 8) SMALL_GEMM_CASE(8)
+    else SMALL_GEMM_CASE(32)
+#undef SMALL_GEMM_CASE
     SPB_CHECK_LAUNCH();
     colsum_kernel<<<ceil_div(K, k_per_block), 64, 0, stream>>>(dlat, z, dbias, K, z, k_per_block);
     SPB_CHECK_LAUNCH();
-    const int64_t n2 = (int64_t)B * T * d_total;
-    seg_scatter_grad_kernel<<<ceil_div(n2, 256), 256, 0, stream>>>(dpooled, segments, mask, d_hidden, d_style, ld_style, B, T, S, d_hidden_dim, d_total);
+    SPB_CHECK_ARG(d_hidden_dim % 4 == 0 && w_style % 4 == 0 && ld_style % 4 == 0 && (reinterpret_cast<uintptr_t>(d_style) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(d_hidden) & 15) == 0,
+                  "spb_latent_level_bwd: widths must be multiples of 4 and gradients 16-byte aligned");
+    {
+        const int want = ceil_div(B * T, 8), cap = 8 * spb_num_sms();
+        seg_scatter_grad_kernel<<<want < cap ? want : cap, 256, 0, stream>>>(dpooled, segments, mask, d_hidden, d_style, ld_style, B, T, S, d_hidden_dim, d_total);
+    }
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }
