@@ -166,11 +166,15 @@ class ScorePerformer(_LMMixin, Model):
         self.mmd_rows: Optional[List[Optional[Tensor]]] = None
 
     def forward_encoders(self, perf=None, perf_mask=None, score=None, score_mask=None, bars=None, beats=None, onsets=None,
-                         deadpan_mask=None, compute_loss: bool = True, table_cache: Optional[dict] = None, side_branch=None):
+                         deadpan_mask=None, compute_loss: bool = True, table_cache: Optional[dict] = None, side_branch=None,
+                         after_score=None):
+        """`after_score(score_embeddings)` (optional) is evaluated right behind the score encoder, on its branch: forward() uses it
+        for the decoder's input embedding, which needs the score but not the style embeddings."""
         table_cache = {} if table_cache is None else table_cache
         score_emb = perf_emb = None
         score_enc_out = perf_enc_out = None
         enc_branch = None
+        extra = None
         if self.score_encoder is not None:
             # the two encoders are independent: the score encoder runs as a second branch next to the performance encoder
             both = self.perf_encoder is not None and side_branch is not None and _os.environ.get("SPB_ENC_BRANCH", "1") == "1"
@@ -179,18 +183,24 @@ class ScorePerformer(_LMMixin, Model):
                 with enc_branch.run(score, score_mask):
                     score_enc_out = self.score_encoder(score, mask=score_mask, table_cache=table_cache)
                     score_emb = score_enc_out.hidden_state
+                    if after_score is not None:
+                        extra = after_score(score_emb)
             else:
                 score_enc_out = self.score_encoder(score, mask=score_mask, table_cache=table_cache)
                 score_emb = score_enc_out.hidden_state
+                if after_score is not None:
+                    extra = after_score(score_emb)
         if self.perf_encoder is not None:
             perf_enc_out = self.perf_encoder(perf, mask=perf_mask, bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask,
                                              compute_loss=compute_loss, z_prior=self.z_prior, table_cache=table_cache,
                                              side_branch=side_branch, mmd_rows=self.mmd_rows)
             perf_emb = perf_enc_out.embeddings
         if enc_branch is not None:
-            enc_branch.join(score_emb)
-        return ScorePerformerEncoderOutputs(score_embeddings=score_emb, score_mask=score_mask, perf_embeddings=perf_emb,
-                                            score_encoder=score_enc_out, perf_encoder=perf_enc_out)
+            enc_branch.join(score_emb, *[t for t in (extra or ()) if isinstance(t, torch.Tensor)])
+        out = ScorePerformerEncoderOutputs(score_embeddings=score_emb, score_mask=score_mask, perf_embeddings=perf_emb,
+                                           score_encoder=score_enc_out, perf_encoder=perf_enc_out)
+        out.after_score = extra
+        return out
 
     def forward(self, perf: Tensor, perf_mask: Optional[Tensor] = None, score: Optional[Tensor] = None,
                 score_mask: Optional[Tensor] = None, noisy_perf: Optional[Tensor] = None, noisy_perf_mask: Optional[Tensor] = None,
@@ -201,9 +211,18 @@ class ScorePerformer(_LMMixin, Model):
         # MMD terms and the classifier heads are dozens of tiny kernels nothing else waits for: they run on a side stream
         # (a parallel branch of the captured graph) underneath the decoder and are joined just before the losses are summed
         branch = SideBranch(perf.device)
+        # the (tied) performance table is built here, before any branch forks off: every stack of the step then finds it -- or a
+        # prefix of it -- in the cache, on a stream that already waits for this one
+        self.perf_decoder.model.token_emb.table(table_cache)
+        # the decoder's input embedding needs the score embeddings but not the latents: it runs behind the score encoder, next to
+        # the performance encoder, instead of after both
+        pre_embed = None
+        if self.score_encoder is not None and hasattr(self.perf_decoder, "pre_embed") and _os.environ.get("SPB_DEC_PRE_EMBED", "1") == "1":
+            pre_embed = lambda score_emb: self.perf_decoder.pre_embed(perf, masked_perf, score_emb, table_cache)
         enc_out = self.forward_encoders(
             perf=default(noisy_perf, perf), perf_mask=default(noisy_perf_mask, perf_mask), score=score, score_mask=score_mask,
-            bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask, table_cache=table_cache, side_branch=branch)
+            bars=bars, beats=beats, onsets=onsets, deadpan_mask=deadpan_mask, table_cache=table_cache, side_branch=branch,
+            after_score=pre_embed)
 
         clf_out = None
         if self.classifiers is not None:
@@ -216,7 +235,8 @@ class ScorePerformer(_LMMixin, Model):
 
         perf_dec_out = self.perf_decoder(perf, mask=perf_mask, style_embeddings=enc_out.perf_embeddings,
                                          context=enc_out.score_embeddings, context_mask=enc_out.score_mask, labels=labels,
-                                         seq_masked=masked_perf, table_cache=table_cache)
+                                         seq_masked=masked_perf, table_cache=table_cache,
+                                         **({} if enc_out.after_score is None else {"pre_embedded": enc_out.after_score}))
         loss, losses = perf_dec_out.loss, perf_dec_out.losses
 
         side_out = []

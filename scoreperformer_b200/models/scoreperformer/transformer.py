@@ -150,12 +150,20 @@ class TupleTransformer(nn.Module, Constructor):
     def forward(self, x: Tensor, mask: Optional[Tensor] = None, x_extra=None, style_embeddings: Optional[Tensor] = None,
                 context: Optional[Tensor] = None, context_mask: Optional[Tensor] = None, caches: Optional[TupleTransformerCaches] = None,
                 logits_keys: Optional[List] = None, return_embeddings: bool = False, return_attn: bool = False,
-                return_caches: bool = False, table_cache: Optional[dict] = None, **kwargs):
+                return_caches: bool = False, table_cache: Optional[dict] = None, pre_embedded: Optional[tuple] = None, **kwargs):
         if return_attn:
             raise NotImplementedError("attention maps are never materialised by the fused attention kernel")
         table_cache = {} if table_cache is None else table_cache
-        h, token_emb, style_embeddings, context = self.embed_inputs(
-            x, x_extra, style_embeddings, context, caches.token_emb if caches is not None else None, table_cache)
+        if pre_embedded is not None:
+            # embed_inputs() was evaluated ahead of time (ScorePerformer.forward runs it next to the performance encoder, before
+            # the style embeddings exist); only possible when the style does not enter through the concatenation
+            assert self.style_emb_mode != EmbeddingModes.CONCAT and caches is None
+            h, token_emb, context = pre_embedded
+            if style_embeddings is not None:
+                style_embeddings = style_embeddings[:, :h.shape[1]]
+        else:
+            h, token_emb, style_embeddings, context = self.embed_inputs(
+                x, x_extra, style_embeddings, context, caches.token_emb if caches is not None else None, table_cache)
         res = self.transformer(h, mask=mask, context=context, context_mask=context_mask, style_embeddings=style_embeddings,
                                intermediates_cache=caches.transformer if caches is not None else None, return_hiddens=return_caches)
         out, intermediates = res if return_caches else (res, None)

@@ -191,6 +191,20 @@ class ScorePerformerMixedLMWrapper(ScorePerformerLMWrapper):
         return decode.unmask_mixlm(self, tokens, tokens_masked, temperature, filter_logits_fn, filter_kwargs, filter_key_ids, caches,
                                    return_caches, **kwargs)
 
+    def pre_embed(self, seq: Tensor, seq_masked: Optional[Tensor] = None, context: Optional[Tensor] = None,
+                  table_cache: Optional[dict] = None):
+        """The input embedding of forward() (same shifts, TupleTransformer.embed_inputs) for callers that can evaluate it before
+        the style embeddings exist; hand the result to forward(pre_embedded=...).  None when the style enters by concatenation."""
+        if self.model.style_emb_mode == "cat":
+            return None
+        seq = seq[:, :-1]
+        if exists(seq_masked):
+            seq_masked = seq_masked[:, 1:]
+        if exists(context) and self.model.context_emb_mode == "cat":
+            context = context[:, 1:]
+        h, token_emb, _, context = self.model.embed_inputs(seq, seq_masked, None, context, None, table_cache)
+        return h, token_emb, context
+
     def forward(self, seq: Tensor, labels: Optional[Tensor] = None, **kwargs):
         seq = seq[:, :-1]
         labels = labels[:, 1:] if exists(labels) else None
