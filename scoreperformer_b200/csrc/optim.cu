@@ -56,7 +56,45 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
     }
 }
 
+// dst_i[0:n_i] += src_i[0:n_i] for up to MULTI_ADD_MAX (dst, src) pairs in one launch (blockIdx.y = pair)
+constexpr int MULTI_ADD_MAX = 48;
+struct MultiAdd {
+    float* dst[MULTI_ADD_MAX];
+    const float* src[MULTI_ADD_MAX];
+    int n[MULTI_ADD_MAX];
+};
+__global__ void __launch_bounds__(256) multi_add_kernel(MultiAdd a) {
+    const int k = blockIdx.y;
+    float* __restrict__ dst = a.dst[k];
+    const float* __restrict__ src = a.src[k];
+    const int n = a.n[k];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] += src[i];
+}
+
 }  // namespace
+
+// Gradient accumulation of many small tensors in one launch: dst_i += src_i (fp32, n_i elements), i < n_pairs.  dsts / srcs / sizes
+// are HOST arrays.  (The AdaLN projections of a stack get their gradients from one batched GEMM; this adds each slice into its
+// parameter's gradient -- modules/layers.py:31-47 has one nn.Linear per norm.)
+extern "C" int spb_multi_add_f32(float* const* dsts, const float* const* srcs, const int* sizes, int n_pairs, cudaStream_t stream) {
+    SPB_CHECK_ARG(n_pairs == 0 || (dsts && srcs && sizes), "spb_multi_add_f32: null pointer");
+    for (int base = 0; base < n_pairs; base += MULTI_ADD_MAX) {
+        MultiAdd a;
+        const int cnt = n_pairs - base < MULTI_ADD_MAX ? n_pairs - base : MULTI_ADD_MAX;
+        int n_max = 0;
+        for (int i = 0; i < MULTI_ADD_MAX; ++i) {
+            const int j = i < cnt ? base + i : base;
+            a.dst[i] = dsts[j]; a.src[i] = srcs[j]; a.n[i] = i < cnt ? sizes[j] : 0;
+            if (a.n[i] > n_max) n_max = a.n[i];
+        }
+        if (n_max == 0) continue;
+        int bx = (n_max + 255) / 256;
+        if (bx > 64) bx = 64;
+        multi_add_kernel<<<dim3(bx, cnt), 256, 0, stream>>>(a);
+        SPB_CHECK_LAUNCH();
+    }
+    return SPB_OK;
+}
 
 // p / g / m / v fp32 [n] (n % 4 == 0, 16-byte aligned); shadow bf16 [n] or null.  grad_norm: device scalar holding the L2 norm of
 // g BEFORE grad_scale (null or max_norm <= 0 disables clipping).  step: device int64 holding the 1-based step number t.

@@ -493,17 +493,19 @@ class TransformerStackFn(torch.autograd.Function):
         if spec.ada:
             dw_ada = K.gemm(dgb_all, style16, trans_a=True, trans_b=True, out_dtype=F32, split_k=0)   # [n_norms*2D, S]
             db_ada = K.colsum(dgb_all)
+            add_dst, add_src = [], []
             for i in range(spec.n_norms):
                 j = _norm_index(spec, i)
                 gw, gb = dw_ada[i * 2 * D:(i + 1) * 2 * D], db_ada[i * 2 * D:(i + 1) * 2 * D]
                 dw_direct, db_direct = direct_grad(params[j]), direct_grad(params[j + 1])
-                if STACK_BACKWARD_DONE is not None and dw_direct is not None and db_direct is not None:
-                    # data parallel: the stack's gradient bucket leaves for NCCL at the end of this node, so nothing may be left
-                    # for autograd's AccumulateGrad to add afterwards
-                    dw_direct.add_(gw)
-                    db_direct.add_(gb)
+                if dw_direct is not None and db_direct is not None:
+                    # straight into the gradient buffers, all norms in one launch (and under data parallelism nothing may be left
+                    # for autograd's AccumulateGrad: the stack's gradient bucket leaves for NCCL at the end of this node)
+                    add_dst += [dw_direct, db_direct]
+                    add_src += [gw, gb]
                 else:
                     grads[j], grads[j + 1] = gw, gb
+            K.multi_add(add_dst, add_src)
             if ctx.needs_input_grad[3]:
                 d_style = K.gemm(dgb_all, w_ada16, trans_b=True, out_dtype=F32).view(ctx.style_shape)
         if wb is not None:

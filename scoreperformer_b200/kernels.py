@@ -294,6 +294,19 @@ def ffn_bwd(dy: Tensor, w2t: Tensor, w1: Tensor, u: Tensor, db1: Optional[Tensor
     return dxn, du
 
 
+def multi_add(dsts: Sequence[Tensor], srcs: Sequence[Tensor]) -> None:
+    """dst_i += src_i for lists of fp32 tensors (contiguous, same numel pairwise) in ONE launch."""
+    if not dsts:
+        return
+    _require_cuda(*dsts, *srcs)
+    assert len(dsts) == len(srcs)
+    for d, s_ in zip(dsts, srcs):
+        assert d.dtype == F32 and s_.dtype == F32 and d.is_contiguous() and s_.is_contiguous() and d.numel() == s_.numel()
+    sizes = (ctypes.c_int * len(dsts))(*[d.numel() for d in dsts])
+    _call("spb_multi_add_f32", _ptr_array(dsts), _ptr_array(srcs), sizes, len(dsts), _stream())
+    _count()
+
+
 def ffn_fused_ok(dim: int, hidden: int) -> bool:
     return dim == 256 and hidden == 1024 and _os.environ.get("SPB_FFN", "fused") == "fused"
 
