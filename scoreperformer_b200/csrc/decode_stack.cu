@@ -275,12 +275,20 @@ decode_stack_kernel(DecodeStackParams p) {
                 for (int h = 0; h < 4; ++h) slope[h] = __expf(p.logslopes[l][h]);
                 float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (live) {
+                    // the rows of the NEXT block of keys are requested before this block is evaluated: with eight warps per SM
+                    // the cache stream is bound by loads in flight, not by arithmetic
+                    uint4 kq[UNR], kn[UNR];
+#pragma unroll
+                    for (int u_ = 0; u_ < UNR; ++u_) {
+                        const int j = k_lo + grp + 4 * u_;
+                        kn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(kvb + (size_t)j * 128 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                     for (int base = k_lo; base < k_hi; base += 4 * UNR) {          // warp-uniform trip count: the body shuffles
-                        uint4 kq[UNR];
 #pragma unroll
                         for (int u_ = 0; u_ < UNR; ++u_) {
-                            const int j = base + grp + 4 * u_;
-                            kq[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(kvb + (size_t)j * 128 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+                            kq[u_] = kn[u_];
+                            const int j = base + 4 * UNR + grp + 4 * u_;
+                            kn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(kvb + (size_t)j * 128 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
                         }
 #pragma unroll
                         for (int u_ = 0; u_ < UNR; ++u_) {
@@ -327,12 +335,18 @@ decode_stack_kernel(DecodeStackParams p) {
                     for (int e = 0; e < 8; ++e) o[h][e] = 0.f;
                 if (live) {
                     const __nv_bfloat16* vbase = kvb + DS_DH + sub * 8;
+                    uint4 vq[UNR], vn[UNR];
+#pragma unroll
+                    for (int u_ = 0; u_ < UNR; ++u_) {
+                        const int j = k_lo + grp + 4 * u_;
+                        vn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                     for (int base = k_lo; base < k_hi; base += 4 * UNR) {
-                        uint4 vq[UNR];
 #pragma unroll
                         for (int u_ = 0; u_ < UNR; ++u_) {
-                            const int j = base + grp + 4 * u_;
-                            vq[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128) : make_uint4(0u, 0u, 0u, 0u);
+                            vq[u_] = vn[u_];
+                            const int j = base + 4 * UNR + grp + 4 * u_;
+                            vn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128) : make_uint4(0u, 0u, 0u, 0u);
                         }
 #pragma unroll
                         for (int u_ = 0; u_ < UNR; ++u_) {
@@ -469,26 +483,53 @@ decode_stack_kernel(DecodeStackParams p) {
         }
         grid_barrier(p.barrier, epoch);
 
-        // ---- E: x += h W2^T, split-K x4 (K = 256 each), fp32 atomics into the residual stream
+        // ---- E: x += h W2^T.  A tile is 32 rows x 16 columns over the WHOLE K = 1024: the four warp pairs of the CTA each take a
+        // quarter of K (two m16n8 pieces per warp) and the quarters are summed through shared memory in a fixed order, so the
+        // residual stream -- and with it every rendered token -- is bit-reproducible from run to run (no atomics)
         {
-            const int col_blocks = DS_D / DS_TN, splits = DS_HID / DS_D;
-            for (int t = blockIdx.x; t < row_blocks * col_blocks * splits; t += gridDim.x) {
-                const int sp = t / (row_blocks * col_blocks), rem = t - sp * row_blocks * col_blocks;
-                const int rb = rem / col_blocks, cb = rem - rb * col_blocks;
-                uint32_t bf[32];
-                load_w<16>(bf, p.w2[l] + sp * DS_D, DS_HID, cb * DS_TN + (warp >> 1) * 8, lane);
+            constexpr int TN_E = 16;
+            const int col_blocks = DS_D / TN_E;
+            const int mh = warp & 1, kq = warp >> 1;
+            __nv_bfloat16* sAk = sA + (size_t)kq * DS_TM * DS_LDA;                       // this warp's K quarter of the staged rows
+            float* red = reinterpret_cast<float*>(smem_raw + 4 * DS_TM * DS_LDA * 2);     // [4 kq][2 mh][2 pieces][32 lanes][4]
+            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+                const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                uint32_t bf0[32], bf1[32];
+                load_w<16>(bf0, p.w2[l] + kq * DS_D, DS_HID, cb * TN_E, lane);
+                load_w<16>(bf1, p.w2[l] + kq * DS_D, DS_HID, cb * TN_E + 8, lane);
                 __syncthreads();
-                stage_rows(sA, p.hmid, DS_HID, sp * DS_D, DS_D, rb * DS_TM, B);
-                __syncthreads();
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
-                const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
-                    if (row < B) {
-                        atomicAdd(p.xres + (size_t)row * DS_D + col, acc[2 * hf]);
-                        atomicAdd(p.xres + (size_t)row * DS_D + col + 1, acc[2 * hf + 1]);
+                for (int q4 = 0; q4 < 4; ++q4) stage_rows(sA + (size_t)q4 * DS_TM * DS_LDA, p.hmid, DS_HID, q4 * DS_D, DS_D, rb * DS_TM, B);
+                __syncthreads();
+                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_pre<16>(acc0, sAk, DS_LDA, bf0, warp, lane);
+                mma_pre<16>(acc1, sAk, DS_LDA, bf1, warp, lane);
+                float4* my = reinterpret_cast<float4*>(red) + ((kq * 2 + mh) * 2) * 32 + lane;
+                my[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+                my[32] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+                __syncthreads();
+                if (kq == 0) {
+#pragma unroll
+                    for (int piece = 0; piece < 2; ++piece) {
+                        float4 sum = reinterpret_cast<const float4*>(red)[((0 * 2 + mh) * 2 + piece) * 32 + lane];
+#pragma unroll
+                        for (int q4 = 1; q4 < 4; ++q4) {
+                            const float4 v = reinterpret_cast<const float4*>(red)[((q4 * 2 + mh) * 2 + piece) * 32 + lane];
+                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                        }
+                        const int col = cb * TN_E + piece * 8 + tig * 2;
+                        const float part[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int row = rb * DS_TM + mh * 16 + g + hf * 8;
+                            if (row < B) {
+                                float2* xr = reinterpret_cast<float2*>(p.xres + (size_t)row * DS_D + col);
+                                float2 v = *xr;
+                                v.x += part[2 * hf];
+                                v.y += part[2 * hf + 1];
+                                *xr = v;
+                            }
+                        }
                     }
                 }
             }
@@ -557,7 +598,9 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     p.gb = reinterpret_cast<__nv_bfloat16*>(gb); p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv);
     p.o = reinterpret_cast<__nv_bfloat16*>(o); p.hmid = reinterpret_cast<__nv_bfloat16*>(hmid);
     p.xres = xres; p.hid_out = hid_out; p.out = out; p.barrier = barrier; p.eps = eps;
-    const int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4;
+    int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4;
+    const int smem_e = 4 * DS_TM * DS_LDA * 2 + 4 * 2 * 2 * 32 * 16;        // phase E: four K quarters of the rows + the reduction scratch
+    if (smem < smem_e) smem = smem_e;
     SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
     decode_stack_kernel<<<spb_num_sms(), DS_THREADS, smem, stream>>>(p);
