@@ -126,6 +126,10 @@ int spb_transpose_bf16(const void* const* srcs, int n_mats, void* dst, int rows,
  * batched AdaLN weight-gradient GEMM into the gradients of the per-norm nn.Linear parameters (modules/layers.py:31-47). */
 int spb_multi_add_f32(float* const* dsts, const float* const* srcs, const int* sizes, int n_pairs, spb_stream_t stream);
 
+/* dst_i = src_i (nbytes_i bytes, device to device) for n_pairs buffers in one launch; host arrays of device pointers / sizes.  Feeds
+ * the tensors of a collated batch (data/collators/score_performance.py:186-234) into the static inputs of the captured step. */
+int spb_multi_copy(void* const* dsts, const void* const* srcs, const long long* nbytes, int n_pairs, spb_stream_t stream);
+
 /* Computed per-field tables W_f = index rows {discrete ids} + MLP(token_values) (modules/transformer/embeddings.py:124-143,199-211),
  * all fields in one launch.  ptrs is a HOST array of device pointers, 7 per field for the forward (index_weight [V,128], token_values
  * [V], discrete mask [V] fp32 0/1, W0 [128], b0 [128], W1 [128,128], b1 [128]) and 12 per field for the backward (+ the five gradient

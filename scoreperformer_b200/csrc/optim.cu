@@ -71,7 +71,49 @@ __global__ void __launch_bounds__(256) multi_add_kernel(MultiAdd a) {
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] += src[i];
 }
 
+// dst_i[0:n_i) = src_i[0:n_i) (bytes) for up to MULTI_ADD_MAX pairs in one launch; 16-byte units when both ends are aligned
+struct MultiCopy {
+    uint8_t* dst[MULTI_ADD_MAX];
+    const uint8_t* src[MULTI_ADD_MAX];
+    long long n[MULTI_ADD_MAX];
+};
+__global__ void __launch_bounds__(256) multi_copy_kernel(MultiCopy a) {
+    const int k = blockIdx.y;
+    uint8_t* __restrict__ dst = a.dst[k];
+    const uint8_t* __restrict__ src = a.src[k];
+    const long long n = a.n[k];
+    const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+    const long long n16 = vec ? n / 16 : 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (long long i = n16 * 16 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) dst[i] = src[i];
+}
+
 }  // namespace
+
+// Many small device-to-device copies in one launch: dst_i = src_i (n_i bytes).  dsts / srcs / nbytes are HOST arrays.  (The tensors
+// of a collated batch -- tokens, masks, segment ids, labels -- go into the static inputs of the captured step this way.)
+extern "C" int spb_multi_copy(void* const* dsts, const void* const* srcs, const long long* nbytes, int n_pairs, cudaStream_t stream) {
+    SPB_CHECK_ARG(n_pairs == 0 || (dsts && srcs && nbytes), "spb_multi_copy: null pointer");
+    for (int base = 0; base < n_pairs; base += MULTI_ADD_MAX) {
+        MultiCopy a;
+        const int cnt = n_pairs - base < MULTI_ADD_MAX ? n_pairs - base : MULTI_ADD_MAX;
+        long long n_max = 0;
+        for (int i = 0; i < MULTI_ADD_MAX; ++i) {
+            const int j = i < cnt ? base + i : base;
+            a.dst[i] = reinterpret_cast<uint8_t*>(dsts[j]); a.src[i] = reinterpret_cast<const uint8_t*>(srcs[j]);
+            a.n[i] = i < cnt ? nbytes[j] : 0;
+            if (a.n[i] > n_max) n_max = a.n[i];
+        }
+        if (n_max == 0) continue;
+        long long bx = (n_max / 16 + 255) / 256;
+        if (bx < 1) bx = 1;
+        if (bx > 128) bx = 128;
+        multi_copy_kernel<<<dim3((unsigned)bx, cnt), 256, 0, stream>>>(a);
+        SPB_CHECK_LAUNCH();
+    }
+    return SPB_OK;
+}
 
 // Gradient accumulation of many small tensors in one launch: dst_i += src_i (fp32, n_i elements), i < n_pairs.  dsts / srcs / sizes
 // are HOST arrays.  (The AdaLN projections of a stack get their gradients from one batched GEMM; this adds each slice into its

@@ -294,6 +294,18 @@ def ffn_bwd(dy: Tensor, w2t: Tensor, w1: Tensor, u: Tensor, db1: Optional[Tensor
     return dxn, du
 
 
+def multi_copy(dsts: Sequence[Tensor], srcs: Sequence[Tensor]) -> None:
+    """dst_i.copy_(src_i) for lists of same-shaped, same-dtype contiguous CUDA tensors in ONE launch."""
+    if not dsts:
+        return
+    _require_cuda(*dsts, *srcs)
+    for d, s_ in zip(dsts, srcs):
+        assert d.dtype == s_.dtype and d.shape == s_.shape and d.is_contiguous() and s_.is_contiguous()
+    sizes = (ctypes.c_longlong * len(dsts))(*[d.numel() * d.element_size() for d in dsts])
+    _call("spb_multi_copy", _ptr_array(dsts), _ptr_array(srcs), sizes, len(dsts), _stream())
+    _count()
+
+
 def multi_add(dsts: Sequence[Tensor], srcs: Sequence[Tensor]) -> None:
     """dst_i += src_i for lists of fp32 tensors (contiguous, same numel pairwise) in ONE launch."""
     if not dsts:

@@ -33,6 +33,7 @@ SIGNATURES = {
     "spb_unpack_batch": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _U32, _U32, _I, c_longlong, _I, _P],
     "spb_ffn_fwd": [_P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _F, _U64, _P, _P],
     "spb_ffn_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _U64, _P, _P],
+    "spb_multi_copy": [_P, _P, _P, _I, _P],
     "spb_multi_add_f32": [_P, _P, _P, _I, _P],
     "spb_transpose_bf16": [_P, _I, _P, _I, _I, _P],
     "spb_glu_bwd": [_P, _P, _P, _P, _I, _I, _F, _U64, _P, _P],

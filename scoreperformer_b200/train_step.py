@@ -376,6 +376,14 @@ class TrainStep:
         if not self._select_graph(batch):
             torch.cuda.synchronize()
             self._capture({k: v.to(dev) for k, v in batch.items()})
+        # device-resident tensors of the right dtype go into the static inputs in one launch, anything else (pinned host memory,
+        # another dtype or layout) through copy_
+        fast = [(self.static_batch[k], v) for k, v in batch.items()
+                if v.is_cuda and v.device == dev and v.dtype == self.static_batch[k].dtype and v.is_contiguous()
+                and v.shape == self.static_batch[k].shape and self.static_batch[k].is_contiguous()]
+        taken = {id(v) for _, v in fast}
         for k, v in batch.items():
-            self.static_batch[k].copy_(v, non_blocking=True)
+            if id(v) not in taken:
+                self.static_batch[k].copy_(v, non_blocking=True)
+        K.multi_copy([d for d, _ in fast], [s for _, s in fast])
         return self._replay()
