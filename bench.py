@@ -381,7 +381,7 @@ def main():
         import scoreperformer_b200.fused as fused_mod
         fused_mod.K.gemm = timed_gemm
         # the other tensor-core kernels of the step, timed the same way: fused feed-forward forward, attention forward / backward
-        other = {"ffn_fwd": [], "attention_fwd": [], "attention_bwd": []}
+        other = {"ffn_fwd": [], "ffn_bwd": [], "attention_fwd": [], "attention_bwd": []}
         orig_other = {name: getattr(K, name) for name in other}
 
         def wrap(name):
@@ -452,18 +452,29 @@ def main():
         n_rows, Dm, Hh = B * T, 256, 1024
         attn_full = 4.0 * B * 4 * T * T * 64
         attn_avg = attn_full * (6 + 4 * 0.5) / 10
-        alg = {"ffn_fwd": 2.0 * n_rows * Dm * 3 * Hh, "attention_fwd": attn_avg, "attention_bwd": 2.5 * attn_avg}
+        alg = {"ffn_fwd": 2.0 * n_rows * Dm * 3 * Hh, "ffn_bwd": 2.0 * n_rows * Dm * 3 * Hh, "attention_fwd": attn_avg,
+               "attention_bwd": 2.5 * attn_avg}
         names = {"ffn_fwd": "ffn_fwd_pair_kernel (GEMM1 -> GLU -> GEMM2 -> +residual, u / h on chip)",
+                 "ffn_bwd": "ffn_bwd_pair_kernel (dh = dy W2 on chip -> GLU' -> du in place -> dxn = du W1, bias gradient)",
                  "attention_fwd": "attn_fwd_tc_kernel (S, P, O in TMEM)", "attention_bwd": "attn_bwd_tc_kernel (+ dQ convert)"}
+        # algorithmic HBM bytes per launch of the fused feed-forward kernels and the DRAM bytes ncu measured
+        # for one launch (profiles/r02_ncu_full_ffn_fused.txt, r02_ncu_full_ffn_bwd.txt)
+        hbm = {"ffn_fwd": {"algorithmic_bytes": n_rows * (512 + 1024 + 1024 + 4096 + 2048.0), "traffic": 53547264 + 182329344},
+               "ffn_bwd": {"algorithmic_bytes": n_rows * (512 + 4096 + 4096 + 512.0), "traffic": 153690368 + 95829760}}
         extra = []
         for name, evs in other.items():
             if not evs:
                 continue
             ms_ = sum(s_.elapsed_time(e_) for s_, e_ in evs)
             tf = alg[name] * len(evs) / (ms_ / 1e3) / 1e12
-            extra.append({"kernel": names[name], "launches_per_step": len(evs), "avg_launch_us": ms_ / len(evs) * 1e3,
-                          "algorithmic_flops_per_launch": alg[name], "achieved": tf, "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
-                          "share_of_step": ms_ / ms_step})
+            ent = {"kernel": names[name], "launches_per_step": len(evs), "avg_launch_us": ms_ / len(evs) * 1e3,
+                   "algorithmic_flops_per_launch": alg[name], "achieved": tf, "unit": "TFLOP/s", "frac": tf / peaks["tflops"],
+                   "share_of_step": ms_ / ms_step}
+            if name in hbm and (B * T == 32768):
+                gbs = hbm[name]["algorithmic_bytes"] * len(evs) / (ms_ / 1e3) / 1e9
+                ent.update({"hbm_algorithmic_bytes_per_launch": hbm[name]["algorithmic_bytes"], "hbm_achieved_gbs": gbs,
+                            "hbm_frac": gbs / peaks["hbm_gbs"], "traffic": hbm[name]["traffic"]})
+            extra.append(ent)
         roofline["other_tensor_kernels"] = extra
         if args.profile_kernels:
             agg = {}
