@@ -76,12 +76,32 @@ class ScorePerformerLMWrapper(LMWrapper):
         # name -> fp32 [V] token values; set by ScorePerformerEvaluator.attach(): the head kernel then accumulates the evaluator's
         # statistics while the logits are in tensor memory, and `forward` returns them as `eval_stats`
         self.eval_token_values = None
+        self._unexpected_labels = None
+        self._excluded_index = {}
 
     def _probe_label_fields(self, labels: Tensor):
+        """Fields that carry labels.  The reference asks every batch (wrappers.py:49-59, a host sync per field); here the set is
+        probed on the first batch (or given: `label_fields`) and then frozen, so the head only evaluates those fields and the
+        step can be captured.  Labels that later show up in an excluded field are COUNTED on the device
+        (`unexpected_label_count()`, read by TrainStep.unexpected_label_count) instead of silently ignored."""
+        n_fields = labels.shape[-1]
         if self.label_fields is None:
-            has = (labels != self.ignore_index).reshape(-1, labels.shape[-1]).any(dim=0)
+            has = (labels != self.ignore_index).reshape(-1, n_fields).any(dim=0)
             self.label_fields = tuple(int(i) for i in torch.nonzero(has).flatten().tolist())
+        excluded = [i for i in range(n_fields) if i not in self.label_fields]
+        if excluded and labels.is_cuda and self.training:
+            if self._unexpected_labels is None or self._unexpected_labels.device != labels.device:
+                self._unexpected_labels = torch.zeros((), dtype=torch.int64, device=labels.device)
+            idx = self._excluded_index.get((labels.device, tuple(excluded)))
+            if idx is None:
+                idx = self._excluded_index[(labels.device, tuple(excluded))] = torch.tensor(excluded, device=labels.device)
+            self._unexpected_labels += (labels.reshape(-1, n_fields).index_select(1, idx) != self.ignore_index).sum()
         return self.label_fields
+
+    def unexpected_label_count(self) -> int:
+        """Labels seen so far in fields outside `label_fields` (they did not enter the loss).  Non-zero means the frozen field set
+        is too small for this data: set `label_fields` explicitly (or to None to re-probe).  Reading it synchronises."""
+        return 0 if self._unexpected_labels is None else int(self._unexpected_labels)
 
     def forward(self, seq: Tensor, labels: Optional[Tensor] = None, **kwargs):
         head = self.model.lm_head

@@ -206,6 +206,13 @@ class TrainStep:
         c = getattr(enc, "segment_overflow", None)
         return 0 if c is None else int(c)
 
+    def unexpected_label_count(self) -> int:
+        """Labels (accumulated over all steps so far) found in output fields outside the LM wrapper's frozen `label_fields`: they
+        did not enter the loss (the reference re-checks the fields every batch, wrappers.py:49-59).  Reading it synchronises."""
+        wrapper = getattr(self.model, "perf_decoder", None)
+        fn = getattr(wrapper, "unexpected_label_count", None)
+        return 0 if fn is None else fn()
+
     def mark_weights_changed(self) -> None:
         """Call after writing parameters from outside the step (load_state_dict, manual edits): rebuilds the bf16 shadow."""
         self._shadow_stale = True

@@ -197,3 +197,23 @@ def test_static_segment_tables_report_overflow():
     m.perf_encoder.segment_overflow.zero_()
     ts.step(sparse)
     assert ts.segment_overflow_count() == 0
+
+
+@pytest.mark.gpu
+def test_frozen_label_fields_count_unexpected_labels():
+    """the label fields are probed on the first batch and frozen (the reference re-checks them every batch,
+    wrappers.py:49-59).  Labels that later appear in an excluded field must be visible: a device counter, read through TrainStep."""
+    from scoreperformer_b200.train_step import TrainStep
+    m = parity.build_model(dropout=False, device="cuda").train()
+    ts = TrainStep(m, lr=0.0, use_graph=False)
+    batch = {k: v.cuda() for k, v in parity.make_batch(2, 48, seed=2).items()}
+    ts.step(batch)
+    fields = m.perf_decoder.label_fields
+    assert ts.unexpected_label_count() == 0 and 0 < len(fields) < batch["labels"].shape[-1]
+    excluded = [i for i in range(batch["labels"].shape[-1]) if i not in fields][0]
+    odd = dict(batch)
+    odd["labels"] = batch["labels"].clone()
+    odd["labels"][:, 1:9, excluded] = 5              # the wrapper shifts the labels by one position: 8 labelled rows per sequence
+    ts.step(odd)
+    assert ts.unexpected_label_count() == 2 * 8
+
