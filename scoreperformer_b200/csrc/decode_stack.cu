@@ -52,6 +52,7 @@ struct DecodeStackParams {
     float* xres;                                 // [B, 256] residual stream
     float* hid_out;                              // [depth, B, 256] inputs of the attention layers (cache contract), or null
     float* out;                                  // [B, 256]
+    __nv_bfloat16* out16;                        // optional bf16 copy of `out` (operand of the head projection), or null
     unsigned* barrier;                           // zeroed by the host before the launch
     float eps;
 };
@@ -560,6 +561,35 @@ decode_stack_kernel(DecodeStackParams p) {
         for (int j = 0; j < 8; ++j) y[j] = v[j] * rstd * (1.f + gm[j]) + bt[j];
         *reinterpret_cast<float4*>(p.out + (size_t)row * DS_D + lane * 8) = make_float4(y[0], y[1], y[2], y[3]);
         *reinterpret_cast<float4*>(p.out + (size_t)row * DS_D + lane * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        if (p.out16 != nullptr)
+            *reinterpret_cast<uint4*>(p.out16 + (size_t)row * DS_D + lane * 8) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    }
+}
+
+// dst_k[b, :] = src_k[b, pos + shift_k, :] for up to 8 row-major [B, T, row] arrays in one launch (blockIdx.y = array): what a
+// note-step reads at its device-side position -- the previous tuple, and the per-position terms prepared before the loop
+constexpr int GATHER_MAX = 8;
+struct GatherParams {
+    const uint8_t* src[GATHER_MAX];
+    uint8_t* dst[GATHER_MAX];
+    int row_bytes[GATHER_MAX];
+    int shift[GATHER_MAX];
+    const long long* pos_dev;
+    int T;
+};
+__global__ void __launch_bounds__(128) gather_at_pos_kernel(GatherParams g) {
+    const int k = blockIdx.y, b = blockIdx.x;
+    long long t = *g.pos_dev + g.shift[k];
+    if (t < 0) t = 0;
+    if (t >= g.T) t = g.T - 1;
+    const int rb = g.row_bytes[k];
+    const uint8_t* __restrict__ src = g.src[k] + ((size_t)b * g.T + (size_t)t) * rb;
+    uint8_t* __restrict__ dst = g.dst[k] + (size_t)b * rb;
+    if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        for (int i = threadIdx.x; i < rb / 16; i += 128) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    } else {
+        for (int i = threadIdx.x; i < rb; i += 128) dst[i] = src[i];
     }
 }
 
@@ -569,11 +599,12 @@ decode_stack_kernel(DecodeStackParams p) {
 // per layer l (7 entries at 7*l): wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048],
 // w2 bf16 [256,1024], kv cache bf16 [B, cap, 128].  w_ada bf16 [(2*depth+1)*512, S] / b_ada fp32 hold (gamma-1 | beta) rows per
 // norm.  scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; `barrier` one uint32.
-// hid_out (fp32 [depth, B, 256], may be NULL) receives the inputs of the attention layers (the reference's cache contract).
+// hid_out (fp32 [depth, B, 256], may be NULL) receives the inputs of the attention layers (the reference's cache contract);
+// out_bf16 (bf16 [B, 256], may be NULL) a bf16 copy of `out`.
 extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada,
                                      const void* const* ptrs, int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap,
-                                     void* gb, void* qkv, void* o, void* hmid, float* xres, float* hid_out, float* out, unsigned* barrier,
-                                     float eps, cudaStream_t stream) {
+                                     void* gb, void* qkv, void* o, void* hmid, float* xres, float* hid_out, float* out, void* out_bf16,
+                                     unsigned* barrier, float eps, cudaStream_t stream) {
     if (B <= 0) return SPB_OK;
     SPB_CHECK_ARG(x_in && style && w_ada && b_ada && ptrs && pos_dev && gb && qkv && o && hmid && xres && out && barrier,
                   "spb_decode_stack_step: null pointer");
@@ -597,13 +628,31 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     p.key_mask = key_mask; p.pos_dev = pos_dev;
     p.gb = reinterpret_cast<__nv_bfloat16*>(gb); p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv);
     p.o = reinterpret_cast<__nv_bfloat16*>(o); p.hmid = reinterpret_cast<__nv_bfloat16*>(hmid);
-    p.xres = xres; p.hid_out = hid_out; p.out = out; p.barrier = barrier; p.eps = eps;
+    p.xres = xres; p.hid_out = hid_out; p.out = out; p.out16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.barrier = barrier; p.eps = eps;
     int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4;
     const int smem_e = 4 * DS_TM * DS_LDA * 2 + 4 * 2 * 2 * 32 * 16;        // phase E: four K quarters of the rows + the reduction scratch
     if (smem < smem_e) smem = smem_e;
     SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
     decode_stack_kernel<<<spb_num_sms(), DS_THREADS, smem, stream>>>(p);
+    SPB_CHECK_LAUNCH();
+    return SPB_OK;
+}
+
+// dst_k[b, :] = src_k[b, *pos_dev + shift_k, :] (row_bytes_k bytes per row; src_k row-major [B, T, row]) for n <= 8 arrays in one
+// launch; positions are clamped to [0, T).  srcs / dsts / row_bytes / shifts are HOST arrays.
+extern "C" int spb_gather_at_pos(const void* const* srcs, void* const* dsts, const int* row_bytes, const int* shifts, int n,
+                                 const long long* pos_dev, int B, int T, cudaStream_t stream) {
+    if (n <= 0 || B <= 0) return SPB_OK;
+    SPB_CHECK_ARG(srcs && dsts && row_bytes && shifts && pos_dev && n <= GATHER_MAX && T > 0, "spb_gather_at_pos: bad arguments (n <= %d)", GATHER_MAX);
+    GatherParams g;
+    for (int i = 0; i < GATHER_MAX; ++i) {
+        const int j = i < n ? i : 0;
+        g.src[i] = reinterpret_cast<const uint8_t*>(srcs[j]); g.dst[i] = reinterpret_cast<uint8_t*>(dsts[j]);
+        g.row_bytes[i] = row_bytes[j]; g.shift[i] = shifts[j];
+    }
+    g.pos_dev = pos_dev; g.T = T;
+    gather_at_pos_kernel<<<dim3(B, n), 128, 0, stream>>>(g);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
 }

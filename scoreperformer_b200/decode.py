@@ -187,7 +187,50 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
                       and all(1 <= k <= 32 for k in ks) and K._os.environ.get("SPB_DECODE", "fused") == "fused")
     seed = K.seed_from_torch() if any(k > 1 for k in ks) else 0
 
+    # Everything of a note-step that does not depend on the tokens sampled so far is evaluated for ALL positions before the loop,
+    # in large launches: the masked tuple of note i+1 through the embedding and its half of project_multiemb (+ bias), and the
+    # context half of project_emb (+ bias).  A step then adds its own half (the previous, complete tuple) as a GEMM with a residual.
+    lean = plan is not None and K._os.environ.get("SPB_DECODE_FRONT", "lean") == "lean"
+    if lean:
+        Dm = dec.dim
+        wm_l, wm_r, wc_l, wc_r = wm16[:, :Dm], wm16[:, Dm:], wc16[:, :Dm], wc16[:, Dm:]
+        P2 = torch.empty((B, T, Dm), dtype=F32, device=dev)
+        C2 = torch.empty((B, T, Dm), dtype=F32, device=dev)
+        cb = max(1, min(B, 32768 // max(T, 1)))
+        for b0 in range(0, B, cb):
+            b1 = min(B, b0 + cb)
+            x2, _, _ = K.embed_ln_fwd(masked_perf[b0:b1].reshape(-1, F).contiguous(), table, sizes, ln_w, ln_b)
+            x2p = K.gemm(x2, wp16, bias=bp, out_dtype=BF16)
+            K.gemm(x2p, wm_r, bias=bm, out=P2[b0:b1].view(-1, Dm))
+            K.gemm(ctx16[b0:b1].reshape(-1, ctx16.shape[-1]), wc_r, bias=bc, out=C2[b0:b1].view(-1, Dm))
+            del x2, x2p
+        feed_c = feed.contiguous()
+        tok_buf = torch.empty((B, F), dtype=feed_c.dtype, device=dev)
+        p2_buf = torch.empty((B, Dm), dtype=F32, device=dev)
+        c2_buf = torch.empty((B, Dm), dtype=F32, device=dev)
+        st_buf = torch.empty((B, style_f.shape[-1]), dtype=F32, device=dev)
+        ln_buf = torch.empty((B, Dm), dtype=BF16, device=dev)
+
+    def step_lean():
+        # one launch reads what this step needs at the device-side position: tuple i, and the prepared terms / style of note i+1
+        K.gather_at_pos([feed_c, P2, C2, style_f], [tok_buf, p2_buf, c2_buf, st_buf], [0, 1, 1, 1], pos_t)
+        x1, _, _ = K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b)
+        x1p = K.gemm(x1, wp16, bias=bp, out_dtype=BF16)
+        te = K.gemm(x1p, wm_l, residual=p2_buf, out_dtype=F32)
+        K.layer_norm_fwd(te, en_w, en_b, out=ln_buf, need_stats=False)
+        x = K.gemm(ln_buf, wc_l, residual=c2_buf, out_dtype=F32)
+        plan.step(x, st_buf, km, pos_t)
+        # tied head for the masked fields only (wrappers.py:364-380); the stack kernel leaves a bf16 copy of its output
+        e_raw = K.gemm(plan.out16, whead16, trans_b=True, out_dtype=BF16)
+        e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)
+        K.sample_fields(e, table16, fields, [offs[f] for f in fields], [sizes[f] for f in fields],
+                        [top_k if top_k is not None else -(-sizes[f] // 10) for f in fields], out, pos_t,
+                        temperature=temperature, seed=seed)
+        pos_t.add_(1)
+
     def step():
+        if lean and fused_sampling and (feed_c is out or teacher is not None):
+            return step_lean()
         nxt = pos_t + 1
         # decoder position i: full tuple of note i, masked tuple / context / style of note i+1 (wrappers.py:409-431)
         x1, _, _ = K.embed_ln_fwd(feed.index_select(1, pos_t).reshape(B, F).contiguous(), table, sizes, ln_w, ln_b)

@@ -175,6 +175,7 @@ class DecodeStackPlan:
         self.xres = torch.empty((B, 256), dtype=F32, device=dev)
         self.hid = torch.empty((self.depth, B, 256), dtype=F32, device=dev) if keep_hiddens else None
         self.out = torch.empty((B, 256), dtype=F32, device=dev)
+        self.out16 = torch.empty((B, 256), dtype=BF16, device=dev)          # bf16 copy of `out`: the head projection's operand
         self.barrier = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def step(self, x: Tensor, style: Tensor, key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5) -> Tensor:
@@ -184,9 +185,26 @@ class DecodeStackPlan:
         assert key_mask is None or (key_mask.is_contiguous() and key_mask.shape == (self.B, self.cap))
         _call("spb_decode_stack_step", _p(x), _p(style), self.S, _p(self.w_ada), _p(self.b_ada), self.ptrs, self.depth, _p(key_mask),
               _p(pos_dev), self.B, self.cap, _p(self.gb), _p(self.qkv), _p(self.o), _p(self.hmid), _p(self.xres), _p(self.hid),
-              _p(self.out), _p(self.barrier), float(eps), _stream())
+              _p(self.out), _p(self.out16), _p(self.barrier), float(eps), _stream())
         _count()
         return self.out
+
+
+def gather_at_pos(srcs: Sequence[Tensor], dsts: Sequence[Tensor], shifts: Sequence[int], pos_dev: Tensor) -> None:
+    """dst_k[b] = src_k[b, pos + shift_k] for contiguous [B, T, ...] sources and [B, ...] destinations, ONE launch (the position is
+    read on the device, so the launch can be replayed from a CUDA graph)."""
+    _require_cuda(*srcs, *dsts)
+    B, T = srcs[0].shape[0], srcs[0].shape[1]
+    rows = []
+    for s_, d in zip(srcs, dsts):
+        assert s_.is_contiguous() and d.is_contiguous() and s_.shape[0] == B and s_.shape[1] == T and d.shape[0] == B
+        assert s_.dtype == d.dtype and s_[0, 0].numel() == d[0].numel()
+        rows.append(d[0].numel() * d.element_size())
+    assert pos_dev.dtype == torch.int64 and pos_dev.is_cuda
+    n = len(srcs)
+    _call("spb_gather_at_pos", _ptr_array(srcs), _ptr_array(dsts), (ctypes.c_int * n)(*rows), (ctypes.c_int * n)(*[int(v) for v in shifts]),
+          n, _p(pos_dev), B, T, _stream())
+    _count()
 
 
 def sample_fields(e: Tensor, table16: Tensor, fields: Sequence[int], offsets: Sequence[int], vocab: Sequence[int], topk: Sequence[int],
