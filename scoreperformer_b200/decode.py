@@ -193,7 +193,12 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     lean = plan is not None and K._os.environ.get("SPB_DECODE_FRONT", "lean") == "lean"
     if lean:
         Dm = dec.dim
-        wm_l, wm_r, wc_l, wc_r = wm16[:, :Dm], wm16[:, Dm:], wc16[:, :Dm], wc16[:, Dm:]
+        wm_r, wc_l, wc_r = wm16[:, Dm:], wc16[:, :Dm], wc16[:, Dm:]
+        # project_emb of the tuple embedding and the left half of project_multiemb are two linear maps in a row: composed once per
+        # rendering in fp32 (W = Wm_left Wp, its bias joins the prepared term), so a step needs one GEMM for both
+        wm_full = te_mod.project_multiemb.weight.detach().float()
+        w_comp16 = K.cast_bf16((wm_full[:, :Dm] @ te_mod.project_emb.weight.detach().float()).contiguous())        # [D, F * 128]
+        b_comp = (wm_full[:, :Dm] @ bp.float()).contiguous()                                                          # [D]
         P2 = torch.empty((B, T, Dm), dtype=F32, device=dev)
         C2 = torch.empty((B, T, Dm), dtype=F32, device=dev)
         cb = max(1, min(B, 32768 // max(T, 1)))
@@ -201,7 +206,7 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
             b1 = min(B, b0 + cb)
             x2, _, _ = K.embed_ln_fwd(masked_perf[b0:b1].reshape(-1, F).contiguous(), table, sizes, ln_w, ln_b)
             x2p = K.gemm(x2, wp16, bias=bp, out_dtype=BF16)
-            K.gemm(x2p, wm_r, bias=bm, out=P2[b0:b1].view(-1, Dm))
+            K.gemm(x2p, wm_r, bias=bm + b_comp, out=P2[b0:b1].view(-1, Dm))
             K.gemm(ctx16[b0:b1].reshape(-1, ctx16.shape[-1]), wc_r, bias=bc, out=C2[b0:b1].view(-1, Dm))
             del x2, x2p
         feed_c = feed.contiguous()
@@ -215,8 +220,7 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
         # one launch reads what this step needs at the device-side position: tuple i, and the prepared terms / style of note i+1
         K.gather_at_pos([feed_c, P2, C2, style_f], [tok_buf, p2_buf, c2_buf, st_buf], [0, 1, 1, 1], pos_t)
         x1, _, _ = K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b)
-        x1p = K.gemm(x1, wp16, bias=bp, out_dtype=BF16)
-        te = K.gemm(x1p, wm_l, residual=p2_buf, out_dtype=F32)
+        te = K.gemm(x1, w_comp16, residual=p2_buf, out_dtype=F32)
         K.layer_norm_fwd(te, en_w, en_b, out=ln_buf, need_stats=False)
         x = K.gemm(ln_buf, wc_l, residual=c2_buf, out_dtype=F32)
         plan.step(x, st_buf, km, pos_t)
