@@ -76,8 +76,8 @@ int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_row
 /* One new position of B scores through a whole AdaLN decoder stack in ONE persistent kernel (cache path of
  * modules/transformer/transformer.py:161-186,219-221; attention.py:139-197; feedforward.py:13-64; layers.py:31-47): phases separated
  * by a grid barrier, weights streamed from L2 once per step, the KV cache appended and read in place.  ptrs = HOST array of device
- * pointers, 7 per layer: wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048], w2 bf16
- * [256,1024], kv cache bf16 [B, cap, 128].  w_ada / b_ada: (gamma-1 | beta) rows of the 2*depth+1 AdaLN linears.  pos_dev: device
+ * pointers, 9 per layer: wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048], w2 bf16
+ * [256,1024], kv cache bf16 [B, cap, 128], wqkv^T bf16 [256,384], wo^T bf16 [256,256] (the per-row products stream the transposes).  w_ada / b_ada: (gamma-1 | beta) rows of the 2*depth+1 AdaLN linears.  pos_dev: device
  * int64 position.  Scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; barrier uint32.
  * hid_out fp32 [depth, B, 256] (may be NULL) = inputs of the attention layers; out fp32 [B,256]; out_bf16 (may be NULL) its bf16 copy.
  * dim 256, 4 heads x 64, hidden 1024. */

@@ -36,7 +36,9 @@ struct DecodeStackParams {
     const __nv_bfloat16* w_ada;                  // [(2*depth+1) * 512, S]
     const float* b_ada;                          // [(2*depth+1) * 512]  (gamma - 1 | beta)
     const __nv_bfloat16* wqkv[DS_MAX_DEPTH];     // [384, 256]
-    const __nv_bfloat16* wo[DS_MAX_DEPTH];       // [256, 256]
+    const __nv_bfloat16* wo[DS_MAX_DEPTH];
+    const __nv_bfloat16* wqkv_t[DS_MAX_DEPTH];   // [256, 384]: Wqkv transposed (input-major), for the per-row matrix-vector products
+    const __nv_bfloat16* wo_t[DS_MAX_DEPTH];     // [256, 256]: Wo transposed       // [256, 256]
     const float* logslopes[DS_MAX_DEPTH];        // [4]
     const __nv_bfloat16* w1[DS_MAX_DEPTH];       // [2048, 256] value rows | gate rows
     const float* b1[DS_MAX_DEPTH];               // [2048]
@@ -211,32 +213,11 @@ decode_stack_kernel(DecodeStackParams p) {
     grid_barrier(p.barrier, epoch);
 
     for (int l = 0; l < p.depth; ++l) {
-        // ---- A: qkv = AdaLN(x) Wqkv^T  (and the cache contract's copy of the layer input)
-        if (p.hid_out != nullptr)
-            for (int i = blockIdx.x * DS_THREADS + threadIdx.x; i < B * DS_D / 4; i += gridDim.x * DS_THREADS)
-                reinterpret_cast<float4*>(p.hid_out + (size_t)l * B * DS_D)[i] = reinterpret_cast<const float4*>(p.xres)[i];
-        {
-            const int col_blocks = DS_QKV / DS_TN;
-            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
-                const int rb = t / col_blocks, cb = t - rb * col_blocks;
-                uint32_t bf[32];
-                load_w<16>(bf, p.wqkv[l], DS_D, cb * DS_TN + (warp >> 1) * 8, lane);
-                __syncthreads();
-                stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l, rb * DS_TM, B, p.eps, warp, lane);
-                __syncthreads();
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
-                const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
-                    if (row < B) *reinterpret_cast<uint32_t*>(p.qkv + (size_t)row * DS_QKV + col) = pack_bf16x2(acc[2 * hf], acc[2 * hf + 1]);
-                }
-            }
-        }
-        grid_barrier(p.barrier, epoch);
-
-        // ---- B: append k|v, attention of the new query over the cache.  Two scores per CTA at a time (warps 0-3 / 4-7).  MQA: the
+        // ---- A + B + C for two scores per CTA at a time (warps 0-3 / 4-7), no grid barrier in between: everything here is local to
+        // a score's row.  A: AdaLN of the residual row and qkv = xn Wqkv^T as a matrix-vector product per row (thread = two output
+        // columns, transposed weights streamed from L2, coalesced); B: append k|v, attention of the new query over the cache;
+        // C: x += mask * (o Wo^T), again per row.  (A 32-row tensor-core tile would share the weights between rows, but costs two
+        // more grid barriers and two more latency-bound tile phases per layer: 5 -> 3 phases.)  MQA: the
         // four heads share K and V, so the four warps of a score split the KEYS and each evaluates all four heads on its quarter
         // -- every cache row is fetched once, and a warp walks a quarter of the sequential load -> use -> load chain.
         {
@@ -245,6 +226,10 @@ decode_stack_kernel(DecodeStackParams p) {
             float* sS = sP;                                                   // [2 scores][4 heads][cap] scores / numerators
             float* sRed = sP + (size_t)(DS_THREADS / 32) * p.cap;             // [2][4 warps][4 heads] maxima, then [2][4][4] sums
             float* sO = sRed + 64;                                            // [2][4 warps][4 heads][64] partial outputs
+            float* sXn = sO + 2 * 4 * 4 * 64;                                 // [2][256] AdaLN'd rows (bf16-rounded)
+            float* sOrow = sXn + 2 * DS_D;                                    // [2][256] attention outputs (bf16-rounded)
+            uint32_t* sQKV = reinterpret_cast<uint32_t*>(sOrow + 2 * DS_D);   // [2][192] qkv rows, bf16 pairs
+            float* sPart = reinterpret_cast<float*>(sQKV + 2 * (DS_QKV / 2));   // [8][2][256] (or [5][2][384]) k-split partial sums
             constexpr int UNR = 8;
             const int bl = warp >> 2, wq = warp & 3;
             const int grp = lane >> 3, sub = lane & 7;
@@ -253,12 +238,83 @@ decode_stack_kernel(DecodeStackParams p) {
             for (int pair = blockIdx.x; pair * 2 < B; pair += gridDim.x) {
                 const int b = pair * 2 + bl;
                 const bool live = b < B;
+                __syncthreads();                                      // the previous pair's rows in shared memory are done with
+                if (wq == 0) {                                        // warps 0 and 4: AdaLN of one residual row each
+                    float* xn = sXn + bl * DS_D + lane * 8;
+                    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (live) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(p.xres + (size_t)b * DS_D + lane * 8);
+                        const float4 v1 = *reinterpret_cast<const float4*>(p.xres + (size_t)b * DS_D + lane * 8 + 4);
+                        if (p.hid_out != nullptr) {                   // the cache contract's copy of the layer input
+                            float* ho = p.hid_out + ((size_t)l * B + b) * DS_D + lane * 8;
+                            *reinterpret_cast<float4*>(ho) = v0;
+                            *reinterpret_cast<float4*>(ho + 4) = v1;
+                        }
+                        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        float s_ = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s_ += v[j];
+                        const float mean = warp_sum(s_) * (1.f / DS_D);
+                        float q_ = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { v[j] -= mean; q_ += v[j] * v[j]; }
+                        const float rstd = rsqrtf(warp_sum(q_) * (1.f / DS_D) + p.eps);
+                        const __nv_bfloat16* gr = p.gb + (size_t)b * ld_gb + (2 * l) * 2 * DS_D + lane * 8;
+                        const uint4 gu = *reinterpret_cast<const uint4*>(gr), bu = *reinterpret_cast<const uint4*>(gr + DS_D);
+                        const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z), g3 = unpack_bf16x2(gu.w);
+                        const float2 b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y), b2 = unpack_bf16x2(bu.z), b3 = unpack_bf16x2(bu.w);
+                        const float gm[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y}, bt[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[j] = __bfloat162float(__float2bfloat16_rn(v[j] * rstd * (1.f + gm[j]) + bt[j]));
+                    }
+                    *reinterpret_cast<float4*>(xn) = make_float4(y[0], y[1], y[2], y[3]);
+                    *reinterpret_cast<float4*>(xn + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                }
                 __syncthreads();
+                // qkv of both rows: thread = 8 adjacent output columns x one fifth of k (16-byte weight loads, all of a thread's
+                // loads in flight together); the five partial sums meet in shared memory and are added in a fixed order
+                if (threadIdx.x < 5 * (DS_QKV / 8)) {
+                    const int kg = threadIdx.x / (DS_QKV / 8), cg = threadIdx.x - kg * (DS_QKV / 8);
+                    const int k_lo2 = kg * 52, k_hi2 = min(DS_D, k_lo2 + 52);
+                    const __nv_bfloat16* wt = p.wqkv_t[l] + cg * 8;
+                    float a0[8], a1[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+#pragma unroll 13
+                    for (int k = k_lo2; k < k_hi2; ++k) {
+                        const uint4 w = __ldg(reinterpret_cast<const uint4*>(wt + (size_t)k * DS_QKV));
+                        const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y), w2 = unpack_bf16x2(w.z), w3 = unpack_bf16x2(w.w);
+                        const float wv[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+                        const float x0 = sXn[k], x1 = sXn[DS_D + k];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { a0[j] = fmaf(x0, wv[j], a0[j]); a1[j] = fmaf(x1, wv[j], a1[j]); }
+                    }
+                    float* pp = sPart + (size_t)kg * 2 * DS_QKV + cg * 8;
+                    *reinterpret_cast<float4*>(pp) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+                    *reinterpret_cast<float4*>(pp + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+                    *reinterpret_cast<float4*>(pp + DS_QKV) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                    *reinterpret_cast<float4*>(pp + DS_QKV + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+                }
+                __syncthreads();
+                if (threadIdx.x < DS_QKV / 2) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int kg = 0; kg < 5; ++kg) {
+                            const float2 v = *reinterpret_cast<const float2*>(sPart + (size_t)(kg * 2 + r) * DS_QKV + threadIdx.x * 2);
+                            s0 += v.x; s1 += v.y;
+                        }
+                        sQKV[r * (DS_QKV / 2) + threadIdx.x] = pack_bf16x2(s0, s1);
+                    }
+                }
+                __syncthreads();
+                const __nv_bfloat16* qrow = reinterpret_cast<const __nv_bfloat16*>(sQKV + bl * (DS_QKV / 2));
                 if (live) {
                     __nv_bfloat16* kvw = p.kv[l] + (size_t)b * p.cap * 128;
                     const int lw = threadIdx.x & 127;
                     if (lw < 16 && pos < p.cap)
-                        reinterpret_cast<uint4*>(kvw + (size_t)pos * 128)[lw] = reinterpret_cast<const uint4*>(p.qkv + (size_t)b * DS_QKV + DS_H * DS_DH)[lw];
+                        reinterpret_cast<uint4*>(kvw + (size_t)pos * 128)[lw] = reinterpret_cast<const uint4*>(qrow + DS_H * DS_DH)[lw];
                 }
                 __syncthreads();
                 const __nv_bfloat16* kvb = p.kv[l] + (size_t)(live ? b : 0) * p.cap * 128;
@@ -266,7 +322,7 @@ decode_stack_kernel(DecodeStackParams p) {
                 float qs[4][8];
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    const uint4 u = live ? *reinterpret_cast<const uint4*>(p.qkv + (size_t)b * DS_QKV + h * DS_DH + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 u = live ? *reinterpret_cast<const uint4*>(qrow + h * DS_DH + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
                     const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
                     qs[h][0] = a.x * scale; qs[h][1] = a.y * scale; qs[h][2] = b2.x * scale; qs[h][3] = b2.y * scale;
                     qs[h][4] = c2.x * scale; qs[h][5] = c2.y * scale; qs[h][6] = d.x * scale; qs[h][7] = d.y * scale;
@@ -397,37 +453,43 @@ decode_stack_kernel(DecodeStackParams p) {
                         r0 += sO[((size_t)(bl * 4 + w2) * 4 + h) * 64 + lane * 2];
                         r1 += sO[((size_t)(bl * 4 + w2) * 4 + h) * 64 + lane * 2 + 1];
                     }
-                    *reinterpret_cast<uint32_t*>(p.o + (size_t)b * DS_D + h * DS_DH + lane * 2) = pack_bf16x2(r0 * inv, r1 * inv);
+                    sOrow[bl * DS_D + h * DS_DH + lane * 2] = __bfloat162float(__float2bfloat16_rn(r0 * inv));
+                    sOrow[bl * DS_D + h * DS_DH + lane * 2 + 1] = __bfloat162float(__float2bfloat16_rn(r1 * inv));
+                } else {
+                    sOrow[bl * DS_D + wq * DS_DH + lane * 2] = 0.f;
+                    sOrow[bl * DS_D + wq * DS_DH + lane * 2 + 1] = 0.f;
                 }
-            }
-        }
-        grid_barrier(p.barrier, epoch);
-
-        // ---- C: x += mask[b, pos] * (o Wo^T)
-        {
-            const int col_blocks = DS_D / DS_TN;
-            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
-                const int rb = t / col_blocks, cb = t - rb * col_blocks;
-                uint32_t bf[32];
-                load_w<16>(bf, p.wo[l], DS_D, cb * DS_TN + (warp >> 1) * 8, lane);
                 __syncthreads();
-                stage_rows(sA, p.o, DS_D, 0, DS_D, rb * DS_TM, B);
-                __syncthreads();
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
-                const int col = cb * DS_TN + (warp >> 1) * 8 + tig * 2;
+                {                                                     // C: x += mask * (o Wo^T): thread = 8 columns x one eighth of k
+                    const int kg = threadIdx.x >> 5, cg = threadIdx.x & 31;
+                    const __nv_bfloat16* wt = p.wo_t[l] + cg * 8;
+                    float a0[8], a1[8];
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
-                    if (row < B) {
-                        const bool keep = p.key_mask == nullptr || pos >= p.cap || p.key_mask[(size_t)row * p.cap + pos];
-                        if (keep) {
-                            float2* xr = reinterpret_cast<float2*>(p.xres + (size_t)row * DS_D + col);
-                            float2 v = *xr;
-                            v.x += acc[2 * hf];
-                            v.y += acc[2 * hf + 1];
-                            *xr = v;
-                        }
+                    for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+#pragma unroll 16
+                    for (int k = kg * 32; k < kg * 32 + 32; ++k) {
+                        const uint4 w = __ldg(reinterpret_cast<const uint4*>(wt + (size_t)k * DS_D));
+                        const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y), w2 = unpack_bf16x2(w.z), w3 = unpack_bf16x2(w.w);
+                        const float wv[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+                        const float x0 = sOrow[k], x1 = sOrow[DS_D + k];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { a0[j] = fmaf(x0, wv[j], a0[j]); a1[j] = fmaf(x1, wv[j], a1[j]); }
+                    }
+                    float* pp = sPart + (size_t)kg * 2 * DS_D + cg * 8;
+                    *reinterpret_cast<float4*>(pp) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+                    *reinterpret_cast<float4*>(pp + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+                    *reinterpret_cast<float4*>(pp + DS_D) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                    *reinterpret_cast<float4*>(pp + DS_D + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+                    __syncthreads();
+                    const int c = threadIdx.x;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8) sum += sPart[(size_t)(k8 * 2 + r) * DS_D + c];
+                        const int row = pair * 2 + r;
+                        if (row < B && (p.key_mask == nullptr || pos >= p.cap || p.key_mask[(size_t)row * p.cap + pos]))
+                            p.xres[(size_t)row * DS_D + c] += sum;
                     }
                 }
             }
@@ -596,8 +658,8 @@ __global__ void __launch_bounds__(128) gather_at_pos_kernel(GatherParams g) {
 }  // namespace
 
 // One new position through an AdaLN decoder stack (see the header of this file).  `ptrs` is a HOST array of device pointers:
-// per layer l (7 entries at 7*l): wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048],
-// w2 bf16 [256,1024], kv cache bf16 [B, cap, 128].  w_ada bf16 [(2*depth+1)*512, S] / b_ada fp32 hold (gamma-1 | beta) rows per
+// per layer l (9 entries at 9*l): wqkv bf16 [384,256], wo bf16 [256,256], logslopes fp32 [4], w1 bf16 [2048,256], b1 fp32 [2048],
+// w2 bf16 [256,1024], kv cache bf16 [B, cap, 128], wqkv^T bf16 [256,384], wo^T bf16 [256,256].  w_ada bf16 [(2*depth+1)*512, S] / b_ada fp32 hold (gamma-1 | beta) rows per
 // norm.  scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; `barrier` one uint32.
 // hid_out (fp32 [depth, B, 256], may be NULL) receives the inputs of the attention layers (the reference's cache contract);
 // out_bf16 (bf16 [B, 256], may be NULL) a bf16 copy of `out`.
@@ -616,20 +678,23 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     p.x_in = x_in; p.style = style;
     p.w_ada = reinterpret_cast<const __nv_bfloat16*>(w_ada); p.b_ada = b_ada;
     for (int l = 0; l < depth; ++l) {
-        p.wqkv[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l]);
-        p.wo[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l + 1]);
-        p.logslopes[l] = reinterpret_cast<const float*>(ptrs[7 * l + 2]);
-        p.w1[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l + 3]);
-        p.b1[l] = reinterpret_cast<const float*>(ptrs[7 * l + 4]);
-        p.w2[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[7 * l + 5]);
-        p.kv[l] = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ptrs[7 * l + 6]));
-        SPB_CHECK_ARG(p.wqkv[l] && p.wo[l] && p.logslopes[l] && p.w1[l] && p.b1[l] && p.w2[l] && p.kv[l], "spb_decode_stack_step: null layer pointer");
+        p.wqkv[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[9 * l]);
+        p.wo[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[9 * l + 1]);
+        p.logslopes[l] = reinterpret_cast<const float*>(ptrs[9 * l + 2]);
+        p.w1[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[9 * l + 3]);
+        p.b1[l] = reinterpret_cast<const float*>(ptrs[9 * l + 4]);
+        p.w2[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[9 * l + 5]);
+        p.kv[l] = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ptrs[9 * l + 6]));
+        p.wqkv_t[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[9 * l + 7]);
+        p.wo_t[l] = reinterpret_cast<const __nv_bfloat16*>(ptrs[9 * l + 8]);
+        SPB_CHECK_ARG(p.wqkv[l] && p.wo[l] && p.logslopes[l] && p.w1[l] && p.b1[l] && p.w2[l] && p.kv[l] && p.wqkv_t[l] && p.wo_t[l],
+                      "spb_decode_stack_step: null layer pointer");
     }
     p.key_mask = key_mask; p.pos_dev = pos_dev;
     p.gb = reinterpret_cast<__nv_bfloat16*>(gb); p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv);
     p.o = reinterpret_cast<__nv_bfloat16*>(o); p.hmid = reinterpret_cast<__nv_bfloat16*>(hmid);
     p.xres = xres; p.hid_out = hid_out; p.out = out; p.out16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.barrier = barrier; p.eps = eps;
-    int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4;
+    int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4 + (2 * DS_D + 2 * DS_D) * 4 + 2 * (DS_QKV / 2) * 4 + 8 * 2 * DS_D * 4;
     const int smem_e = 4 * DS_TM * DS_LDA * 2 + 4 * 2 * 2 * 32 * 16;        // phase E: four K quarters of the rows + the reduction scratch
     if (smem < smem_e) smem = smem_e;
     SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -161,9 +161,12 @@ class DecodeStackPlan:
         self.w_ada, self.b_ada = w_ada, b_ada
         self._keep = [layers, kv_caches]                       # keep the tensors alive as long as the pointers are used
         ptrs = []
+        self._transposed = []
         for w, kv in zip(layers, kv_caches):
             assert kv.dtype == BF16 and kv.is_contiguous() and kv.shape == (B, self.cap, 128)
-            for t in (w["wqkv"], w["wo"], w["ls"], w["w1"], w["b1"], w["w2"], kv):
+            wqkv_t, wo_t = w["wqkv"].t().contiguous(), w["wo"].t().contiguous()      # input-major copies for the per-row products
+            self._transposed += [wqkv_t, wo_t]
+            for t in (w["wqkv"], w["wo"], w["ls"], w["w1"], w["b1"], w["w2"], kv, wqkv_t, wo_t):
                 assert t.is_contiguous()
                 ptrs.append(t.data_ptr())
         self.ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
