@@ -95,3 +95,23 @@ class SyntheticTokenizer:
             vals[4:] = (np.arange(v - 4, dtype=np.float32) - 0.25 * v) * (0.5 + 0.125 * i)
             out[key] = vals / np.abs(vals).max() if normalize else vals
         return out
+
+
+class SyntheticDataset(torch.utils.data.Dataset):
+    """`n` synthetic note-tuple sequences of `seq_len` notes, one sample = one row of `make_batch` (the fields of
+    ScorePerformer.forward).  Stands in for ScorePerformanceDataset where no corpus is available (benchmarks, trainer tests)."""
+
+    def __init__(self, n: int, seq_len: int, seed: int = 1234, **kwargs):
+        self.rows = make_batch(n, seq_len, seed=seed, **kwargs)
+        self.n = n
+
+    def __len__(self) -> int:
+        return self.n
+
+    def __getitem__(self, i: int) -> Dict[str, torch.Tensor]:
+        return {k: v[i] for k, v in self.rows.items()}
+
+
+def collate_rows(samples) -> Dict[str, torch.Tensor]:
+    """Collator of SyntheticDataset: stacks the per-sample fields (all sequences have one length)."""
+    return {k: torch.stack([s[k] for s in samples]) for k in samples[0]}

@@ -187,3 +187,26 @@ def test_mixlm_masking_statement_matches_reference_collator():
     bad["perf_mask"][0, 3] = False                       # a hole: not a prefix mask
     with pytest.raises(ValueError):
         pack_batch(bad, pin=False)
+
+
+def test_trainer_sampler_shards_an_epoch():
+    """f4 host logic: with N ranks every rank draws a disjoint shard of the epoch's permutation (experiments/trainer.py:166-174 gets
+    a DistributedSampler), reshuffled by set_epoch, and the step count per epoch follows drop_last on both levels."""
+    from scoreperformer_b200.synthetic import SyntheticDataset, collate_rows
+    from scoreperformer_b200.trainer import make_sampler, steps_per_epoch
+    data = SyntheticDataset(37, 16, seed=1)
+    assert make_sampler(data, 1, 0, True, 0) is None
+    shards = []
+    for rank in range(4):
+        s = make_sampler(data, 4, rank, True, 5)
+        s.set_epoch(0)
+        e0 = list(iter(s))
+        s.set_epoch(1)
+        assert list(iter(s)) != e0 and len(e0) == 37 // 4
+        shards.append(e0)
+    flat = [i for sh in shards for i in sh]
+    assert len(set(flat)) == len(flat) == 36
+    assert steps_per_epoch(37, 4, 4) == 2 and steps_per_epoch(24, 4) == 6
+    batch = collate_rows([data[i] for i in shards[0][:3]])
+    assert batch["perf"].shape[0] == 3 and set(batch) == set(data[0])
+
