@@ -700,6 +700,67 @@ class TiedHeadCEFn(torch.autograd.Function):
         return dh, dproj, None if d1 else dln_w, None if d2 else dln_b, dtable, None, None, None, None, None, None
 
 
+class UntiedHeadCEFn(torch.autograd.Function):
+    """Per-field `nn.Linear(dim, V_f)` heads + masked cross-entropy, mean over the fields that carry labels
+    (models/scoreperformer/embeddings.py:287-313 `lm` head, wrappers.py:45-59): the variant of recipes/.../ablation/no_io_tie.yaml.
+
+    hidden [n, dim] fp32 / bf16; labels int64 [n, F]; fields = indices into the label columns, params = (weight [V_f, dim],
+    bias [V_f]) per listed field.  Returns (loss, per-field losses [len(fields)], counts).  One GEMM + one CE-rows kernel per field
+    (logits live for one field at a time); backward: dW_f = c_f dlogits^T h, db_f = c_f colsum(dlogits), dh = sum_f c_f dlogits W_f."""
+
+    @staticmethod
+    def forward(ctx, hidden, labels, ignore_index: int, fields: Tuple[int, ...], *params):
+        dev = hidden.device
+        n = hidden.shape[0]
+        h16 = K.cast_bf16(hidden.contiguous()) if hidden.dtype == F32 else hidden.contiguous()
+        nf = len(fields)
+        acc = torch.zeros((2, nf), dtype=F32, device=dev)
+        loss_sum, count = acc[0], acc[1]
+        need_grad = any(ctx.needs_input_grad)
+        dlogits, w16s = [], []
+        for i, f in enumerate(fields):
+            W, b = params[2 * i], params[2 * i + 1]
+            V = W.shape[0]
+            w_16 = w16(W)
+            logits = K.gemm(h16, w_16, bias=b.detach().float().contiguous(), out_dtype=F32)                 # [n, V]
+            dl = torch.empty((n, (V + 7) // 8 * 8), dtype=BF16, device=dev) if need_grad else None
+            K.ce_rows(logits, labels[:, f], V, loss_sum[i:i + 1], count[i:i + 1], dl, None, ignore_index)
+            dlogits.append(dl)
+            w16s.append(w_16)
+        active = count > 0
+        per_field = loss_sum / count.clamp(min=1.0)
+        n_active = active.sum().clamp(min=1)
+        loss = (per_field * active).sum() / n_active
+        ctx.saved = (h16, dlogits, w16s, count, active, n_active)
+        ctx.params, ctx.h_dtype = params, hidden.dtype
+        ctx.mark_non_differentiable(per_field, count)
+        return loss, per_field, count
+
+    @staticmethod
+    def backward(ctx, g, _g1, _g2):
+        h16, dlogits, w16s, count, active, n_active = ctx.saved
+        params = ctx.params
+        coef = (g * active.float() / (count.clamp(min=1.0) * n_active)).contiguous()
+        dh = torch.zeros((h16.shape[0], h16.shape[1]), dtype=F32, device=h16.device)
+        grads = []
+        for i, dl in enumerate(dlogits):
+            W, b = params[2 * i], params[2 * i + 1]
+            V = W.shape[0]
+            a = dl[:, :V] if dl.shape[1] != V else dl
+            grads.append(wgrad(W, a, h16, alpha=coef[i:i + 1]))                                             # [V, dim]
+            db, direct = vgrad(b)
+            cs = K.colsum(a) * coef[i]
+            if direct:
+                db.add_(cs)
+                grads.append(None)
+            else:
+                grads.append(cs)
+            K.gemm(a, w16s[i], trans_b=True, out=dh, accumulate=True, alpha=coef[i:i + 1])                 # dh += c dlogits W
+        if ctx.h_dtype != F32:
+            dh = dh.to(ctx.h_dtype)
+        return (dh, None, None, None) + tuple(grads)
+
+
 def tied_head_logits(hidden: Tensor, proj_w: Tensor, ln_w: Tensor, ln_b: Tensor, table: Tensor, sizes: Sequence[int],
                      fields: Sequence[int], emb: int) -> List[Tensor]:
     """Inference-side logits (fp32 [n, V_f] per requested field); no autograd."""

@@ -17,7 +17,7 @@ from torch import Tensor
 from ... import fused
 from ...modules.sampling import top_k
 from ...utils import ExplicitEnum, exists
-from .embeddings import TupleTokenTiedLMHead
+from .embeddings import TupleTokenLMHead, TupleTokenTiedLMHead
 from .transformer import TupleTransformer, TupleTransformerCaches, TupleTransformerOutput
 
 
@@ -107,12 +107,25 @@ class ScorePerformerLMWrapper(LMWrapper):
         head = self.model.lm_head
         fused_head = isinstance(head, TupleTokenTiedLMHead) and self.model.regression_head is None and exists(labels)
         if not fused_head:
+            if exists(labels) and isinstance(head, TupleTokenLMHead) and self.model.regression_head is None:
+                # untied `lm` head (ablation recipe no_io_tie): one GEMM + one masked-CE kernel per labelled field, the logits of a
+                # field live only between the two (wrappers.py:45-59 of the reference)
+                kwargs.pop("return_embeddings", None)
+                out = self.model(seq, return_embeddings=True, **kwargs)
+                hidden = out.hidden_state
+                b, t, d = hidden.shape
+                names = list(head.heads.keys())
+                fields = self._probe_label_fields(labels)
+                params = [p for f in fields for p in (head.heads[names[f]].weight, head.heads[names[f]].bias)]
+                loss, per_field, _ = fused.UntiedHeadCEFn.apply(hidden.reshape(b * t, d), labels.reshape(b * t, -1).contiguous(),
+                                                                self.ignore_index, tuple(fields), *params)
+                out.logits = LazyLogits(names, lambda: head(hidden.detach()))
+                return ScorePerformerLMOutput(loss=loss, losses={names[f]: per_field[i] for i, f in enumerate(fields)}, **out.__dict__)
             out = self.model(seq, **kwargs)
             loss = losses = None
             if exists(labels):
-                # generic (untied `lm` head) path: logits come from the head, CE per field through the fused CE kernel
-                raise NotImplementedError("training with an untied `lm` head / regression head is not implemented on the sm_100a "
-                                          "path yet (ablation recipes no_io_tie); see DESIGN.md")
+                raise NotImplementedError("training with a regression head is not implemented on the sm_100a path (no recipe of the "
+                                          "reference uses it); see DESIGN.md")
             return ScorePerformerLMOutput(loss=loss, losses=losses, **out.__dict__)
 
         table_cache = kwargs.get("table_cache")
