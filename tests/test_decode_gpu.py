@@ -154,3 +154,60 @@ def test_unmask_tokens_adapter_runs_the_batched_renderer(setup):
     got_p = model.perf_decoder.unmask_tokens(tokens_in[:, :9], b["masked_perf"][:, :9], filter_logits_fn=top_p, filter_kwargs={"thres": 0.5},
                                              disable_tqdm=True, context=enc.score_embeddings[:, :9], style_embeddings=enc.perf_embeddings[:, :9])
     assert int((got_p == 1).sum()) == int((tokens_in[:, 0] == 1).sum()) and got_p.shape == tokens_in[:, :9].shape
+
+
+def _cut_caches(caches, left_idx=0, right_idx=None):
+    """What ScorePerformerGenerator.cut_caches does to the caches it hands back (inference/generators.py:428-443): every cached
+    tensor is sliced along the note axis."""
+    from scoreperformer_b200.modules.transformer import AttentionIntermediates, TransformerIntermediates
+    right_idx = caches.token_emb.shape[1] if right_idx is None else right_idx
+    caches.token_emb = caches.token_emb[:, left_idx:right_idx]
+    caches.transformer = TransformerIntermediates(
+        hiddens=[t[..., left_idx:right_idx, :] for t in caches.transformer.hiddens],
+        attention=[AttentionIntermediates(inter.keys[..., left_idx:right_idx, :], inter.values[..., left_idx:right_idx, :], None)
+                   for inter in caches.transformer.attention])
+    return caches
+
+
+def test_generator_loop_with_cache_slicing(setup):
+    """f3, the device side of inference/generators.py:106-295: notes arrive in groups (chord grouping), every `unmask_tokens` call
+    continues from the caches the previous one returned, and a time-window cut throws the last generated note away and slices the
+    caches (`cut_caches`).  Greedy decoding: the loop with cuts must produce exactly what the loop without cuts produces (slicing
+    the caches changes nothing), and agree with the one-shot batched rendering up to near-ties."""
+    g, model, batch = setup
+    from scoreperformer_b200.decode import render_batch
+    from scoreperformer_b200.modules.sampling import top_k
+    b, enc = _encoders(model, batch)
+    tokens_in = torch.from_numpy(g["tokens_in"]).cuda()
+    masked = b["masked_perf"]
+    T = tokens_in.shape[1]
+
+    def loop(cut_every):
+        seq = tokens_in[:, :1].clone()
+        caches, cur, it = None, 1, 0
+        while cur < T:
+            group = min(3, T - cur)
+            new = tokens_in[:, cur:cur + group]                       # masked tuples of the next notes
+            inp = torch.cat([seq, new], dim=1)
+            L = inp.shape[1]
+            if caches is not None:                                    # the generator's own consistency check (:212-216)
+                assert L - 1 - group == caches.token_emb.shape[1]
+            out, caches = model.perf_decoder.unmask_tokens(inp, masked[:, :L], filter_logits_fn=top_k, filter_kwargs={"k": 1},
+                                                           caches=caches, return_caches=True, disable_tqdm=True,
+                                                           context=enc.score_embeddings[:, :L], style_embeddings=enc.perf_embeddings[:, :L])
+            assert caches.token_emb.shape[1] == L - 1
+            keep = group
+            it += 1
+            if cut_every and it % cut_every == 0 and group > 1:       # the last note fell outside the time window
+                keep = group - 1
+                caches = _cut_caches(caches, right_idx=caches.token_emb.shape[1] - 1)
+            seq = torch.cat([seq, out[:, cur:cur + keep]], dim=1)
+            cur += keep
+        return seq
+
+    plain, cut = loop(0), loop(2)
+    assert plain.shape == cut.shape == tokens_in.shape
+    assert torch.equal(plain, cut)
+    want = render_batch(model, tokens_in, masked, enc.score_embeddings, enc.perf_embeddings)
+    assert float((plain == want).float().mean()) > 0.95
+
