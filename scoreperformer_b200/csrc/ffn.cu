@@ -530,17 +530,14 @@ ffn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     SPB_MBAR_WAIT(&h_wr[b], ph);
                     mbar_arrive_cluster(h_full_l[b]);
                     if (save) {
-                        // the stores of the PREVIOUS chunk have had a whole chunk to read their tiles: release those now
-                        if (g > 0) {
-                            bulk_wait_group_read<0>();
-                            mbar_arrive(&st_empty[b ^ 1]);
-                        }
                         if (m0 < p.n_rows) {
                             tma_store_2d(&tmU, smem + P_SU_OFF + b * 32768, c * CH, m0);
                             tma_store_2d(&tmU, smem + P_SU_OFF + b * 32768 + 16384, HID + c * CH, m0);
                             tma_store_2d(&tmH, smem + P_SH_OFF + b * 16384, c * CH, m0);
                             bulk_commit_group();
+                            bulk_wait_group_read<0>();         // ~0.5 us: the tiles are handed back a whole chunk before they are needed
                         }
+                        mbar_arrive(&st_empty[b]);
                     }
                 }
             }
