@@ -648,3 +648,31 @@ def test_sample_fields_greedy_and_topk(k):
             want = torch.softmax(val / temp, -1)
             got = torch.stack([(drawn == i).float().mean() for i in ind])
             assert float((got - want).abs().max()) < 0.04, (f, got.tolist(), want.tolist())
+
+
+# ------------------------------------------------------------------ multi-buffer helpers
+def test_multi_add_copy_gather(k):
+    """spb_multi_add_f32 / spb_multi_copy / spb_gather_at_pos: many small adds / copies / position gathers in one launch each."""
+    torch.manual_seed(1)
+    sizes = [5, 512 * 64, 512, 7 * 13, 100003] + [33] * 60           # more pairs than one launch holds (48)
+    dst = [randn(n) for n in sizes]
+    src = [randn(n) for n in sizes]
+    want = [d + s_ for d, s_ in zip(dst, src)]
+    k.multi_add(dst, src)
+    assert all(torch.equal(a, b) for a, b in zip(dst, want))
+    # copies: mixed dtypes, odd byte counts, an unaligned view
+    base = torch.arange(1000, device="cuda", dtype=torch.uint8)
+    srcs = [torch.randint(0, 1000, (64, 512, 12), device="cuda"), torch.rand(7, device="cuda") > 0.5, randn(33, 3, dtype=BF16), base[3:990]]
+    dsts = [torch.zeros_like(t) for t in srcs[:3]] + [torch.zeros(987, device="cuda", dtype=torch.uint8)]
+    k.multi_copy(dsts, srcs)
+    assert all(torch.equal(a, b) for a, b in zip(dsts, srcs))
+    # gather at a device-side position, with shifts and clamping at the sequence end
+    B, T = 5, 9
+    a, b_, c = torch.randint(0, 99, (B, T, 12), device="cuda"), randn(B, T, 256), randn(B, T, 64)
+    oa, ob, oc = torch.empty((B, 12), dtype=a.dtype, device="cuda"), torch.empty((B, 256), device="cuda"), torch.empty((B, 64), device="cuda")
+    for pos in (0, 3, T - 1):
+        pos_t = torch.tensor([pos], device="cuda")
+        k.gather_at_pos([a, b_, c], [oa, ob, oc], [0, 1, 1], pos_t)
+        nxt = min(pos + 1, T - 1)
+        assert torch.equal(oa, a[:, pos]) and torch.equal(ob, b_[:, nxt]) and torch.equal(oc, c[:, nxt])
+
