@@ -10,11 +10,11 @@
 // from L2 once per step over the whole chip, the KV cache is read once -- and the phases are separated by a grid barrier
 // (one atomic counter; all CTAs are co-resident: grid <= #SMs, one CTA per SM):
 //   phase 0        gb = style W_ada^T + b          (gamma-1 | beta) of all 2*depth+1 AdaLNs, bf16 scratch
-//   per layer  A   qkv  = AdaLN(x) Wqkv^T                                 32x32 tiles, mma.sync m16n8k16 (M is tiny: tcgen05's
-//              B   cache[pos] = k|v ;  o = softmax(q K^T s - slope|i-j|) V   128-row tiles would idle 3/4 of the tensor core)
-//              C   x   += mask * (o Wo^T)
-//              D   h    = GLU(AdaLN(x) W1^T + b1)
-//              E   x   += h W2^T                     split-K x4, fp32 atomics into the residual stream
+//                                                 (skipped when the caller prepared the terms of all positions: gb_all)
+//   per layer  ABC per score (two per CTA), no barrier in between: qkv = AdaLN(x) Wqkv^T as a per-row product over the
+//                  transposed weights; cache[pos] = k|v; o = softmax(q K^T s - slope|i-j|) V; x += mask * (o Wo^T)
+//              D   h    = GLU(AdaLN(x) W1^T + b1)     32x16 tiles, mma.sync m16n8k16 (M is tiny: tcgen05's 128-row tiles would
+//              E   x   += h W2^T                       idle 3/4 of the tensor core); K split inside the CTA, fixed summation order
 //   final          out  = AdaLN(x)
 // Algorithmic HBM/L2 bytes per note-step: B * pos * 4 layers * 256 B of KV cache (the roofline term) + 7.6 MB of
 // weights out of L2.
@@ -57,6 +57,8 @@ struct DecodeStackParams {
     __nv_bfloat16* out16;                        // optional bf16 copy of `out` (operand of the head projection), or null
     unsigned* barrier;                           // zeroed by the host before the launch
     float eps;
+    const __nv_bfloat16* gb_all;                 // optional [B, T_all, (2*depth+1)*512]: the AdaLN terms of every position, prepared ahead
+    int T_all;
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
@@ -128,7 +130,7 @@ __device__ __forceinline__ void mma_pre(float (&acc)[4], const __nv_bfloat16* sA
 }
 
 // AdaLN of 32 rows of the fp32 residual stream -> bf16 smem tile [32][DS_LDA]; one warp per 4 rows (rows beyond B are zeroed)
-__device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres, const __nv_bfloat16* gb, int ld_gb, int norm_idx, int row0,
+__device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres, const __nv_bfloat16* gb, size_t ld_gb, int norm_idx, int row0,
                                             int B, float eps, int warp, int lane) {
     for (int rr = warp; rr < DS_TM; rr += DS_THREADS / 32) {
         const int row = row0 + rr;
@@ -183,11 +185,20 @@ decode_stack_kernel(DecodeStackParams p) {
     const int row_blocks = (B + DS_TM - 1) / DS_TM;
     const int pos = (int)*p.pos_dev;
     unsigned epoch = 0;
+    // the AdaLN terms of this step: computed here (phase 0) from the style rows, or -- when the caller prepared them for all positions
+    // in one large GEMM -- read in place at position pos + 1 (the style a note-step uses is that of the note it predicts)
+    const __nv_bfloat16* gbp = p.gb;
+    size_t gb_stride = (size_t)ld_gb;
+    if (p.gb_all != nullptr) {
+        const int t_style = min(pos + 1, p.T_all - 1);
+        gbp = p.gb_all + (size_t)t_style * ld_gb;
+        gb_stride = (size_t)p.T_all * ld_gb;
+    }
 
     // ---- phase 0: gb = style W_ada^T + b_ada for every norm; the residual stream starts as the input
     {
         const int col_blocks = ld_gb / DS_TN;
-        for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+        for (int t = blockIdx.x; t < row_blocks * col_blocks && p.gb_all == nullptr; t += gridDim.x) {
             const int rb = t / col_blocks, cb = t - rb * col_blocks;
             __syncthreads();
             for (int i = threadIdx.x; i < DS_TM * p.S; i += DS_THREADS) {        // style rows -> bf16 tile (S <= 256)
@@ -259,7 +270,7 @@ decode_stack_kernel(DecodeStackParams p) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { v[j] -= mean; q_ += v[j] * v[j]; }
                         const float rstd = rsqrtf(warp_sum(q_) * (1.f / DS_D) + p.eps);
-                        const __nv_bfloat16* gr = p.gb + (size_t)b * ld_gb + (2 * l) * 2 * DS_D + lane * 8;
+                        const __nv_bfloat16* gr = gbp + (size_t)b * gb_stride + (2 * l) * 2 * DS_D + lane * 8;
                         const uint4 gu = *reinterpret_cast<const uint4*>(gr), bu = *reinterpret_cast<const uint4*>(gr + DS_D);
                         const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z), g3 = unpack_bf16x2(gu.w);
                         const float2 b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y), b2 = unpack_bf16x2(bu.z), b3 = unpack_bf16x2(bu.w);
@@ -512,7 +523,7 @@ decode_stack_kernel(DecodeStackParams p) {
                 load_w<16>(bf, p.w1[l], DS_D, wrow0, lane);
                 if (rb != staged_rb) {
                     __syncthreads();
-                    stage_adaln(sA, p.xres, p.gb, ld_gb, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
+                    stage_adaln(sA, p.xres, gbp, gb_stride, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
                     staged_rb = rb;
                 }
                 __syncthreads();
@@ -613,7 +624,7 @@ decode_stack_kernel(DecodeStackParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { v[j] -= mean; q += v[j] * v[j]; }
         const float rstd = rsqrtf(warp_sum(q) * (1.f / DS_D) + p.eps);
-        const __nv_bfloat16* gr = p.gb + (size_t)row * ld_gb + (2 * p.depth) * 2 * DS_D + lane * 8;
+        const __nv_bfloat16* gr = gbp + (size_t)row * gb_stride + (2 * p.depth) * 2 * DS_D + lane * 8;
         const uint4 gu = *reinterpret_cast<const uint4*>(gr), bu = *reinterpret_cast<const uint4*>(gr + DS_D);
         const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z), g3 = unpack_bf16x2(gu.w);
         const float2 b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y), b2 = unpack_bf16x2(bu.z), b3 = unpack_bf16x2(bu.w);
@@ -662,11 +673,13 @@ __global__ void __launch_bounds__(128) gather_at_pos_kernel(GatherParams g) {
 // w2 bf16 [256,1024], kv cache bf16 [B, cap, 128], wqkv^T bf16 [256,384], wo^T bf16 [256,256].  w_ada bf16 [(2*depth+1)*512, S] / b_ada fp32 hold (gamma-1 | beta) rows per
 // norm.  scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; `barrier` one uint32.
 // hid_out (fp32 [depth, B, 256], may be NULL) receives the inputs of the attention layers (the reference's cache contract);
-// out_bf16 (bf16 [B, 256], may be NULL) a bf16 copy of `out`.
+// out_bf16 (bf16 [B, 256], may be NULL) a bf16 copy of `out`.  gb_all (bf16 [B, T_all, (2*depth+1)*512], may be NULL): the
+// (gamma-1 | beta) rows of every position, prepared by one GEMM before a rendering loop; the step then reads position *pos_dev + 1
+// in place and `style` / phase 0 are not used.
 extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada,
                                      const void* const* ptrs, int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap,
                                      void* gb, void* qkv, void* o, void* hmid, float* xres, float* hid_out, float* out, void* out_bf16,
-                                     unsigned* barrier, float eps, cudaStream_t stream) {
+                                     unsigned* barrier, float eps, const void* gb_all, int T_all, cudaStream_t stream) {
     if (B <= 0) return SPB_OK;
     SPB_CHECK_ARG(x_in && style && w_ada && b_ada && ptrs && pos_dev && gb && qkv && o && hmid && xres && out && barrier,
                   "spb_decode_stack_step: null pointer");
@@ -694,6 +707,8 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     p.gb = reinterpret_cast<__nv_bfloat16*>(gb); p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv);
     p.o = reinterpret_cast<__nv_bfloat16*>(o); p.hmid = reinterpret_cast<__nv_bfloat16*>(hmid);
     p.xres = xres; p.hid_out = hid_out; p.out = out; p.out16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.barrier = barrier; p.eps = eps;
+    p.gb_all = reinterpret_cast<const __nv_bfloat16*>(gb_all); p.T_all = T_all;
+    SPB_CHECK_ARG(gb_all == nullptr || T_all > 0, "spb_decode_stack_step: gb_all needs T_all > 0");
     int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4 + (2 * DS_D + 2 * DS_D) * 4 + 2 * (DS_QKV / 2) * 4 + 8 * 2 * DS_D * 4;
     const int smem_e = 4 * DS_TM * DS_LDA * 2 + 4 * 2 * 2 * 32 * 16;        // phase E: four K quarters of the rows + the reduction scratch
     if (smem < smem_e) smem = smem_e;

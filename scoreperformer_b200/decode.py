@@ -209,6 +209,10 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
             K.gemm(x2p, wm_r, bias=bm + b_comp, out=P2[b0:b1].view(-1, Dm))
             K.gemm(ctx16[b0:b1].reshape(-1, ctx16.shape[-1]), wc_r, bias=bc, out=C2[b0:b1].view(-1, Dm))
             del x2, x2p
+        # ... and the AdaLN terms of every position (one GEMM instead of a tile phase per step), memory permitting
+        gb_all = None
+        if B * T * plan.gb.shape[1] * 2 <= int(K._os.environ.get("SPB_DECODE_GB_ALL_BYTES", str(8 << 30))):
+            gb_all = plan.prepare_adaln(style_f)
         feed_c = feed.contiguous()
         tok_buf = torch.empty((B, F), dtype=feed_c.dtype, device=dev)
         p2_buf = torch.empty((B, Dm), dtype=F32, device=dev)
@@ -218,12 +222,15 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
 
     def step_lean():
         # one launch reads what this step needs at the device-side position: tuple i, and the prepared terms / style of note i+1
-        K.gather_at_pos([feed_c, P2, C2, style_f], [tok_buf, p2_buf, c2_buf, st_buf], [0, 1, 1, 1], pos_t)
+        if gb_all is None:
+            K.gather_at_pos([feed_c, P2, C2, style_f], [tok_buf, p2_buf, c2_buf, st_buf], [0, 1, 1, 1], pos_t)
+        else:
+            K.gather_at_pos([feed_c, P2, C2], [tok_buf, p2_buf, c2_buf], [0, 1, 1], pos_t)
         x1, _, _ = K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b)
         te = K.gemm(x1, w_comp16, residual=p2_buf, out_dtype=F32)
         K.layer_norm_fwd(te, en_w, en_b, out=ln_buf, need_stats=False)
         x = K.gemm(ln_buf, wc_l, residual=c2_buf, out_dtype=F32)
-        plan.step(x, st_buf, km, pos_t)
+        plan.step(x, st_buf if gb_all is None else None, km, pos_t, gb_all=gb_all)
         # tied head for the masked fields only (wrappers.py:364-380); the stack kernel leaves a bf16 copy of its output
         e_raw = K.gemm(plan.out16, whead16, trans_b=True, out_dtype=BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)

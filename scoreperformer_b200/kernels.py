@@ -179,16 +179,30 @@ class DecodeStackPlan:
         self.hid = torch.empty((self.depth, B, 256), dtype=F32, device=dev) if keep_hiddens else None
         self.out = torch.empty((B, 256), dtype=F32, device=dev)
         self.out16 = torch.empty((B, 256), dtype=BF16, device=dev)          # bf16 copy of `out`: the head projection's operand
+        self._no_style = torch.zeros((B, style_dim), dtype=F32, device=dev)   # placeholder when the AdaLN terms are prepared ahead
         self.barrier = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def step(self, x: Tensor, style: Tensor, key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5) -> Tensor:
+    def prepare_adaln(self, style_all: Tensor) -> Tensor:
+        """(gamma-1 | beta) rows of every AdaLN for ALL positions, style_all fp32 [B, T, S] -> bf16 [B, T, (2*depth+1)*512]: one
+        large GEMM before a rendering loop instead of a tile phase in every note-step (pass the result as `gb_all` to step())."""
+        B, T, S = style_all.shape
+        assert B == self.B and S == self.S
+        s16 = cast_bf16(style_all.reshape(B * T, S).contiguous())
+        return gemm(s16, self.w_ada, bias=self.b_ada, out_dtype=BF16).view(B, T, -1)
+
+    def step(self, x: Tensor, style: Optional[Tensor], key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5,
+             gb_all: Optional[Tensor] = None) -> Tensor:
         assert x.dtype == F32 and x.is_contiguous() and x.shape == (self.B, 256)
+        if gb_all is not None:
+            assert gb_all.dtype == BF16 and gb_all.is_contiguous() and gb_all.shape[0] == self.B and gb_all.shape[2] == self.gb.shape[1]
+            style = self._no_style if style is None else style
         assert style.dtype == F32 and style.is_contiguous() and style.shape == (self.B, self.S)
         assert pos_dev.dtype == torch.int64 and pos_dev.is_cuda
         assert key_mask is None or (key_mask.is_contiguous() and key_mask.shape == (self.B, self.cap))
         _call("spb_decode_stack_step", _p(x), _p(style), self.S, _p(self.w_ada), _p(self.b_ada), self.ptrs, self.depth, _p(key_mask),
               _p(pos_dev), self.B, self.cap, _p(self.gb), _p(self.qkv), _p(self.o), _p(self.hmid), _p(self.xres), _p(self.hid),
-              _p(self.out), _p(self.out16), _p(self.barrier), float(eps), _stream())
+              _p(self.out), _p(self.out16), _p(self.barrier), float(eps), _p(gb_all), gb_all.shape[1] if gb_all is not None else 0,
+              _stream())
         _count()
         return self.out
 
