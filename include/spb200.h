@@ -81,11 +81,14 @@ int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_row
  * int64 position.  Scratch: bf16 gb [B,(2*depth+1)*512], qkv [B,384], o [B,256], hmid [B,1024]; fp32 xres [B,256]; barrier uint32.
  * hid_out fp32 [depth, B, 256] (may be NULL) = inputs of the attention layers; out fp32 [B,256]; out_bf16 (may be NULL) its bf16 copy;
  * gb_all bf16 [B, T_all, (2*depth+1)*512] (may be NULL) = the AdaLN terms of all positions prepared ahead (read at *pos_dev + 1).
+ * front (HOST array of 8 device pointers, may be NULL): x = LN(x1 Wf^T + p2) Wc^T + c2 replaces x_in (TupleTransformer.embed_inputs,
+ * transformer.py:158-185, for the cached step): x1 bf16 [B,1536], Wf bf16 [256,1536], p2 fp32 [B,256], scratch fp32 [B,256],
+ * LayerNorm weight / bias fp32 [256], Wc^T bf16 [256,256], c2 fp32 [B,256].
  * dim 256, 4 heads x 64, hidden 1024. */
 int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada, const void* const* ptrs,
                           int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap, void* gb, void* qkv, void* o,
                           void* hmid, float* xres, float* hid_out, float* out, void* out_bf16, unsigned* barrier, float eps,
-                          const void* gb_all, int T_all, spb_stream_t stream);
+                          const void* gb_all, int T_all, const void* const* front, spb_stream_t stream);
 /* dst_k[b, :] = src_k[b, *pos_dev + shift_k, :] for n <= 8 row-major [B, T, row_bytes_k] arrays in one launch (host arrays of device
  * pointers / sizes / shifts; positions clamped to [0, T)): the inputs a note-step of the rendering loop (wrappers.py:409-431) reads at
  * its device-side position. */

@@ -59,7 +59,17 @@ struct DecodeStackParams {
     float eps;
     const __nv_bfloat16* gb_all;                 // optional [B, T_all, (2*depth+1)*512]: the AdaLN terms of every position, prepared ahead
     int T_all;
+    // optional input front of the rendering loop (decode.py): x = LN(x1 Wf^T + p2) Wc^T + c2 replaces x_in
+    const __nv_bfloat16* f_x1;                   // [B, 1536] tuple embedding of the previous note (bf16), or null: no front
+    const __nv_bfloat16* f_w;                    // [256, 1536] composed projection (project_multiemb left half . project_emb)
+    const float* f_p2;                           // [B, 256] prepared term of the masked tuple (+ biases)
+    float* f_te;                                 // [B, 256] scratch
+    const float* f_lnw;                          // emb_norm weight / bias [256]
+    const float* f_lnb;
+    const __nv_bfloat16* f_wct;                  // [256, 256] left half of the decoder's project_emb, transposed (input-major)
+    const float* f_c2;                           // [B, 256] prepared context term (+ bias)
 };
+constexpr int DS_FK = 1536, DS_FKQ = DS_FK / 4, DS_FLDA = DS_FKQ + 8;      // front GEMM: K, K per warp-pair quarter, padded smem row
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
     __syncthreads();
@@ -162,16 +172,29 @@ __device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres
     }
 }
 
-// copy 32 rows x K bf16 columns (k0..k0+K of a [B, ld] matrix) into the smem tile
-__device__ __forceinline__ void stage_rows(__nv_bfloat16* sA, const __nv_bfloat16* src, int ld, int k0, int K, int row0, int B) {
-    const int per_row = K / 8;
-    for (int i = threadIdx.x; i < DS_TM * per_row; i += DS_THREADS) {
-        const int rr = i / per_row, c = (i - rr * per_row) * 8;
-        const int row = row0 + rr;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (row < B) v = *reinterpret_cast<const uint4*>(src + (size_t)row * ld + k0 + c);
-        *reinterpret_cast<uint4*>(sA + (size_t)rr * DS_LDA + c) = v;
-    }
+// The four K quarters (KQ columns each, KQ = PT * 64) of 32 rows of a bf16 [B, ld] matrix -> four smem tiles [32][lda], with ALL of a
+// thread's 16-byte loads issued before the first store: a loop of load -> store pairs walks the L2 latency once per iteration.
+template <int PT>
+__device__ __forceinline__ void stage_quarters(__nv_bfloat16* sA, int lda, const __nv_bfloat16* src, int ld, int row0, int B) {
+    constexpr int KQ = PT * 64, PER_ROW = KQ / 8;
+    uint4 v[4][PT];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int i = threadIdx.x + j * DS_THREADS;
+            const int rr = i / PER_ROW, c = (i - rr * PER_ROW) * 8;
+            const int row = row0 + rr;
+            v[q4][j] = row < B ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)row * ld + q4 * KQ + c)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int i = threadIdx.x + j * DS_THREADS;
+            const int rr = i / PER_ROW, c = (i - rr * PER_ROW) * 8;
+            *reinterpret_cast<uint4*>(sA + (size_t)q4 * DS_TM * lda + (size_t)rr * lda + c) = v[q4][j];
+        }
 }
 
 __global__ void __launch_bounds__(DS_THREADS, 1)
@@ -218,8 +241,55 @@ decode_stack_kernel(DecodeStackParams p) {
                     *reinterpret_cast<uint32_t*>(p.gb + (size_t)row * ld_gb + col) = pack_bf16x2(acc[2 * hf] + bb0, acc[2 * hf + 1] + bb1);
             }
         }
-        for (int i = blockIdx.x * DS_THREADS + threadIdx.x; i < B * DS_D / 4; i += gridDim.x * DS_THREADS)
-            reinterpret_cast<float4*>(p.xres)[i] = reinterpret_cast<const float4*>(p.x_in)[i];
+        if (p.f_x1 == nullptr) {
+            for (int i = blockIdx.x * DS_THREADS + threadIdx.x; i < B * DS_D / 4; i += gridDim.x * DS_THREADS)
+                reinterpret_cast<float4*>(p.xres)[i] = reinterpret_cast<const float4*>(p.x_in)[i];
+        } else {
+            // front, first half: te = x1 Wf^T + p2.  32 x 16 tiles over the whole K = 1536: the four warp pairs take a quarter of K
+            // each and the quarters are summed through shared memory in a fixed order (same scheme as phase E)
+            constexpr int TN_F = 16;
+            const int col_blocks = DS_D / TN_F;
+            const int mh = warp & 1, kq = warp >> 1;
+            __nv_bfloat16* sAk = sA + (size_t)kq * DS_TM * DS_FLDA;
+            float* red = reinterpret_cast<float*>(smem_raw + 4 * DS_TM * DS_FLDA * 2);
+            for (int t = blockIdx.x; t < row_blocks * col_blocks; t += gridDim.x) {
+                const int rb = t / col_blocks, cb = t - rb * col_blocks;
+                uint32_t bf0[2 * (DS_FKQ / 16)], bf1[2 * (DS_FKQ / 16)];
+                load_w<DS_FKQ / 16>(bf0, p.f_w + kq * DS_FKQ, DS_FK, cb * TN_F, lane);
+                load_w<DS_FKQ / 16>(bf1, p.f_w + kq * DS_FKQ, DS_FK, cb * TN_F + 8, lane);
+                __syncthreads();
+                stage_quarters<DS_FKQ / 64>(sA, DS_FLDA, p.f_x1, DS_FK, rb * DS_TM, B);
+                __syncthreads();
+                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_pre<DS_FKQ / 16>(acc0, sAk, DS_FLDA, bf0, warp, lane);
+                mma_pre<DS_FKQ / 16>(acc1, sAk, DS_FLDA, bf1, warp, lane);
+                float4* my = reinterpret_cast<float4*>(red) + ((kq * 2 + mh) * 2) * 32 + lane;
+                my[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+                my[32] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+                __syncthreads();
+                if (kq == 0) {
+#pragma unroll
+                    for (int piece = 0; piece < 2; ++piece) {
+                        float4 sum = reinterpret_cast<const float4*>(red)[((0 * 2 + mh) * 2 + piece) * 32 + lane];
+#pragma unroll
+                        for (int q4 = 1; q4 < 4; ++q4) {
+                            const float4 v = reinterpret_cast<const float4*>(red)[((q4 * 2 + mh) * 2 + piece) * 32 + lane];
+                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                        }
+                        const int col = cb * TN_F + piece * 8 + tig * 2;
+                        const float part[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int row = rb * DS_TM + mh * 16 + g + hf * 8;
+                            if (row < B) {
+                                const float2 r2 = *reinterpret_cast<const float2*>(p.f_p2 + (size_t)row * DS_D + col);
+                                *reinterpret_cast<float2*>(p.f_te + (size_t)row * DS_D + col) = make_float2(part[2 * hf] + r2.x, part[2 * hf + 1] + r2.y);
+                            }
+                        }
+                    }
+                }
+            }
+        }
     }
     grid_barrier(p.barrier, epoch);
 
@@ -250,6 +320,66 @@ decode_stack_kernel(DecodeStackParams p) {
                 const int b = pair * 2 + bl;
                 const bool live = b < B;
                 __syncthreads();                                      // the previous pair's rows in shared memory are done with
+                if (l == 0 && p.f_x1 != nullptr) {
+                    // front, second half: x = LN(te) Wc^T + c2 for the two rows of this pair (per-row product like the out-projection)
+                    if (wq == 0) {
+                        float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (live) {
+                            const float4 v0 = *reinterpret_cast<const float4*>(p.f_te + (size_t)b * DS_D + lane * 8);
+                            const float4 v1 = *reinterpret_cast<const float4*>(p.f_te + (size_t)b * DS_D + lane * 8 + 4);
+                            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                            float s_ = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) s_ += v[j];
+                            const float mean = warp_sum(s_) * (1.f / DS_D);
+                            float q_ = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { v[j] -= mean; q_ += v[j] * v[j]; }
+                            const float rstd = rsqrtf(warp_sum(q_) * (1.f / DS_D) + p.eps);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                y[j] = __bfloat162float(__float2bfloat16_rn(v[j] * rstd * p.f_lnw[lane * 8 + j] + p.f_lnb[lane * 8 + j]));
+                        }
+                        float* xo = sOrow + bl * DS_D + lane * 8;
+                        *reinterpret_cast<float4*>(xo) = make_float4(y[0], y[1], y[2], y[3]);
+                        *reinterpret_cast<float4*>(xo + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                    }
+                    __syncthreads();
+                    {
+                        const int kg = threadIdx.x >> 5, cg = threadIdx.x & 31;
+                        const __nv_bfloat16* wt = p.f_wct + cg * 8;
+                        float a0[8], a1[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+#pragma unroll 16
+                        for (int k = kg * 32; k < kg * 32 + 32; ++k) {
+                            const uint4 w = __ldg(reinterpret_cast<const uint4*>(wt + (size_t)k * DS_D));
+                            const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y), w2 = unpack_bf16x2(w.z), w3 = unpack_bf16x2(w.w);
+                            const float wv[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+                            const float x0 = sOrow[k], x1 = sOrow[DS_D + k];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { a0[j] = fmaf(x0, wv[j], a0[j]); a1[j] = fmaf(x1, wv[j], a1[j]); }
+                        }
+                        float* pp = sPart + (size_t)kg * 2 * DS_D + cg * 8;
+                        *reinterpret_cast<float4*>(pp) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+                        *reinterpret_cast<float4*>(pp + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+                        *reinterpret_cast<float4*>(pp + DS_D) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                        *reinterpret_cast<float4*>(pp + DS_D + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+                        __syncthreads();
+                        const int c = threadIdx.x;
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const int row = pair * 2 + r;
+                            if (row < B) {
+                                float sum = p.f_c2[(size_t)row * DS_D + c];
+#pragma unroll
+                                for (int k8 = 0; k8 < 8; ++k8) sum += sPart[(size_t)(k8 * 2 + r) * DS_D + c];
+                                p.xres[(size_t)row * DS_D + c] = sum;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
                 if (wq == 0) {                                        // warps 0 and 4: AdaLN of one residual row each
                     float* xn = sXn + bl * DS_D + lane * 8;
                     float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -572,8 +702,7 @@ decode_stack_kernel(DecodeStackParams p) {
                 load_w<16>(bf0, p.w2[l] + kq * DS_D, DS_HID, cb * TN_E, lane);
                 load_w<16>(bf1, p.w2[l] + kq * DS_D, DS_HID, cb * TN_E + 8, lane);
                 __syncthreads();
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) stage_rows(sA + (size_t)q4 * DS_TM * DS_LDA, p.hmid, DS_HID, q4 * DS_D, DS_D, rb * DS_TM, B);
+                stage_quarters<DS_D / 64>(sA, DS_LDA, p.hmid, DS_HID, rb * DS_TM, B);
                 __syncthreads();
                 float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_pre<16>(acc0, sAk, DS_LDA, bf0, warp, lane);
@@ -675,13 +804,16 @@ __global__ void __launch_bounds__(128) gather_at_pos_kernel(GatherParams g) {
 // hid_out (fp32 [depth, B, 256], may be NULL) receives the inputs of the attention layers (the reference's cache contract);
 // out_bf16 (bf16 [B, 256], may be NULL) a bf16 copy of `out`.  gb_all (bf16 [B, T_all, (2*depth+1)*512], may be NULL): the
 // (gamma-1 | beta) rows of every position, prepared by one GEMM before a rendering loop; the step then reads position *pos_dev + 1
-// in place and `style` / phase 0 are not used.
+// in place and `style` / phase 0 are not used.  front (HOST array of 8 device pointers, may be NULL) = the input front of the
+// rendering loop evaluated inside this launch instead of x_in: x1 bf16 [B,1536], Wf bf16 [256,1536], p2 fp32 [B,256], scratch fp32
+// [B,256], LayerNorm weight / bias fp32 [256], Wc^T bf16 [256,256], c2 fp32 [B,256]:  x = LN(x1 Wf^T + p2) Wc^T + c2.
 extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada,
                                      const void* const* ptrs, int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap,
                                      void* gb, void* qkv, void* o, void* hmid, float* xres, float* hid_out, float* out, void* out_bf16,
-                                     unsigned* barrier, float eps, const void* gb_all, int T_all, cudaStream_t stream) {
+                                     unsigned* barrier, float eps, const void* gb_all, int T_all, const void* const* front,
+                                     cudaStream_t stream) {
     if (B <= 0) return SPB_OK;
-    SPB_CHECK_ARG(x_in && style && w_ada && b_ada && ptrs && pos_dev && gb && qkv && o && hmid && xres && out && barrier,
+    SPB_CHECK_ARG((x_in || front) && style && w_ada && b_ada && ptrs && pos_dev && gb && qkv && o && hmid && xres && out && barrier,
                   "spb_decode_stack_step: null pointer");
     SPB_CHECK_ARG(depth >= 1 && depth <= DS_MAX_DEPTH, "spb_decode_stack_step: depth must be in 1..%d", DS_MAX_DEPTH);
     SPB_CHECK_ARG(S % 16 == 0 && S >= 16 && S <= DS_D, "spb_decode_stack_step: style width must be a multiple of 16 in [16, 256], got %d", S);
@@ -709,9 +841,19 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     p.xres = xres; p.hid_out = hid_out; p.out = out; p.out16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.barrier = barrier; p.eps = eps;
     p.gb_all = reinterpret_cast<const __nv_bfloat16*>(gb_all); p.T_all = T_all;
     SPB_CHECK_ARG(gb_all == nullptr || T_all > 0, "spb_decode_stack_step: gb_all needs T_all > 0");
+    p.f_x1 = nullptr;
+    if (front != nullptr) {
+        for (int i = 0; i < 8; ++i) SPB_CHECK_ARG(front[i] != nullptr, "spb_decode_stack_step: front[%d] is null", i);
+        p.f_x1 = reinterpret_cast<const __nv_bfloat16*>(front[0]); p.f_w = reinterpret_cast<const __nv_bfloat16*>(front[1]);
+        p.f_p2 = reinterpret_cast<const float*>(front[2]); p.f_te = reinterpret_cast<float*>(const_cast<void*>(front[3]));
+        p.f_lnw = reinterpret_cast<const float*>(front[4]); p.f_lnb = reinterpret_cast<const float*>(front[5]);
+        p.f_wct = reinterpret_cast<const __nv_bfloat16*>(front[6]); p.f_c2 = reinterpret_cast<const float*>(front[7]);
+    }
     int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4 + (2 * DS_D + 2 * DS_D) * 4 + 2 * (DS_QKV / 2) * 4 + 8 * 2 * DS_D * 4;
     const int smem_e = 4 * DS_TM * DS_LDA * 2 + 4 * 2 * 2 * 32 * 16;        // phase E: four K quarters of the rows + the reduction scratch
     if (smem < smem_e) smem = smem_e;
+    const int smem_f = 4 * DS_TM * DS_FLDA * 2 + 4 * 2 * 2 * 32 * 16;       // front GEMM: four K quarters of the rows + the reduction scratch
+    if (front != nullptr && smem < smem_f) smem = smem_f;
     SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
     decode_stack_kernel<<<spb_num_sms(), DS_THREADS, smem, stream>>>(p);

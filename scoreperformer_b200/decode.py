@@ -219,6 +219,13 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
         c2_buf = torch.empty((B, Dm), dtype=F32, device=dev)
         st_buf = torch.empty((B, style_f.shape[-1]), dtype=F32, device=dev)
         ln_buf = torch.empty((B, Dm), dtype=BF16, device=dev)
+        # the rest of the front (te = x1 W^T + p2, emb_norm, project_emb's left half + c2) runs inside the stack kernel when the
+        # tuple embedding has the recipe's width; x1 is then a static buffer the embedding kernel fills
+        front_in_kernel = gb_all is not None and len(sizes) * 128 == 1536 and Dm == 256 \
+            and K._os.environ.get("SPB_DECODE_FRONT_IN_KERNEL", "1") == "1"
+        if front_in_kernel:
+            x1_buf = torch.empty((B, 1536), dtype=BF16, device=dev)
+            plan.set_front(x1_buf, w_comp16, p2_buf, en_w.float().contiguous(), en_b.float().contiguous(), wc_l.t().contiguous(), c2_buf)
 
     def step_lean():
         # one launch reads what this step needs at the device-side position: tuple i, and the prepared terms / style of note i+1
@@ -226,11 +233,15 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
             K.gather_at_pos([feed_c, P2, C2, style_f], [tok_buf, p2_buf, c2_buf, st_buf], [0, 1, 1, 1], pos_t)
         else:
             K.gather_at_pos([feed_c, P2, C2], [tok_buf, p2_buf, c2_buf], [0, 1, 1], pos_t)
-        x1, _, _ = K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b)
-        te = K.gemm(x1, w_comp16, residual=p2_buf, out_dtype=F32)
-        K.layer_norm_fwd(te, en_w, en_b, out=ln_buf, need_stats=False)
-        x = K.gemm(ln_buf, wc_l, residual=c2_buf, out_dtype=F32)
-        plan.step(x, st_buf if gb_all is None else None, km, pos_t, gb_all=gb_all)
+        if front_in_kernel:
+            K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b, out=x1_buf)
+            plan.step(None, None, km, pos_t, gb_all=gb_all, use_front=True)
+        else:
+            x1, _, _ = K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b)
+            te = K.gemm(x1, w_comp16, residual=p2_buf, out_dtype=F32)
+            K.layer_norm_fwd(te, en_w, en_b, out=ln_buf, need_stats=False)
+            x = K.gemm(ln_buf, wc_l, residual=c2_buf, out_dtype=F32)
+            plan.step(x, st_buf if gb_all is None else None, km, pos_t, gb_all=gb_all)
         # tied head for the masked fields only (wrappers.py:364-380); the stack kernel leaves a bf16 copy of its output
         e_raw = K.gemm(plan.out16, whead16, trans_b=True, out_dtype=BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)

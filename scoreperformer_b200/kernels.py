@@ -180,6 +180,7 @@ class DecodeStackPlan:
         self.out = torch.empty((B, 256), dtype=F32, device=dev)
         self.out16 = torch.empty((B, 256), dtype=BF16, device=dev)          # bf16 copy of `out`: the head projection's operand
         self._no_style = torch.zeros((B, style_dim), dtype=F32, device=dev)   # placeholder when the AdaLN terms are prepared ahead
+        self._front = None
         self.barrier = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def prepare_adaln(self, style_all: Tensor) -> Tensor:
@@ -190,9 +191,24 @@ class DecodeStackPlan:
         s16 = cast_bf16(style_all.reshape(B * T, S).contiguous())
         return gemm(s16, self.w_ada, bias=self.b_ada, out_dtype=BF16).view(B, T, -1)
 
-    def step(self, x: Tensor, style: Optional[Tensor], key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5,
-             gb_all: Optional[Tensor] = None) -> Tensor:
-        assert x.dtype == F32 and x.is_contiguous() and x.shape == (self.B, 256)
+    def set_front(self, x1: Tensor, w_front: Tensor, p2: Tensor, ln_w: Tensor, ln_b: Tensor, wc_t: Tensor, c2: Tensor) -> None:
+        """Let step() evaluate the input front of the rendering loop itself: x = LN(x1 w_front^T + p2) wc_t + c2 (static buffers:
+        x1 bf16 [B, 1536], p2 / c2 fp32 [B, 256] are refilled by the caller before every step)."""
+        B = self.B
+        assert x1.dtype == BF16 and x1.shape == (B, 1536) and x1.is_contiguous() and w_front.dtype == BF16 and w_front.shape == (256, 1536)
+        assert w_front.is_contiguous() and wc_t.dtype == BF16 and wc_t.shape == (256, 256) and wc_t.is_contiguous()
+        for t in (p2, c2):
+            assert t.dtype == F32 and t.shape == (B, 256) and t.is_contiguous()
+        for t in (ln_w, ln_b):
+            assert t.dtype == F32 and t.numel() == 256 and t.is_contiguous()
+        self._front_te = torch.empty((B, 256), dtype=F32, device=x1.device)
+        self._front_keep = (x1, w_front, p2, self._front_te, ln_w, ln_b, wc_t, c2)
+        self._front = _ptr_array(self._front_keep)
+
+    def step(self, x: Optional[Tensor], style: Optional[Tensor], key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5,
+             gb_all: Optional[Tensor] = None, use_front: bool = False) -> Tensor:
+        front = self._front if use_front else None
+        assert front is not None or (x is not None and x.dtype == F32 and x.is_contiguous() and x.shape == (self.B, 256))
         if gb_all is not None:
             assert gb_all.dtype == BF16 and gb_all.is_contiguous() and gb_all.shape[0] == self.B and gb_all.shape[2] == self.gb.shape[1]
             style = self._no_style if style is None else style
@@ -202,7 +218,7 @@ class DecodeStackPlan:
         _call("spb_decode_stack_step", _p(x), _p(style), self.S, _p(self.w_ada), _p(self.b_ada), self.ptrs, self.depth, _p(key_mask),
               _p(pos_dev), self.B, self.cap, _p(self.gb), _p(self.qkv), _p(self.o), _p(self.hmid), _p(self.xres), _p(self.hid),
               _p(self.out), _p(self.out16), _p(self.barrier), float(eps), _p(gb_all), gb_all.shape[1] if gb_all is not None else 0,
-              _stream())
+              front, _stream())
         _count()
         return self.out
 
