@@ -139,19 +139,33 @@ __device__ __forceinline__ void mma_pre(float (&acc)[4], const __nv_bfloat16* sA
     }
 }
 
-// AdaLN of 32 rows of the fp32 residual stream -> bf16 smem tile [32][DS_LDA]; one warp per 4 rows (rows beyond B are zeroed)
+// AdaLN of 32 rows of the fp32 residual stream -> bf16 smem tile [32][DS_LDA]; one warp per 4 rows (rows beyond B are zeroed).
+// The loads of all four rows (residual and gamma / beta) are issued before the first reduction.
 __device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres, const __nv_bfloat16* gb, size_t ld_gb, int norm_idx, int row0,
                                             int B, float eps, int warp, int lane) {
-    for (int rr = warp; rr < DS_TM; rr += DS_THREADS / 32) {
-        const int row = row0 + rr;
+    constexpr int RPW = DS_TM / (DS_THREADS / 32);          // 4 rows per warp
+    float4 x0[RPW], x1[RPW];
+    uint4 gu[RPW], bu[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int row = row0 + warp + i * (DS_THREADS / 32);
+        const bool ok = row < B;
+        const float* xr = xres + (size_t)(ok ? row : 0) * DS_D + lane * 8;
+        const __nv_bfloat16* gr = gb + (size_t)(ok ? row : 0) * ld_gb + norm_idx * 2 * DS_D + lane * 8;
+        x0[i] = *reinterpret_cast<const float4*>(xr);
+        x1[i] = *reinterpret_cast<const float4*>(xr + 4);
+        gu[i] = *reinterpret_cast<const uint4*>(gr);
+        bu[i] = *reinterpret_cast<const uint4*>(gr + DS_D);
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int rr = warp + i * (DS_THREADS / 32);
         __nv_bfloat16* dst = sA + (size_t)rr * DS_LDA + lane * 8;
-        if (row >= B) {
+        if (row0 + rr >= B) {
             *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
             continue;
         }
-        const float4 v0 = *reinterpret_cast<const float4*>(xres + (size_t)row * DS_D + lane * 8);
-        const float4 v1 = *reinterpret_cast<const float4*>(xres + (size_t)row * DS_D + lane * 8 + 4);
-        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float v[8] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w, x1[i].x, x1[i].y, x1[i].z, x1[i].w};
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[j];
@@ -160,10 +174,8 @@ __device__ __forceinline__ void stage_adaln(__nv_bfloat16* sA, const float* xres
 #pragma unroll
         for (int j = 0; j < 8; ++j) { v[j] -= mean; q += v[j] * v[j]; }
         const float rstd = rsqrtf(warp_sum(q) * (1.f / DS_D) + eps);
-        const __nv_bfloat16* gr = gb + (size_t)row * ld_gb + norm_idx * 2 * DS_D + lane * 8;
-        const uint4 gu = *reinterpret_cast<const uint4*>(gr), bu = *reinterpret_cast<const uint4*>(gr + DS_D);
-        const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z), g3 = unpack_bf16x2(gu.w);
-        const float2 b0 = unpack_bf16x2(bu.x), b1 = unpack_bf16x2(bu.y), b2 = unpack_bf16x2(bu.z), b3 = unpack_bf16x2(bu.w);
+        const float2 g0 = unpack_bf16x2(gu[i].x), g1 = unpack_bf16x2(gu[i].y), g2 = unpack_bf16x2(gu[i].z), g3 = unpack_bf16x2(gu[i].w);
+        const float2 b0 = unpack_bf16x2(bu[i].x), b1 = unpack_bf16x2(bu[i].y), b2 = unpack_bf16x2(bu[i].z), b3 = unpack_bf16x2(bu[i].w);
         const float gm[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y}, bt[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
         float y[8];
 #pragma unroll
