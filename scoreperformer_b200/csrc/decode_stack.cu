@@ -656,13 +656,30 @@ decode_stack_kernel(DecodeStackParams p) {
             const int per_cta = (total + gridDim.x - 1) / gridDim.x;
             const int t_lo = blockIdx.x * per_cta, t_hi = min(total, t_lo + per_cta);
             int staged_rb = -1;
+            // warps 0-3 (n-pieces 0,1 of the tile) take the value columns, warps 4-7 the matching gate columns
+            const int piece = (warp >> 1) & 1, is_gate = warp >> 2;
+            // the weight fragments and the bias of tile t + 1 are requested while tile t is computed: a CTA walks 3-4 tiles, and
+            // a fresh L2 round trip per tile was most of the phase
+            uint32_t bf_next[32];
+            float2 bias_next = make_float2(0.f, 0.f);
+            if (t_lo < t_hi) {
+                const int cb0 = t_lo - (t_lo / col_blocks) * col_blocks;
+                const int wr = (is_gate ? DS_HID : 0) + cb0 * 16 + piece * 8;
+                load_w<16>(bf_next, p.w1[l], DS_D, wr, lane);
+                bias_next = *reinterpret_cast<const float2*>(p.b1[l] + wr + tig * 2);
+            }
             for (int t = t_lo; t < t_hi; ++t) {
                 const int rb = t / col_blocks, cb = t - rb * col_blocks;
-                // warps 0-3 (n-pieces 0,1 of the tile) take the value columns, warps 4-7 the matching gate columns
-                const int piece = (warp >> 1) & 1, is_gate = warp >> 2;
-                const int wrow0 = (is_gate ? DS_HID : 0) + cb * 16 + piece * 8;
                 uint32_t bf[32];
-                load_w<16>(bf, p.w1[l], DS_D, wrow0, lane);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) bf[i] = bf_next[i];
+                const float2 bias = bias_next;
+                if (t + 1 < t_hi) {
+                    const int cbn = (t + 1) - ((t + 1) / col_blocks) * col_blocks;
+                    const int wr = (is_gate ? DS_HID : 0) + cbn * 16 + piece * 8;
+                    load_w<16>(bf_next, p.w1[l], DS_D, wr, lane);
+                    bias_next = *reinterpret_cast<const float2*>(p.b1[l] + wr + tig * 2);
+                }
                 if (rb != staged_rb) {
                     __syncthreads();
                     stage_adaln(sA, p.xres, gbp, gb_stride, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
@@ -671,8 +688,7 @@ decode_stack_kernel(DecodeStackParams p) {
                 __syncthreads();
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
-                const int wcol = wrow0 + tig * 2;
-                acc[0] += p.b1[l][wcol]; acc[1] += p.b1[l][wcol + 1]; acc[2] += p.b1[l][wcol]; acc[3] += p.b1[l][wcol + 1];
+                acc[0] += bias.x; acc[1] += bias.y; acc[2] += bias.x; acc[3] += bias.y;
                 // value and gate of the same (row, hidden) live in warps w and w + 4: exchange through smem (reuse the score area)
                 float* ex = sP;                      // [4 value warps][32 lanes][4]
                 __syncthreads();
