@@ -649,67 +649,43 @@ decode_stack_kernel(DecodeStackParams p) {
         }
         grid_barrier(p.barrier, epoch);
 
-        // ---- D: h = GLU(AdaLN(x) W1^T + b1): a tile is 32 rows x 16 hidden units (16 value + 16 gate columns)
+        // ---- D: h = GLU(AdaLN(x) W1^T + b1): a tile is 32 rows x 32 hidden units; every warp computes the value AND the gate columns of
+        // its 8 hidden units (two m16n8 chains), so the GLU needs no exchange between warps and a CTA walks two tiles, not four
         {
             // every CTA takes a contiguous run of tiles (column blocks fastest): the AdaLN'd rows are staged once per run
-            const int col_blocks = DS_HID / 16, total = row_blocks * col_blocks;
+            constexpr int TH = 32;
+            const int col_blocks = DS_HID / TH, total = row_blocks * col_blocks;
             const int per_cta = (total + gridDim.x - 1) / gridDim.x;
             const int t_lo = blockIdx.x * per_cta, t_hi = min(total, t_lo + per_cta);
+            const int piece = warp >> 1;
             int staged_rb = -1;
-            // warps 0-3 (n-pieces 0,1 of the tile) take the value columns, warps 4-7 the matching gate columns
-            const int piece = (warp >> 1) & 1, is_gate = warp >> 2;
-            // the weight fragments and the bias of tile t + 1 are requested while tile t is computed: a CTA walks 3-4 tiles, and
-            // a fresh L2 round trip per tile was most of the phase
-            uint32_t bf_next[32];
-            float2 bias_next = make_float2(0.f, 0.f);
-            if (t_lo < t_hi) {
-                const int cb0 = t_lo - (t_lo / col_blocks) * col_blocks;
-                const int wr = (is_gate ? DS_HID : 0) + cb0 * 16 + piece * 8;
-                load_w<16>(bf_next, p.w1[l], DS_D, wr, lane);
-                bias_next = *reinterpret_cast<const float2*>(p.b1[l] + wr + tig * 2);
-            }
             for (int t = t_lo; t < t_hi; ++t) {
                 const int rb = t / col_blocks, cb = t - rb * col_blocks;
-                uint32_t bf[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) bf[i] = bf_next[i];
-                const float2 bias = bias_next;
-                if (t + 1 < t_hi) {
-                    const int cbn = (t + 1) - ((t + 1) / col_blocks) * col_blocks;
-                    const int wr = (is_gate ? DS_HID : 0) + cbn * 16 + piece * 8;
-                    load_w<16>(bf_next, p.w1[l], DS_D, wr, lane);
-                    bias_next = *reinterpret_cast<const float2*>(p.b1[l] + wr + tig * 2);
-                }
+                const int hcol0 = cb * TH + piece * 8;
+                uint32_t bfv[32], bfg[32];
+                load_w<16>(bfv, p.w1[l], DS_D, hcol0, lane);
+                load_w<16>(bfg, p.w1[l], DS_D, DS_HID + hcol0, lane);
+                const float2 bias_v = *reinterpret_cast<const float2*>(p.b1[l] + hcol0 + tig * 2);
+                const float2 bias_g = *reinterpret_cast<const float2*>(p.b1[l] + DS_HID + hcol0 + tig * 2);
                 if (rb != staged_rb) {
                     __syncthreads();
                     stage_adaln(sA, p.xres, gbp, gb_stride, 2 * l + 1, rb * DS_TM, B, p.eps, warp, lane);
                     staged_rb = rb;
+                    __syncthreads();
                 }
-                __syncthreads();
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_pre<16>(acc, sA, DS_LDA, bf, warp, lane);
-                acc[0] += bias.x; acc[1] += bias.y; acc[2] += bias.x; acc[3] += bias.y;
-                // value and gate of the same (row, hidden) live in warps w and w + 4: exchange through smem (reuse the score area)
-                float* ex = sP;                      // [4 value warps][32 lanes][4]
-                __syncthreads();
-                if (is_gate) {
+                float av[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_pre<16>(av, sA, DS_LDA, bfv, warp, lane);
+                mma_pre<16>(ag, sA, DS_LDA, bfg, warp, lane);
+                av[0] += bias_v.x; av[1] += bias_v.y; av[2] += bias_v.x; av[3] += bias_v.y;
+                ag[0] += bias_g.x; ag[1] += bias_g.y; ag[2] += bias_g.x; ag[3] += bias_g.y;
+                float hv[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) ex[((warp - 4) * 32 + lane) * 4 + e] = acc[e];
-                }
-                __syncthreads();
-                if (!is_gate) {
-                    float hv[4];
+                for (int e = 0; e < 4; ++e) hv[e] = av[e] * ag[e] / (1.f + __expf(-ag[e]));
+                const int hcol = hcol0 + tig * 2;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float gt = ex[(warp * 32 + lane) * 4 + e];
-                        hv[e] = acc[e] * gt / (1.f + __expf(-gt));
-                    }
-                    const int hcol = cb * 16 + piece * 8 + tig * 2;
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
-                        if (row < B) *reinterpret_cast<uint32_t*>(p.hmid + (size_t)row * DS_HID + hcol) = pack_bf16x2(hv[2 * hf], hv[2 * hf + 1]);
-                    }
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int row = rb * DS_TM + (warp & 1) * 16 + g + hf * 8;
+                    if (row < B) *reinterpret_cast<uint32_t*>(p.hmid + (size_t)row * DS_HID + hcol) = pack_bf16x2(hv[2 * hf], hv[2 * hf + 1]);
                 }
             }
         }
