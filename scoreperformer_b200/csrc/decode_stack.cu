@@ -98,6 +98,16 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
 // acc[4] of this warp's m16n8 piece of a 32 x 32 CTA tile: rows r0 + 16*(warp&1).., columns of W  n0 + 8*(warp>>1)..
 // A: smem bf16 [32][lda] (k contiguous);  W: global bf16 [N][ldw] (k contiguous), rows n_row0.. are this tile's columns
 __device__ __forceinline__ void tile_mma(float (&acc)[4], const __nv_bfloat16* sA, int lda, const __nv_bfloat16* __restrict__ W, int ldw,
@@ -316,17 +326,17 @@ decode_stack_kernel(DecodeStackParams p) {
         {
             const int n_keys = min(p.cap, pos + 1);
             const float scale = rsqrtf((float)DS_DH);
-            float* sS = sP;                                                   // [2 scores][4 heads][cap] scores / numerators
+            // (the first 8 * cap floats of sP held the scores of the scalar attention; the tensor-core path keeps them in registers)
             float* sRed = sP + (size_t)(DS_THREADS / 32) * p.cap;             // [2][4 warps][4 heads] maxima, then [2][4][4] sums
             float* sO = sRed + 64;                                            // [2][4 warps][4 heads][64] partial outputs
             float* sXn = sO + 2 * 4 * 4 * 64;                                 // [2][256] AdaLN'd rows (bf16-rounded)
             float* sOrow = sXn + 2 * DS_D;                                    // [2][256] attention outputs (bf16-rounded)
             uint32_t* sQKV = reinterpret_cast<uint32_t*>(sOrow + 2 * DS_D);   // [2][192] qkv rows, bf16 pairs
             float* sPart = reinterpret_cast<float*>(sQKV + 2 * (DS_QKV / 2));   // [8][2][256] (or [5][2][384]) k-split partial sums
-            constexpr int UNR = 8;
+            constexpr int VST_ROW = 144, VST_STAGE = 16 * VST_ROW;            // V tile of 16 keys x 64 dims, rows padded to 144 B
+            const uint32_t vst = smem_u32(sPart + 8 * 2 * DS_D) + (uint32_t)(warp * 3 * VST_STAGE);     // three stages per warp
             const int bl = warp >> 2, wq = warp & 3;
-            const int grp = lane >> 3, sub = lane & 7;
-            const int per_warp = ((n_keys + 3) / 4 + 3) & ~3;                 // keys per warp, a multiple of 4
+            const int per_warp = ((n_keys + 3) / 4 + 15) & ~15;               // keys per warp, a multiple of 16 (one PV k-step)
             const int k_lo = wq * per_warp, k_hi = min(n_keys, k_lo + per_warp);
             for (int pair = blockIdx.x; pair * 2 < B; pair += gridDim.x) {
                 const int b = pair * 2 + bl;
@@ -471,134 +481,132 @@ decode_stack_kernel(DecodeStackParams p) {
                 }
                 __syncthreads();
                 const __nv_bfloat16* kvb = p.kv[l] + (size_t)(live ? b : 0) * p.cap * 128;
-                float* ss = sS + (size_t)bl * 4 * p.cap;
-                float qs[4][8];
+                // ---- attention on tensor cores (mma.sync m16n8k16, fp32 accumulate), online softmax per warp over its quarter of the
+                // keys.  S = q K^T: the 4 heads are rows 0-3 of the A tile (rows 4-15 zero); the 64 dims are permuted so that thread
+                // (g, tig) owns dims [16 tig, 16 tig + 16) of key row g -- its B fragments of all four k-steps are two 16-byte loads
+                // straight from the cache row, whole 128-byte lines per key.  O = P V: P is the S accumulator fragment re-packed as A,
+                // V tiles of 16 keys are staged by cp.async (three stages per warp) and read with ldmatrix.trans.
+                uint32_t qa0[4], qa2[4];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const uint4 u = live ? *reinterpret_cast<const uint4*>(qrow + h * DS_DH + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
-                    const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-                    qs[h][0] = a.x * scale; qs[h][1] = a.y * scale; qs[h][2] = b2.x * scale; qs[h][3] = b2.y * scale;
-                    qs[h][4] = c2.x * scale; qs[h][5] = c2.y * scale; qs[h][6] = d.x * scale; qs[h][7] = d.y * scale;
+                for (int s_ = 0; s_ < 4; ++s_) {
+                    const bool has = live && g < 4;
+                    qa0[s_] = has ? *reinterpret_cast<const uint32_t*>(qrow + g * DS_DH + tig * 16 + 4 * s_) : 0u;
+                    qa2[s_] = has ? *reinterpret_cast<const uint32_t*>(qrow + g * DS_DH + tig * 16 + 4 * s_ + 2) : 0u;
                 }
-                float slope[4];
+                const float slope_h = g < 4 ? __expf(p.logslopes[l][g]) : 0.f;
+                const int nblk = live ? (max(0, k_hi - k_lo) + 15) / 16 : 0;
+                auto issue_v = [&](int blk, int st) {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) slope[h] = __expf(p.logslopes[l][h]);
-                float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                if (live) {
-                    // the rows of the NEXT block of keys are requested before this block is evaluated: with eight warps per SM
-                    // the cache stream is bound by loads in flight, not by arithmetic
-                    uint4 kq[UNR], kn[UNR];
-#pragma unroll
-                    for (int u_ = 0; u_ < UNR; ++u_) {
-                        const int j = k_lo + grp + 4 * u_;
-                        kn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(kvb + (size_t)j * 128 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = lane + 32 * i, row = c >> 3, col = c & 7;
+                        const int j = k_lo + blk * 16 + row;
+                        const bool ok = j < k_hi;
+                        cp_async16_zfill(vst + (uint32_t)(st * VST_STAGE + row * VST_ROW + col * 16),
+                                         kvb + (size_t)(ok ? j : 0) * 128 + DS_DH + col * 8, ok ? 16 : 0);
                     }
-                    for (int base = k_lo; base < k_hi; base += 4 * UNR) {          // warp-uniform trip count: the body shuffles
+                    cp_async_commit();
+                };
+                auto load_k = [&](int blk, uint4 (&kr)[4]) {
 #pragma unroll
-                        for (int u_ = 0; u_ < UNR; ++u_) {
-                            kq[u_] = kn[u_];
-                            const int j = base + 4 * UNR + grp + 4 * u_;
-                            kn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(kvb + (size_t)j * 128 + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
-                        }
+                    for (int tile = 0; tile < 2; ++tile) {
+                        const int j = k_lo + blk * 16 + tile * 8 + g;
+                        const bool ok = j < k_hi;
+                        const uint4* src = reinterpret_cast<const uint4*>(kvb + (size_t)(ok ? j : 0) * 128 + tig * 16);
+                        kr[2 * tile] = ok ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+                        kr[2 * tile + 1] = ok ? __ldg(src + 1) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                };
+                float m_run = -INFINITY, l_run = 0.f;
+                float oacc[8][4];
 #pragma unroll
-                        for (int u_ = 0; u_ < UNR; ++u_) {
-                            const int j = base + grp + 4 * u_;
-                            const float2 a = unpack_bf16x2(kq[u_].x), b2 = unpack_bf16x2(kq[u_].y), c2 = unpack_bf16x2(kq[u_].z), d = unpack_bf16x2(kq[u_].w);
-                            float acc[4];
+                for (int n = 0; n < 8; ++n) { oacc[n][0] = 0.f; oacc[n][1] = 0.f; oacc[n][2] = 0.f; oacc[n][3] = 0.f; }
+                uint4 kr[4], kn[4];
+                if (nblk > 0) {
+                    issue_v(0, 0);
+                    load_k(0, kn);
+                }
+                for (int blk = 0; blk < nblk; ++blk) {
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                acc[h] = qs[h][0] * a.x + qs[h][1] * a.y + qs[h][2] * b2.x + qs[h][3] * b2.y + qs[h][4] * c2.x + qs[h][5] * c2.y +
-                                         qs[h][6] * d.x + qs[h][7] * d.y;
-                                acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
-                                acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
-                                acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 4);
-                            }
-                            if (j < k_hi) {
-                                const bool ok = p.key_mask == nullptr || p.key_mask[(size_t)b * p.cap + j];
-                                const float dist = (float)(pos - j);
+                    for (int i = 0; i < 4; ++i) kr[i] = kn[i];
+                    if (blk + 1 < nblk) {
+                        issue_v(blk + 1, (blk + 1) % 3);
+                        load_k(blk + 1, kn);
+                        cp_async_wait<1>();
+                    } else {
+                        cp_async_wait<0>();
+                    }
+                    __syncwarp();
+                    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_bf16_16816(s0, qa0[0], 0u, qa2[0], 0u, kr[0].x, kr[0].y);
+                    mma_bf16_16816(s0, qa0[1], 0u, qa2[1], 0u, kr[0].z, kr[0].w);
+                    mma_bf16_16816(s0, qa0[2], 0u, qa2[2], 0u, kr[1].x, kr[1].y);
+                    mma_bf16_16816(s0, qa0[3], 0u, qa2[3], 0u, kr[1].z, kr[1].w);
+                    mma_bf16_16816(s1, qa0[0], 0u, qa2[0], 0u, kr[2].x, kr[2].y);
+                    mma_bf16_16816(s1, qa0[1], 0u, qa2[1], 0u, kr[2].z, kr[2].w);
+                    mma_bf16_16816(s1, qa0[2], 0u, qa2[2], 0u, kr[3].x, kr[3].y);
+                    mma_bf16_16816(s1, qa0[3], 0u, qa2[3], 0u, kr[3].z, kr[3].w);
+                    // this lane (g < 4): head g, keys jb + 2 tig + {0,1} (tile 0) and jb + 8 + 2 tig + {0,1} (tile 1)
+                    const int jb = k_lo + blk * 16;
+                    float pv[4] = {s0[0], s0[1], s1[0], s1[1]};
+                    float mblk = -INFINITY;
 #pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    const float sc = ok ? acc[h] - slope[h] * dist : -INFINITY;
-                                    if (sub == h) ss[(size_t)h * p.cap + j] = sc;
-                                    mx[h] = fmaxf(mx[h], sc);
-                                }
-                            }
-                        }
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = jb + (t >> 1) * 8 + tig * 2 + (t & 1);
+                        const bool ok = g < 4 && j < k_hi && (p.key_mask == nullptr || p.key_mask[(size_t)b * p.cap + j]);
+                        pv[t] = ok ? pv[t] * scale - slope_h * (float)(pos - j) : -INFINITY;
+                        mblk = fmaxf(mblk, pv[t]);
+                    }
+                    mblk = fmaxf(mblk, __shfl_xor_sync(0xffffffffu, mblk, 1));
+                    mblk = fmaxf(mblk, __shfl_xor_sync(0xffffffffu, mblk, 2));
+                    const float m_new = fmaxf(m_run, mblk);
+                    const float m_use = m_new == -INFINITY ? 0.f : m_new;
+                    const float alpha = m_run == -INFINITY ? 0.f : __expf(m_run - m_use);
+                    float psum = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        pv[t] = pv[t] == -INFINITY ? 0.f : __expf(pv[t] - m_use);
+                        psum += pv[t];
+                    }
+                    l_run = l_run * alpha + psum;
+                    m_run = m_new;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) { oacc[n][0] *= alpha; oacc[n][1] *= alpha; }
+                    const uint32_t pa0 = pack_bf16x2(pv[0], pv[1]), pa2 = pack_bf16x2(pv[2], pv[3]);
+                    const uint32_t stage = vst + (uint32_t)((blk % 3) * VST_STAGE);
+                    // ldmatrix.x4.trans: matrices (keys 0-7 | 8-15) x (dim block 2 np | 2 np + 1); lane L supplies row L & 7 of matrix L >> 3
+                    const uint32_t lrow = stage + (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * VST_ROW + (lane >> 4) * 16);
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {
+                        uint32_t r0, r1, r2, r3;
+                        ldsm_x4_trans(lrow + (uint32_t)(np * 32), r0, r1, r2, r3);
+                        mma_bf16_16816(oacc[2 * np], pa0, 0u, pa2, 0u, r0, r1);
+                        mma_bf16_16816(oacc[2 * np + 1], pa0, 0u, pa2, 0u, r2, r3);
                     }
                 }
-#pragma unroll
-                for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
-                if (lane < 4) sRed[(bl * 4 + wq) * 4 + lane] = mx[lane];
+                // the four lanes of a head hold partial sums of its keys; the four warps of the score meet through shared memory
+                l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+                l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+                if (g < 4 && tig == 0) sRed[(bl * 4 + wq) * 4 + g] = m_run;
                 __syncthreads();
-                float m_use[4];
+                {
+                    float fac = 0.f;
+                    if (g < 4) {
+                        const float mg = fmaxf(fmaxf(sRed[(bl * 4 + 0) * 4 + g], sRed[(bl * 4 + 1) * 4 + g]),
+                                               fmaxf(sRed[(bl * 4 + 2) * 4 + g], sRed[(bl * 4 + 3) * 4 + g]));
+                        fac = m_run == -INFINITY ? 0.f : __expf(m_run - mg);
+                        if (tig == 0) sRed[32 + (bl * 4 + wq) * 4 + g] = l_run * fac;
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float m = fmaxf(fmaxf(sRed[(bl * 4 + 0) * 4 + h], sRed[(bl * 4 + 1) * 4 + h]),
-                                          fmaxf(sRed[(bl * 4 + 2) * 4 + h], sRed[(bl * 4 + 3) * 4 + h]));
-                    m_use[h] = m == -INFINITY ? 0.f : m;
-                }
-                __syncthreads();                              // everyone has read the maxima: the slots are reused for the sums
-                float o[4][8], sum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int h = 0; h < 4; ++h)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[h][e] = 0.f;
-                if (live) {
-                    const __nv_bfloat16* vbase = kvb + DS_DH + sub * 8;
-                    uint4 vq[UNR], vn[UNR];
-#pragma unroll
-                    for (int u_ = 0; u_ < UNR; ++u_) {
-                        const int j = k_lo + grp + 4 * u_;
-                        vn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128) : make_uint4(0u, 0u, 0u, 0u);
+                        for (int n = 0; n < 8; ++n)
+                            *reinterpret_cast<float2*>(sO + ((size_t)(bl * 4 + wq) * 4 + g) * 64 + n * 8 + tig * 2) =
+                                make_float2(oacc[n][0] * fac, oacc[n][1] * fac);
                     }
-                    for (int base = k_lo; base < k_hi; base += 4 * UNR) {
-#pragma unroll
-                        for (int u_ = 0; u_ < UNR; ++u_) {
-                            vq[u_] = vn[u_];
-                            const int j = base + 4 * UNR + grp + 4 * u_;
-                            vn[u_] = j < k_hi ? *reinterpret_cast<const uint4*>(vbase + (size_t)j * 128) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-#pragma unroll
-                        for (int u_ = 0; u_ < UNR; ++u_) {
-                            const int j = base + grp + 4 * u_;
-                            if (j < k_hi) {
-                                const float2 a0 = unpack_bf16x2(vq[u_].x), a1 = unpack_bf16x2(vq[u_].y), a2 = unpack_bf16x2(vq[u_].z), a3 = unpack_bf16x2(vq[u_].w);
-#pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    const float e = __expf(ss[(size_t)h * p.cap + j] - m_use[h]);
-                                    sum[h] += e;
-                                    o[h][0] += e * a0.x; o[h][1] += e * a0.y; o[h][2] += e * a1.x; o[h][3] += e * a1.y;
-                                    o[h][4] += e * a2.x; o[h][5] += e * a2.y; o[h][6] += e * a3.x; o[h][7] += e * a3.y;
-                                }
-                            }
-                        }
-                    }
-                }
-                // the four key groups of the warp meet through shuffles, the four warps of the score through shared memory
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 8);
-                    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 16);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        o[h][e] += __shfl_xor_sync(0xffffffffu, o[h][e], 8);
-                        o[h][e] += __shfl_xor_sync(0xffffffffu, o[h][e], 16);
-                    }
-                }
-                if (grp == 0) {
-#pragma unroll
-                    for (int h = 0; h < 4; ++h)
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) sO[((size_t)(bl * 4 + wq) * 4 + h) * 64 + sub * 8 + e] = o[h][e];
-                    if (sub == 0)
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) sRed[(bl * 4 + wq) * 4 + h] = sum[h];      // every lane of a group holds the same sums
                 }
                 __syncthreads();
                 if (live) {
                     // warp wq finishes head wq: 64 dims, two per lane
                     const int h = wq;
-                    const float tot = sRed[(bl * 4 + 0) * 4 + h] + sRed[(bl * 4 + 1) * 4 + h] + sRed[(bl * 4 + 2) * 4 + h] + sRed[(bl * 4 + 3) * 4 + h];
+                    const float tot = sRed[32 + (bl * 4 + 0) * 4 + h] + sRed[32 + (bl * 4 + 1) * 4 + h] + sRed[32 + (bl * 4 + 2) * 4 + h] +
+                                      sRed[32 + (bl * 4 + 3) * 4 + h];
                     const float inv = tot > 0.f ? 1.f / tot : 0.f;
                     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
@@ -853,7 +861,7 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
         p.f_lnw = reinterpret_cast<const float*>(front[4]); p.f_lnb = reinterpret_cast<const float*>(front[5]);
         p.f_wct = reinterpret_cast<const __nv_bfloat16*>(front[6]); p.f_c2 = reinterpret_cast<const float*>(front[7]);
     }
-    int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4 + (2 * DS_D + 2 * DS_D) * 4 + 2 * (DS_QKV / 2) * 4 + 8 * 2 * DS_D * 4;
+    int smem = DS_TM * DS_LDA * 2 + (DS_THREADS / 32) * cap * 4 + 64 * 4 + 2 * 4 * 4 * 64 * 4 + (2 * DS_D + 2 * DS_D) * 4 + 2 * (DS_QKV / 2) * 4 + 8 * 2 * DS_D * 4 + (DS_THREADS / 32) * 3 * 16 * 144;
     const int smem_e = 4 * DS_TM * DS_LDA * 2 + 4 * 2 * 2 * 32 * 16;        // phase E: four K quarters of the rows + the reduction scratch
     if (smem < smem_e) smem = smem_e;
     const int smem_f = 4 * DS_TM * DS_FLDA * 2 + 4 * 2 * 2 * 32 * 16;       // front GEMM: four K quarters of the rows + the reduction scratch
