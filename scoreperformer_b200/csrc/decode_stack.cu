@@ -520,17 +520,24 @@ decode_stack_kernel(DecodeStackParams p) {
                 float oacc[8][4];
 #pragma unroll
                 for (int n = 0; n < 8; ++n) { oacc[n][0] = 0.f; oacc[n][1] = 0.f; oacc[n][2] = 0.f; oacc[n][3] = 0.f; }
-                uint4 kr[4], kn[4];
+                // two blocks of 16 keys are in flight behind the one being evaluated (K in registers, V in the shared-memory ring)
+                uint4 kr[4], kn[4], kn2[4];
                 if (nblk > 0) {
                     issue_v(0, 0);
                     load_k(0, kn);
                 }
+                if (nblk > 1) {
+                    issue_v(1, 1);
+                    load_k(1, kn2);
+                }
                 for (int blk = 0; blk < nblk; ++blk) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) kr[i] = kn[i];
-                    if (blk + 1 < nblk) {
-                        issue_v(blk + 1, (blk + 1) % 3);
-                        load_k(blk + 1, kn);
+                    for (int i = 0; i < 4; ++i) { kr[i] = kn[i]; kn[i] = kn2[i]; }
+                    if (blk + 2 < nblk) {
+                        issue_v(blk + 2, (blk + 2) % 3);
+                        load_k(blk + 2, kn2);
+                        cp_async_wait<2>();
+                    } else if (blk + 1 < nblk) {
                         cp_async_wait<1>();
                     } else {
                         cp_async_wait<0>();
