@@ -924,35 +924,58 @@ struct SampleParams {
 
 __global__ void __launch_bounds__(32 * SF_MAX_FIELDS)
 sample_fields_kernel(SampleParams p) {
-    __shared__ float s_e[SF_MAX_FIELDS][128];
     const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (w >= p.n_fields) return;
     const int f = p.field[w], V = p.V[w], k = p.k[w];
     const long long pos = *p.pos_dev;
+    // logits of 32 vocabulary rows at a time: every lane multiplies ITS four dims of e with the same four dims of each row (one
+    // coalesced 256-byte row per load instruction; a lane reading whole rows costs 32 L1 wavefronts per instruction), then a
+    // transposing butterfly (31 shuffles) leaves the complete dot product of row 32 i + L in lane L
+    float e4[4];
     {
         const uint2 u = *reinterpret_cast<const uint2*>(p.e + (size_t)b * p.ld_e + f * 128 + lane * 4);
         const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
-        s_e[w][lane * 4] = a.x; s_e[w][lane * 4 + 1] = a.y; s_e[w][lane * 4 + 2] = c.x; s_e[w][lane * 4 + 3] = c.y;
+        e4[0] = a.x; e4[1] = a.y; e4[2] = c.x; e4[3] = c.y;
+    }
+    const __nv_bfloat16* tbase = p.table + (size_t)p.offset[w] * 128 + lane * 4;
+    __shared__ float s_lg[SF_MAX_FIELDS][256];
+    uint2 un[32];                                            // the rows of the next group are in flight while this one is reduced
+#pragma unroll
+    for (int r = 0; r < 32; ++r) un[r] = r < V ? __ldg(reinterpret_cast<const uint2*>(tbase + (size_t)r * 128)) : make_uint2(0u, 0u);
+#pragma unroll 1                                             // one copy of the 32-row body: the kernel is short, its code should be too
+    for (int i = 0; i < 8; ++i) {
+        s_lg[w][lane + 32 * i] = -INFINITY;
+        if (32 * i >= V) continue;                           // warp-uniform
+        float x[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const float2 a = unpack_bf16x2(un[r].x), c = unpack_bf16x2(un[r].y);
+            x[r] = e4[0] * a.x + e4[1] * a.y + e4[2] * c.x + e4[3] * c.y;
+        }
+        if (32 * (i + 1) < V) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int v = 32 * (i + 1) + r;
+                un[r] = v < V ? __ldg(reinterpret_cast<const uint2*>(tbase + (size_t)v * 128)) : make_uint2(0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int s_ = 16; s_ >= 1; s_ >>= 1) {
+            const bool upper = (lane & s_) != 0;
+#pragma unroll
+            for (int r = 0; r < s_; ++r) {
+                const float send = upper ? x[r] : x[r + s_];
+                const float keep = upper ? x[r + s_] : x[r];
+                x[r] = keep + __shfl_xor_sync(0xffffffffu, send, s_);
+            }
+        }
+        const int v = lane + 32 * i;
+        if (v < V && v >= p.n_banned) s_lg[w][v] = x[0];
     }
     __syncwarp();
     float lg[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int v = lane + 32 * i;
-        float acc = -INFINITY;
-        if (v < V && v >= p.n_banned) {
-            const __nv_bfloat16* tr = p.table + (size_t)(p.offset[w] + v) * 128;
-            acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const uint4 u = *reinterpret_cast<const uint4*>(tr + c * 8);
-                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-                const float* ev = &s_e[w][c * 8];
-                acc += ev[0] * a0.x + ev[1] * a0.y + ev[2] * a1.x + ev[3] * a1.y + ev[4] * a2.x + ev[5] * a2.y + ev[6] * a3.x + ev[7] * a3.y;
-            }
-        }
-        lg[i] = acc;
-    }
+    for (int i = 0; i < 8; ++i) lg[i] = s_lg[w][lane + 32 * i];
     // k rounds of warp arg-max: round t leaves its winner (value, token) in lane t
     float top_val = -INFINITY;
     int top_idx = 0;
