@@ -262,9 +262,19 @@ small_gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restri
             live |= (a != 0.f);
         }
         if (!__syncthreads_or(live)) continue;
-        for (int k = 0; k < kt; ++k) {
-            sB[k * 512 + c0] = c0 < n ? Bm[(size_t)(kk + k) * ldb + c0] : 0.f;
-            sB[k * 512 + c1] = c1 < n ? Bm[(size_t)(kk + k) * ldb + c1] : 0.f;
+        {
+            // all 64 loads of the chunk leave before the first store (a loop of load -> store pairs pays the memory latency per row)
+            float b0v[32], b1v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                b0v[k] = (k < kt && c0 < n) ? __ldg(Bm + (size_t)(kk + k) * ldb + c0) : 0.f;
+                b1v[k] = (k < kt && c1 < n) ? __ldg(Bm + (size_t)(kk + k) * ldb + c1) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                sB[k * 512 + c0] = b0v[k];
+                sB[k * 512 + c1] = b1v[k];
+            }
         }
         __syncthreads();
         for (int k = 0; k < kt; ++k) {
