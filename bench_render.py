@@ -70,7 +70,7 @@ def main():
         "config": {"workload": f"configs[4]: {B} scores x {T} notes, fields (3,5,10,11) rendered note by note", "scores": B, "notes": T},
         "seconds": dt, "cold_seconds": dt_cold, "warm_seconds_all": times[1:], "encoder_seconds": t_enc, "gpu_launches": K.LAUNCHES, "filled_mask_tokens": int((out != tokens).sum()),
         "roofline": {"bound": "hbm", "achieved": kv_bytes / dt / 1e9, "peak": 6450.6, "unit": "GB/s", "frac": kv_bytes / dt / 1e9 / 6450.6,
-                     "note": "algorithmic KV-cache reads only (SURVEY 8(d)); a note-step is 8 launches captured in a CUDA graph: one gather at the device-side position, the tuple embedding of the previous note, ONE persistent kernel for the rest of the input front and the 4-layer decoder stack (grid-barrier phases, csrc/decode_stack.cu; everything that does not depend on sampled tokens -- masked-tuple and context terms, AdaLN terms -- is prepared for all positions before the loop), head projection + LayerNorm (2), ONE head + sampling kernel, the barrier reset and the position increment"},
+                     "note": "algorithmic KV-cache reads only (SURVEY 8(d)); a note-step is 6 launches captured in a CUDA graph: one gather at the device-side position, the tuple embedding of the previous note, ONE persistent kernel for the rest of the input front and the 4-layer decoder stack (grid-barrier phases, tensor-core attention over the KV cache, csrc/decode_stack.cu; everything that does not depend on sampled tokens -- masked-tuple and context terms, AdaLN terms -- is prepared for all positions before the loop), head projection + LayerNorm (2), ONE head + sampling kernel whose last CTA advances the position"},
         "cpu_baseline": {"value": (n - 1) / dt_cpu, "unit": "notes/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"oracle port of unmask_tokens, batch 1, cached, {n} notes"}}))
 

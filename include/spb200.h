@@ -84,11 +84,12 @@ int spb_glu_bwd(const void* dh, const void* u, void* du, float* dbias, int n_row
  * front (HOST array of 8 device pointers, may be NULL): x = LN(x1 Wf^T + p2) Wc^T + c2 replaces x_in (TupleTransformer.embed_inputs,
  * transformer.py:158-185, for the cached step): x1 bf16 [B,1536], Wf bf16 [256,1536], p2 fp32 [B,256], scratch fp32 [B,256],
  * LayerNorm weight / bias fp32 [256], Wc^T bf16 [256,256], c2 fp32 [B,256].
- * dim 256, 4 heads x 64, hidden 1024. */
+ * barrier_is_zero: the caller guarantees *barrier == 0 (spb_sample_fields' `advance` clears it at the end of a note-step), so no memset
+ * node is enqueued.  dim 256, 4 heads x 64, hidden 1024. */
 int spb_decode_stack_step(const float* x_in, const float* style, int S, const void* w_ada, const float* b_ada, const void* const* ptrs,
                           int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap, void* gb, void* qkv, void* o,
                           void* hmid, float* xres, float* hid_out, float* out, void* out_bf16, unsigned* barrier, float eps,
-                          const void* gb_all, int T_all, const void* const* front, spb_stream_t stream);
+                          const void* gb_all, int T_all, const void* const* front, int barrier_is_zero, spb_stream_t stream);
 /* dst_k[b, :] = src_k[b, *pos_dev + shift_k, :] for n <= 8 row-major [B, T, row_bytes_k] arrays in one launch (host arrays of device
  * pointers / sizes / shifts; positions clamped to [0, T)): the inputs a note-step of the rendering loop (wrappers.py:409-431) reads at
  * its device-side position. */
@@ -97,10 +98,12 @@ int spb_gather_at_pos(const void* const* srcs, void* const* dsts, const int* row
 
 /* Tied heads of the rendered fields + sampling in one launch (modules/sampling.py:28-59, wrappers.py:358-397): per listed field
  * (host int arrays: field index, first table row, vocabulary <= 256, top-k <= 32; k = 1 is greedy) logits = e_f . table_f^T stay in
- * registers, tokens [0, n_banned) are never emitted, and the drawn token is written to tokens[b, *pos_dev + 1, field] (int64 [B,T,F]). */
+ * registers, tokens [0, n_banned) are never emitted, and the drawn token is written to tokens[b, *pos_dev + 1, field] (int64 [B,T,F]).
+ * advance (uint32 [2], may be NULL; [0] must be zero): the last CTA to finish does *pos_dev += 1 and clears advance[0] and advance[1]
+ * (= the grid-barrier word of spb_decode_stack_step when the two are laid out together), ending the note-step without further launches. */
 int spb_sample_fields(const void* e, int ld_e, const void* table, const int* fields, const int* offsets, const int* vocab, const int* topk,
                       int n_fields, int n_banned, float temperature, uint64_t seed, const long long* pos_dev, long long* tokens, int B,
-                      int T, int F, spb_stream_t stream);
+                      int T, int F, unsigned* advance, spb_stream_t stream);
 
 /* Device side of the collator (data/collators/performance.py:239-255 MixedLM mask_sequence, score_performance.py:186-234): expands a
  * packed batch -- uint16 tokens, int32 segment ids [3, n] (bars | beats | onsets), uint8 directions, int32 lengths -- into the int64

@@ -830,7 +830,7 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
                                      const void* const* ptrs, int depth, const uint8_t* key_mask, const long long* pos_dev, int B, int cap,
                                      void* gb, void* qkv, void* o, void* hmid, float* xres, float* hid_out, float* out, void* out_bf16,
                                      unsigned* barrier, float eps, const void* gb_all, int T_all, const void* const* front,
-                                     cudaStream_t stream) {
+                                     int barrier_is_zero, cudaStream_t stream) {
     if (B <= 0) return SPB_OK;
     SPB_CHECK_ARG((x_in || front) && style && w_ada && b_ada && ptrs && pos_dev && gb && qkv && o && hmid && xres && out && barrier,
                   "spb_decode_stack_step: null pointer");
@@ -874,7 +874,7 @@ extern "C" int spb_decode_stack_step(const float* x_in, const float* style, int 
     const int smem_f = 4 * DS_TM * DS_FLDA * 2 + 4 * 2 * 2 * 32 * 16;       // front GEMM: four K quarters of the rows + the reduction scratch
     if (front != nullptr && smem < smem_f) smem = smem_f;
     SPB_CHECK_CUDA(cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
+    if (!barrier_is_zero) SPB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), stream));
     decode_stack_kernel<<<spb_num_sms(), DS_THREADS, smem, stream>>>(p);
     SPB_CHECK_LAUNCH();
     return SPB_OK;
@@ -920,12 +920,12 @@ struct SampleParams {
     const long long* pos_dev;
     long long* tokens;            // [B, T, F]
     int T, F;
+    unsigned* advance;            // optional [2]: [0] = CTA counter (zero between launches), [1] = word to clear (the stack kernel's barrier)
 };
 
 __global__ void __launch_bounds__(32 * SF_MAX_FIELDS)
 sample_fields_kernel(SampleParams p) {
-    const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (w >= p.n_fields) return;
+    const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;      // the block has exactly n_fields warps
     const int f = p.field[w], V = p.V[w], k = p.k[w];
     const long long pos = *p.pos_dev;
     // logits of 32 vocabulary rows at a time: every lane multiplies ITS four dims of e with the same four dims of each row (one
@@ -1017,6 +1017,22 @@ sample_fields_kernel(SampleParams p) {
         token = __shfl_sync(0xffffffffu, top_idx, pick);
     }
     if (lane == 0 && pos + 1 < p.T) p.tokens[((size_t)b * p.T + (size_t)(pos + 1)) * p.F + f] = token;
+    if (p.advance != nullptr) {
+        // the last CTA to finish ends the note-step: position += 1 and the decode-stack kernel's grid-barrier word back to zero
+        // (every other CTA read the position before it counted itself in), instead of two more launches per step
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(p.advance, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            *const_cast<long long*>(p.pos_dev) = pos + 1;
+            p.advance[0] = 0u;
+            p.advance[1] = 0u;
+        }
+    }
 }
 
 }  // namespace
@@ -1026,7 +1042,7 @@ sample_fields_kernel(SampleParams p) {
 // tokens[b, *pos_dev + 1, field] (int64 [B, T, F]).  V <= 256, k <= 32, at most 8 fields.
 extern "C" int spb_sample_fields(const void* e, int ld_e, const void* table, const int* fields, const int* offsets, const int* vocab,
                                  const int* topk, int n_fields, int n_banned, float temperature, uint64_t seed, const long long* pos_dev,
-                                 long long* tokens, int B, int T, int F, cudaStream_t stream) {
+                                 long long* tokens, int B, int T, int F, unsigned* advance, cudaStream_t stream) {
     if (B <= 0 || n_fields <= 0) return SPB_OK;
     SPB_CHECK_ARG(e && table && fields && offsets && vocab && topk && pos_dev && tokens, "spb_sample_fields: null pointer");
     SPB_CHECK_ARG(n_fields <= SF_MAX_FIELDS && ld_e % 4 == 0 && temperature > 0.f, "spb_sample_fields: at most %d fields, ld_e %% 4 == 0, temperature > 0", SF_MAX_FIELDS);
@@ -1040,7 +1056,7 @@ extern "C" int spb_sample_fields(const void* e, int ld_e, const void* table, con
         p.field[i] = fields[i]; p.offset[i] = offsets[i]; p.V[i] = vocab[i]; p.k[i] = topk[i] < vocab[i] ? topk[i] : vocab[i];
     }
     p.n_banned = n_banned; p.inv_temperature = 1.f / temperature; p.seed = seed; p.pos_dev = pos_dev;
-    p.tokens = tokens; p.T = T; p.F = F;
+    p.tokens = tokens; p.T = T; p.F = F; p.advance = advance;
     sample_fields_kernel<<<B, 32 * n_fields, 0, stream>>>(p);
     SPB_CHECK_LAUNCH();
     return SPB_OK;

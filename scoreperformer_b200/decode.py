@@ -235,7 +235,7 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
             K.gather_at_pos([feed_c, P2, C2], [tok_buf, p2_buf, c2_buf], [0, 1, 1], pos_t)
         if front_in_kernel:
             K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b, out=x1_buf)
-            plan.step(None, None, km, pos_t, gb_all=gb_all, use_front=True)
+            plan.step(None, None, km, pos_t, gb_all=gb_all, use_front=True, barrier_is_zero=True)
         else:
             x1, _, _ = K.embed_ln_fwd(tok_buf, table, sizes, ln_w, ln_b)
             te = K.gemm(x1, w_comp16, residual=p2_buf, out_dtype=F32)
@@ -245,10 +245,16 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
         # tied head for the masked fields only (wrappers.py:364-380); the stack kernel leaves a bf16 copy of its output
         e_raw = K.gemm(plan.out16, whead16, trans_b=True, out_dtype=BF16)
         e, _, _ = K.layer_norm_fwd(e_raw, hn_w, hn_b, out_dtype=BF16, need_stats=False)
-        K.sample_fields(e, table16, fields, [offs[f] for f in fields], [sizes[f] for f in fields],
-                        [top_k if top_k is not None else -(-sizes[f] // 10) for f in fields], out, pos_t,
-                        temperature=temperature, seed=seed)
-        pos_t.add_(1)
+        if front_in_kernel:
+            # the sampling kernel's last CTA ends the step: position += 1, grid-barrier word of the stack kernel back to zero
+            K.sample_fields(e, table16, fields, [offs[f] for f in fields], [sizes[f] for f in fields],
+                            [top_k if top_k is not None else -(-sizes[f] // 10) for f in fields], out, pos_t,
+                            temperature=temperature, seed=seed, advance=plan.advance)
+        else:
+            K.sample_fields(e, table16, fields, [offs[f] for f in fields], [sizes[f] for f in fields],
+                            [top_k if top_k is not None else -(-sizes[f] // 10) for f in fields], out, pos_t,
+                            temperature=temperature, seed=seed)
+            pos_t.add_(1)
 
     def step():
         if lean and fused_sampling and (feed_c is out or teacher is not None):

@@ -181,7 +181,8 @@ class DecodeStackPlan:
         self.out16 = torch.empty((B, 256), dtype=BF16, device=dev)          # bf16 copy of `out`: the head projection's operand
         self._no_style = torch.zeros((B, style_dim), dtype=F32, device=dev)   # placeholder when the AdaLN terms are prepared ahead
         self._front = None
-        self.barrier = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.advance = torch.zeros(2, dtype=torch.int32, device=dev)         # [CTA counter of sample_fields, grid-barrier word]
+        self.barrier = self.advance[1:]
 
     def prepare_adaln(self, style_all: Tensor) -> Tensor:
         """(gamma-1 | beta) rows of every AdaLN for ALL positions, style_all fp32 [B, T, S] -> bf16 [B, T, (2*depth+1)*512]: one
@@ -206,7 +207,7 @@ class DecodeStackPlan:
         self._front = _ptr_array(self._front_keep)
 
     def step(self, x: Optional[Tensor], style: Optional[Tensor], key_mask: Optional[Tensor], pos_dev: Tensor, eps: float = 1e-5,
-             gb_all: Optional[Tensor] = None, use_front: bool = False) -> Tensor:
+             gb_all: Optional[Tensor] = None, use_front: bool = False, barrier_is_zero: bool = False) -> Tensor:
         front = self._front if use_front else None
         assert front is not None or (x is not None and x.dtype == F32 and x.is_contiguous() and x.shape == (self.B, 256))
         if gb_all is not None:
@@ -218,7 +219,7 @@ class DecodeStackPlan:
         _call("spb_decode_stack_step", _p(x), _p(style), self.S, _p(self.w_ada), _p(self.b_ada), self.ptrs, self.depth, _p(key_mask),
               _p(pos_dev), self.B, self.cap, _p(self.gb), _p(self.qkv), _p(self.o), _p(self.hmid), _p(self.xres), _p(self.hid),
               _p(self.out), _p(self.out16), _p(self.barrier), float(eps), _p(gb_all), gb_all.shape[1] if gb_all is not None else 0,
-              front, _stream())
+              front, int(barrier_is_zero), _stream())
         _count()
         return self.out
 
@@ -241,8 +242,11 @@ def gather_at_pos(srcs: Sequence[Tensor], dsts: Sequence[Tensor], shifts: Sequen
 
 
 def sample_fields(e: Tensor, table16: Tensor, fields: Sequence[int], offsets: Sequence[int], vocab: Sequence[int], topk: Sequence[int],
-                  tokens: Tensor, pos_dev: Tensor, temperature: float = 1.0, seed: int = 0, n_banned: int = 2) -> None:
-    """Heads of `fields` + top-k sampling (k = 1: greedy) + write of tokens[:, pos + 1, field], one launch (csrc/decode_stack.cu)."""
+                  tokens: Tensor, pos_dev: Tensor, temperature: float = 1.0, seed: int = 0, n_banned: int = 2,
+                  advance: Optional[Tensor] = None) -> None:
+    """Heads of `fields` + top-k sampling (k = 1: greedy) + write of tokens[:, pos + 1, field], one launch (csrc/decode_stack.cu).
+    `advance` (int32 [2], [0] zero): the last CTA also does pos += 1 and clears both words (DecodeStackPlan.barrier is laid out so that
+    advance[1] is the stack kernel's grid-barrier word)."""
     import ctypes
     _require_cuda(e, table16, tokens)
     assert e.dtype == BF16 and e.stride(1) == 1 and table16.dtype == BF16 and table16.is_contiguous() and table16.shape[1] == 128
@@ -251,7 +255,7 @@ def sample_fields(e: Tensor, table16: Tensor, fields: Sequence[int], offsets: Se
     arr = lambda xs: (ctypes.c_int * n)(*[int(x) for x in xs])
     B, T, F = tokens.shape
     _call("spb_sample_fields", _p(e), e.stride(0), _p(table16), arr(fields), arr(offsets), arr(vocab), arr(topk), n, int(n_banned),
-          float(temperature), int(seed), _p(pos_dev), _p(tokens), B, T, F, _stream())
+          float(temperature), int(seed), _p(pos_dev), _p(tokens), B, T, F, _p(advance), _stream())
     _count()
 
 
