@@ -9,13 +9,23 @@
 // launch / dependency latency (8 us per kernel, 0.5 ms per note).  Here every SM takes a slice of every phase -- weights stream
 // from L2 once per step over the whole chip, the KV cache is read once -- and the phases are separated by a grid barrier
 // (one atomic counter; all CTAs are co-resident: grid <= #SMs, one CTA per SM):
-//   phase 0        gb = style W_ada^T + b          (gamma-1 | beta) of all 2*depth+1 AdaLNs, bf16 scratch
-//                                                 (skipped when the caller prepared the terms of all positions: gb_all)
-//   per layer  ABC per score (two per CTA), no barrier in between: qkv = AdaLN(x) Wqkv^T as a per-row product over the
-//                  transposed weights; cache[pos] = k|v; o = softmax(q K^T s - slope|i-j|) V; x += mask * (o Wo^T)
-//              D   h    = GLU(AdaLN(x) W1^T + b1)     32x16 tiles, mma.sync m16n8k16 (M is tiny: tcgen05's 128-row tiles would
-//              E   x   += h W2^T                       idle 3/4 of the tensor core); K split inside the CTA, fixed summation order
-//   final          out  = AdaLN(x)
+//   phase 0        gb = style W_ada^T + b          (gamma-1 | beta) of all 2*depth+1 AdaLNs, bf16 scratch -- skipped when the caller
+//                                                 prepared the terms of all positions with one GEMM (gb_all);
+//                  with `front`: te = x1 Wf^T + p2  first half of the input front of the rendering loop, 32x16 tiles over K = 1536
+//   per layer  ABC per score (two per CTA, warps 0-3 / 4-7), no barrier in between:
+//                  [layer 0 with `front`: x = LN(te) Wc^T + c2 as a per-row product]
+//                  qkv = AdaLN(x) Wqkv^T as a per-row product over the transposed weights (16-byte loads, k split over thread
+//                  groups, fixed summation order); cache[pos] = k|v;
+//                  o = softmax(q K^T s - slope|i-j|) V on tensor cores: mma.sync m16n8k16 with the 4 heads as rows 0-3, online
+//                  softmax per warp over its quarter of the keys, K fragments straight from the cache rows (dims permuted so a
+//                  thread owns 16 contiguous dims), V tiles through a cp.async ring + ldmatrix.trans;
+//                  x += mask * (o Wo^T) as a per-row product
+//              D   h    = GLU(AdaLN(x) W1^T + b1)     32x32 tiles, mma.sync m16n8k16 (M is tiny: tcgen05's 128-row tiles would idle
+//                                                     3/4 of the tensor core); value and gate chains in the same warp
+//              E   x   += h W2^T                       32x16 tiles over K = 1024, K split inside the CTA, fixed summation order
+//   final          out  = AdaLN(x)  (+ a bf16 copy for the head projection)
+// Tile phases issue all of their staging loads before the first shared-memory store.  Nothing in the kernel uses atomics on data:
+// a rendering is bit-reproducible.
 // Algorithmic HBM/L2 bytes per note-step: B * pos * 4 layers * 256 B of KV cache (the roofline term) + 7.6 MB of
 // weights out of L2.
 #include "common.cuh"
