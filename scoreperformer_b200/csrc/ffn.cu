@@ -13,7 +13,8 @@
 //   out       = acc + resid                                                   fp32, once per tile
 // The MMA thread issues GEMM1(c+1) before GEMM2(c), so the tensor pipe works on the next chunk while the epilogue warps run the
 // GLU of this one (u is double-buffered in TMEM: 256 + 2 x 128 = 512 columns).
-// For the (unfused) backward the kernel can also emit u (bf16 [n, 2048], bias included) and h (bf16 [n, 1024]).
+// For the backward (ffn_bwd.cu consumes u, the dW2 weight-gradient GEMM consumes h) the kernel can also emit u (bf16 [n, 2048], bias
+// included) and h (bf16 [n, 1024]).
 // HBM traffic per row: 512 B (xn) + 1 KB (resid) + 1 KB (out) [+ 4 KB u + 2 KB h when saved]; the weights (1.5 MB) stream from L2.
 #include "attention_tc.cuh"
 #include <stdlib.h>
