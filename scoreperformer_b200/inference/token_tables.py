@@ -1,0 +1,215 @@
+"""Value tables of an SPMuple vocabulary: what the rendering loop and the messengers need from the tokenizer, without `miditok`.
+
+The reference's inference package reaches into its tokenizer for a handful of things only: field order (`vocab_types_idx`), the
+special-token ids, per-field value tables (`decode_token_type`, data/tokenizers/common/octuple_m.py:371-390 and
+spmuple/spmuple.py:756-775), score ticks from Bar / Position / TimeSig (`compute_ticks`, octuple_m.py:460-519), and the local-tempo
+helpers of SPMuple2 (spmuple/spmuple2.py:548-593).  `TokenTables` holds exactly those tables and restates those functions in numpy,
+so a rendering service can run from a checkpoint plus a small table file.  `TokenTables.from_tokenizer` lifts them out of a real
+`SPMuple` / `SPMuple2` object when `miditok` is available; both the reference tokenizer and a `TokenTables` can be handed to
+`messengers.SPMupleMessenger` / `generators.ScorePerformerGenerator` (duck-typed).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+SPECIAL_TOKENS = ("PAD", "MASK", "SOS", "EOS")          # data/tokenizers/constants.py:4
+SOS_TOKEN, EOS_TOKEN = "SOS_None", "EOS_None"
+DEFAULT_TEMPO = 120                                      # miditok.constants.TEMPO
+NOTE_ON_MIDI_EVENT = 144                                 # inference/messengers.py:12
+
+_COMPOUND_BEATS = {6: 2, 9: 3, 18: 3, 12: 4, 24: 4}     # beats per bar of compound metres (octuple_m.py:508-510)
+
+
+def find_closest(array: np.ndarray, values):
+    """Index of the entry of the sorted `array` nearest to each value; ties go to the upper neighbour (utils/functions.py
+    `find_closest`)."""
+    array = np.asarray(array)
+    hi = np.searchsorted(array, values, side="left")
+    lo = np.maximum(hi - 1, 0)
+    hi_c = np.minimum(hi, len(array) - 1)
+    take_lo = (hi == len(array)) | (np.fabs(values - array[lo]) < np.fabs(values - array[hi_c]))
+    return np.where(take_lo, lo, hi_c) if isinstance(hi, np.ndarray) else (int(lo) if take_lo else int(hi_c))
+
+
+def is_spmuple2(tokenizer) -> bool:
+    """The reference tests `isinstance(tokenizer, SPMuple2)` (generators.py:80,101,168); without `miditok` the class cannot be
+    imported, so the family is read from a flag or from the class names in the MRO."""
+    flag = getattr(tokenizer, "spmuple2", None)
+    if flag is not None:
+        return bool(flag)
+    return any(c.__name__ == "SPMuple2" for c in type(tokenizer).__mro__)
+
+
+@dataclass
+class TokenTables:
+    vocab_types_idx: Dict[str, int]                      # field name -> column of the note tuple
+    sizes: Dict[str, int]                                # field name -> vocabulary size (special tokens included)
+    beat_res: int                                        # samples per beat of the position grid (max of config.beat_res)
+    pitch_min: int
+    velocities: np.ndarray                               # value of Velocity token i (0 = unperformed note)
+    duration_values: np.ndarray                          # beats of Duration token i
+    tempos: np.ndarray
+    time_signatures: np.ndarray                          # [n, 2]
+    position_shifts: Optional[np.ndarray] = None
+    rel_onset_deviations: Optional[np.ndarray] = None
+    rel_performed_durations: Optional[np.ndarray] = None
+    additional_params: Dict[str, object] = field(default_factory=dict)
+    use_tempos: bool = True
+    spmuple2: bool = True
+    zero_token: int = len(SPECIAL_TOKENS)
+
+    def __post_init__(self):
+        for name in ("velocities", "duration_values", "tempos", "time_signatures", "position_shifts", "rel_onset_deviations",
+                     "rel_performed_durations"):
+            v = getattr(self, name)
+            if v is not None:
+                setattr(self, name, np.asarray(v))
+        # the attribute paths the reference code walks: tokenizer.config.beat_res / .additional_params / .use_tempos
+        self.config = SimpleNamespace(beat_res={(0, 4): self.beat_res}, additional_params=self.additional_params,
+                                      use_tempos=self.use_tempos, pitch_range=(self.pitch_min, self.pitch_min + 88))
+        self._max_beat_res = self.beat_res
+        self._duration_values = self.duration_values
+        self._current_midi_metadata = {}
+
+    # ---------------------------------------------------------------- ids
+    def __getitem__(self, item: Tuple[int, str]) -> int:
+        """`tokenizer[dim, 'SOS_None']`, `tokenizer[dim, 'Tempo_96']` (generators.py:51-52,310)."""
+        _, name = item
+        kind, _, value = name.partition("_")
+        if kind in SPECIAL_TOKENS:
+            return SPECIAL_TOKENS.index(kind)
+        table = {"Tempo": self.tempos, "Velocity": self.velocities}.get(kind)
+        if table is None:
+            raise KeyError(name)
+        hit = np.nonzero(table == float(value))[0]
+        if hit.size == 0:
+            raise KeyError(name)
+        return int(hit[0]) + self.zero_token
+
+    # ---------------------------------------------------------------- values
+    def decode_token_type(self, tokens: np.ndarray, token_type: str) -> np.ndarray:
+        ids = tokens[:, self.vocab_types_idx[token_type]] - self.zero_token
+        if token_type == "Pitch":
+            return ids + self.pitch_min
+        if token_type == "Velocity":
+            return self.velocities[ids]
+        if token_type in ("Duration", "PerfDuration"):
+            return self.duration_values[ids] * self.beat_res
+        if token_type == "Tempo":
+            return self.tempos[ids]
+        if token_type == "TimeSig":
+            return self.time_signatures[ids]
+        if token_type == "PositionShift":
+            return self.position_shifts[ids]
+        if token_type == "OnsetDev":
+            return ids - 2 * self.beat_res
+        if token_type == "RelOnsetDev":
+            return self.rel_onset_deviations[ids]
+        if token_type == "RelPerfDuration":
+            return self.rel_performed_durations[ids]
+        return ids
+
+    def compute_ticks(self, tokens: np.ndarray, time_division: int = 480, compute_beat_ticks: bool = False) -> Dict[str, object]:
+        """Score ticks of every note, bar and beat from the Bar / Position / TimeSig columns.  As in the reference the
+        time-signature map is rebuilt from the tokens given, so it is exact for full-length or single-metre windows only."""
+        ticks_per_sample = time_division / self.beat_res
+        bars = self.decode_token_type(tokens, "Bar")
+        positions = self.decode_token_type(tokens, "Position")
+
+        ts_col = tokens[:, self.vocab_types_idx["TimeSig"]]
+        seg_start = np.concatenate([[0], np.flatnonzero(ts_col[1:] != ts_col[:-1]) + 1])     # first note of every metre segment
+        metres = self.decode_token_type(tokens[seg_start], "TimeSig")
+        bar_len = time_division * 4 * metres[:, 0] / metres[:, 1]
+        seg_bar = bars[seg_start]
+        seg_tick = np.concatenate([[0], np.cumsum(bar_len[:-1] * np.diff(seg_bar))])
+
+        def segment_of(n):                                 # metre segment of unit 0..n (bars or beats), clamped to the first
+            return np.maximum(0, np.searchsorted(seg_bar, np.arange(n + 1), side="right") - 1)
+
+        bar_ticks = np.concatenate([[0], np.cumsum(bar_len[segment_of(bars[-1])])])
+        out = {"note_on": bar_ticks[bars] + positions * ticks_per_sample, "time_sig": (metres, seg_tick), "bar": bar_ticks}
+        if compute_beat_ticks:
+            beats_in_bar = metres[:, 0]                    # a view: like the reference, the returned metres carry the folded count
+            folded = beats_in_bar.copy()
+            for numerator, beats in _COMPOUND_BEATS.items():
+                folded[beats_in_bar == numerator] = beats
+            beats_in_bar[:] = folded
+            beat_len = bar_len // beats_in_bar
+            n_beats = int(np.sum(np.diff(np.concatenate([seg_bar, [bars[-1] + 1]])) * beats_in_bar))
+            out["beat"] = np.concatenate([[0], np.cumsum(beat_len[segment_of(n_beats)])])
+        return out
+
+    def compute_position_shifts(self, score_positions: np.ndarray, onset_shift: Optional[bool] = None) -> np.ndarray:
+        """Distance of every note to the previous onset (spmuple/spmuple.py:721-736)."""
+        if onset_shift is None:
+            onset_shift = self.additional_params["onset_position_shifts"]
+        if not onset_shift:
+            return np.concatenate([score_positions[:1], np.diff(score_positions)])
+        onsets, inverse = np.unique(score_positions, return_inverse=True)
+        order = np.sort(inverse)                            # the reference indexes by sorted onset id, not by note order
+        shifts = onsets[order] - onsets[order - 1]
+        neg = shifts < 0
+        shifts[neg] = score_positions[neg]
+        return shifts
+
+    # ---------------------------------------------------------------- SPMuple2 local tempo
+    def filter_onsets_in_window(self, onset_pair: np.ndarray, onset_pairs: np.ndarray, index: int) -> np.ndarray:
+        """Earlier (tick, time) onsets that vote on the local tempo: at least `tempo_min_onset_dist` seconds back, inside
+        `tempo_window` seconds, widened to the last `tempo_min_onsets` within four windows (spmuple/spmuple2.py:548-576)."""
+        p = self.additional_params
+        now = onset_pair[1]
+        past = onset_pairs[:index]
+        far = past[past[:, 1] <= now - p["tempo_min_onset_dist"]]
+        if len(far) == 0:
+            far = past
+        win = far[far[:, 1] >= now - p["tempo_window"]]
+        if len(win) < p["tempo_min_onsets"]:
+            win = far[max(0, len(far) - p["tempo_min_onsets"]):]
+            win = win[win[:, 1] >= now - 4 * p["tempo_window"]]
+        return far if len(win) == 0 else win
+
+    def compute_local_tempo(self, distances: np.ndarray) -> float:
+        """Recency-weighted mean of tick / second ratios, floored at the slowest tempo (spmuple/spmuple2.py:578-593)."""
+        dt = distances[:, 1]
+        local = distances[:, 0] / dt * self._current_midi_metadata["tempo_scale"]
+        w = 1 - dt / (dt.max() + 0.01)
+        w /= w.sum()
+        tempo = max(self.tempos[0], (w * local).sum())
+        if self.use_tempos and self.additional_params["use_quantized_tempos"]:
+            tempo = self.tempos[find_closest(self.tempos, tempo)]
+        return tempo
+
+    # ---------------------------------------------------------------- construction / storage
+    @classmethod
+    def from_tokenizer(cls, tok) -> "TokenTables":
+        """Lift the tables out of a reference `SPMuple` / `SPMuple2` tokenizer (needs `miditok` in the calling process)."""
+        opt = lambda name: getattr(tok, name, None)
+        return cls(vocab_types_idx=dict(tok.vocab_types_idx), sizes=dict(tok.sizes), beat_res=int(max(tok.config.beat_res.values())),
+                   pitch_min=int(tok.config.pitch_range[0]), velocities=np.asarray(tok.velocities),
+                   duration_values=np.asarray(tok.duration_values), tempos=np.asarray(tok.tempos),
+                   time_signatures=np.asarray(tok.time_signatures), position_shifts=opt("position_shifts"),
+                   rel_onset_deviations=opt("rel_onset_deviations"), rel_performed_durations=opt("rel_performed_durations"),
+                   additional_params=dict(tok.config.additional_params), use_tempos=bool(tok.config.use_tempos),
+                   spmuple2=is_spmuple2(tok), zero_token=int(tok.zero_token))
+
+    _ARRAYS = ("velocities", "duration_values", "tempos", "time_signatures", "position_shifts", "rel_onset_deviations",
+               "rel_performed_durations")
+
+    def save(self, path: str) -> None:
+        import json
+        arrays = {k: getattr(self, k) for k in self._ARRAYS if getattr(self, k) is not None}
+        meta = dict(vocab_types_idx=self.vocab_types_idx, sizes=self.sizes, beat_res=self.beat_res, pitch_min=self.pitch_min,
+                    additional_params=self.additional_params, use_tempos=self.use_tempos, spmuple2=self.spmuple2,
+                    zero_token=self.zero_token)
+        np.savez(path, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+
+    @classmethod
+    def load(cls, path: str) -> "TokenTables":
+        import json
+        with np.load(path) as z:
+            meta = json.loads(bytes(z["meta"]).decode())
+            return cls(**meta, **{k: z[k] for k in cls._ARRAYS if k in z.files})

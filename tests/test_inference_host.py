@@ -1,0 +1,186 @@
+"""f3: the rendering loop and the messengers against the unmodified reference.
+
+tests/golden/inference_generator.npz and inference_messenger.npz were produced by oracle/gen_inference_golden.py from the
+reference's `ScorePerformerGenerator`, `SPMupleMessenger`, `SPMuple2Messenger` and tokenizer methods on the synthetic vocabulary /
+pieces of oracle/inference_cases.py.  Here `scoreperformer_b200.inference` gets the same inputs and the same stand-in decoder: every
+decoder call (window length, cache length, token digests, embedding slices), every returned chunk, message, tempo state and cache
+length must be IDENTICAL -- integers exactly, times to the last bit.  Host code only: no GPU needed.
+"""
+import os
+import sys
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import inference_cases as cases  # noqa: E402
+from scoreperformer_b200.inference import (ScorePerformerGenerator, SPMuple2IntermediateData, SPMuple2Messenger, SPMupleMessenger,  # noqa: E402
+                                           TokenTables)
+from scoreperformer_b200.inference.token_tables import find_closest  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@dataclass
+class Attn:
+    keys: Optional[torch.Tensor] = None
+    values: Optional[torch.Tensor] = None
+    qk_similarities: Optional[torch.Tensor] = None
+
+
+@dataclass
+class Inter:
+    hiddens: Optional[List[torch.Tensor]] = None
+    attention: Optional[List[Attn]] = None
+
+
+@dataclass
+class Caches:
+    token_emb: Optional[torch.Tensor] = None
+    transformer: Optional[Inter] = None
+
+
+@pytest.fixture(scope="module")
+def gen_golden():
+    return np.load(os.path.join(GOLDEN, "inference_generator.npz"))
+
+
+@pytest.fixture(scope="module")
+def msg_golden():
+    return np.load(os.path.join(GOLDEN, "inference_messenger.npz"))
+
+
+def same(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} != {b.shape}"
+    assert np.array_equal(a, b), f"{what}: max |diff| {np.abs(a.astype(np.float64) - b.astype(np.float64)).max()}"
+
+
+@pytest.mark.parametrize("name", list(cases.SCENARIOS))
+def test_rendering_loop_matches_reference(gen_golden, name):
+    g = gen_golden
+    tok = TokenTables(**cases.table_kwargs(**cases.SCENARIOS[name][1]))
+    windows, final = cases.run_scenario(name, ScorePerformerGenerator, SPMuple2Messenger, tok, (Caches, Inter, Attn),
+                                        SPMuple2IntermediateData)
+    assert len(windows) == int(g[f"{name}/n_windows"])
+    for i, w in enumerate(windows):
+        for k, v in w.items():
+            same(v, g[f"{name}/w{i}/{k}"], f"{name} window {i} {k}")
+    for k, v in final.items():
+        same(v, g[f"{name}/final/{k}"], f"{name} final {k}")
+
+
+def test_scenarios_reach_the_branches_they_are_meant_for(gen_golden):
+    """The goldens are only worth something if the reference actually truncated contexts, dropped and re-used caches, cut chords at
+    window ends and refreshed tempo tokens while producing them."""
+    g = gen_golden
+
+    def calls(name):
+        return np.concatenate([g[f"{name}/w{i}/calls"] for i in range(int(g[f"{name}/n_windows"]))])
+
+    c = calls("chords_ctx48")
+    assert c[:, 0].max() < 48 + 4 and (c[1:, 1] == -1).any() and (c[:, 1] > 0).any()      # truncated; caches dropped and re-used
+    assert (c[:, 5] > 0).any()                                                           # context slices that do not start at note 0
+    kept = [g[f"chords_ctx48/w{i}/seq"].shape[0] for i in range(int(g["chords_ctx48/n_windows"]))]
+    made = [g[f"chords_ctx48/w{i}/calls"].shape[0] for i in range(int(g["chords_ctx48/n_windows"]))]
+    assert any(m > 0 and k == 0 for m, k in zip(made, kept))                             # a window whose only chord came too late
+    cache_after = [g[f"chords_ctx48/w{i}/state"][0] for i in range(len(kept))]
+    assert any(b < a for a, b in zip(cache_after, cache_after[1:]))                      # cache rows cut / context truncated
+    assert (calls("no_caches_ctx32")[:, 1] == -1).all()
+    notes = g["tempo_is_input/final/notes"]
+    assert len(np.unique(notes[1:-1, 5])) > 1 and not (notes[1:-1, 5] == 1).any()        # Tempo column rewritten, never MASKed
+    assert g["single_notes_delta/w0/state"][3] != g["single_notes_delta/w5/state"][3]    # delta embedding written back
+
+
+MESSENGER_CASES = {
+    "spm2_refit": ("spm2", {}, 11, False),
+    "spm2_refit_raw": ("spm2", dict(use_quantized_tempos=False, tempo_min_onsets=3, tempo_window=2.), 12, False),
+    "spm2_token_tempo": ("spm2", dict(decode_recompute_tempos=False), 13, False),
+    "spm2_onset_tempo": ("spm2", dict(onset_tempos=True), 14, True),
+    "spm_beat": ("spm", {}, 15, False),
+    "spm_bar_abs": ("spm", dict(bar_tempos=True, use_position_shifts=False, onset_position_shifts=True), 16, True),
+    "spm_plain_shift": ("spm", dict(use_position_shifts=False, onset_position_shifts=False), 17, False),
+}
+
+
+@pytest.mark.parametrize("name", list(MESSENGER_CASES))
+def test_messenger_matches_reference(msg_golden, name):
+    """A piece fed in chunks that split chords, tempo state carried from chunk to chunk: messages (time, 144, pitch, velocity) of
+    every chunk, the stateless onset times, tick messages (SPMuple), the final tempo map / onset pairs, and the one-shot decoding."""
+    g = msg_golden
+    family, params, seed, metre = MESSENGER_CASES[name]
+    tok = TokenTables(**cases.table_kwargs(**params), spmuple2=family == "spm2")
+    msgr = (SPMuple2Messenger if family == "spm2" else SPMupleMessenger)(tok)
+    piece, cuts = cases.random_chunks(seed, metre_change=metre)
+    state, lo = None, 0
+    for i, hi in enumerate(cuts):
+        chunk = piece[lo:hi]
+        if f"{name}/c{i}/ticks" in g.files:
+            same(msgr.tokens_to_messages(chunk.copy(), intermediates=state, to_times=False, sort=False), g[f"{name}/c{i}/ticks"],
+                 f"{name} chunk {i} ticks")
+        messages, state = msgr.tokens_to_messages(chunk.copy(), intermediates=state, return_intermediates=True)
+        same(messages, g[f"{name}/c{i}/messages"], f"{name} chunk {i} messages")
+        same(msgr.tokens_to_messages(chunk.copy(), note_attributes=False, note_off_events=False, intermediates=None, sort=False),
+             g[f"{name}/c{i}/onsets"], f"{name} chunk {i} onsets")
+        lo = hi
+    same(state.tempos, g[f"{name}/tempos"], f"{name} tempo map")
+    if family == "spm2":
+        same(state.onset_pairs, g[f"{name}/pairs"], f"{name} onset pairs")
+    same(msgr.tokens_to_messages(piece.copy()), g[f"{name}/whole"], f"{name} whole piece")
+
+
+@pytest.mark.parametrize("metre", [0, 1])
+def test_token_tables_ticks_and_shifts(msg_golden, metre):
+    g = msg_golden
+    tok = TokenTables(**cases.table_kwargs())
+    piece = cases.make_piece(200, 31, bool(metre))
+    ticks = tok.compute_ticks(piece, 8, compute_beat_ticks=True)
+    tag = f"ticks{metre}"
+    same(ticks["note_on"], g[f"{tag}/note_on"], "note ticks")
+    same(ticks["bar"], g[f"{tag}/bar"], "bar ticks")
+    same(ticks["beat"], g[f"{tag}/beat"], "beat ticks")
+    same(ticks["time_sig"][0], g[f"{tag}/metres"], "metres")
+    same(ticks["time_sig"][1], g[f"{tag}/metre_ticks"], "metre ticks")
+    same(tok.compute_position_shifts(ticks["note_on"].copy(), onset_shift=True), g[f"{tag}/shifts_onset"], "onset shifts")
+    same(tok.compute_position_shifts(ticks["note_on"].copy(), onset_shift=False), g[f"{tag}/shifts_plain"], "plain shifts")
+
+
+def test_find_closest_and_table_io(msg_golden, tmp_path):
+    g = msg_golden
+    tok = TokenTables(**cases.table_kwargs())
+    same(find_closest(tok.tempos, g["closest/probe"]), g["closest/index"], "find_closest (array)")
+    same([find_closest(tok.tempos, float(v)) for v in g["closest/probe"][:40]], g["closest/scalars"], "find_closest (scalar)")
+    assert tok[0, "SOS_None"] == 2 and tok[0, "EOS_None"] == 3 and tok[5, "Tempo_96"] == 4 + 33
+    path = str(tmp_path / "tables.npz")
+    tok.save(path)
+    back = TokenTables.load(path)
+    piece = cases.make_piece(50, 3)
+    for field in cases.FIELDS:
+        same(back.decode_token_type(piece, field), tok.decode_token_type(piece, field), field)
+    assert back.additional_params == tok.additional_params and back.vocab_types_idx == tok.vocab_types_idx
+
+
+def test_cut_caches_views_and_window_helpers():
+    from scoreperformer_b200.inference.generators import bar_starts, chord_end, overflow_shift, resume_start
+    L = 10
+    mk = lambda d: torch.arange(L, dtype=torch.float32)[None, :, None].expand(1, L, d).clone()
+    c = Caches(token_emb=mk(4), transformer=Inter(hiddens=[mk(4)], attention=[Attn(mk(2), mk(2), None)]))
+    base = c.transformer.attention[0].keys
+    c = ScorePerformerGenerator.cut_caches(c, left_idx=2, right_idx=7)
+    assert c.token_emb.shape == (1, 5, 4) and c.transformer.hiddens[0].shape == (1, 5, 4)
+    k = c.transformer.attention[0].keys
+    assert k.shape == (1, 5, 2) and k.data_ptr() == base[:, 2:].data_ptr() and float(k[0, 0, 0]) == 2.     # a view, not a copy
+    assert isinstance(c.transformer, Inter) and isinstance(c.transformer.attention[0], Attn)
+
+    bars = np.array([4, 4, 5, 5, 5, 6, 7, 7])
+    assert bar_starts(bars).tolist() == [1, 4, 5]
+    notes = np.array([[4, 0], [4, 0], [4, 8], [5, 0], [5, 0], [5, 0]])
+    assert [chord_end(notes, i) for i in (0, 2, 3)] == [2, 3, 6]
+    assert resume_start(bars, 9, 64) == 0
+    assert resume_start(bars, 9, 6) == 6                         # 9 - (4 + 1) < 6: the context restarts behind the change at 4
+    assert overflow_shift(bars, 0, 6) == 5                       # 8 - 4 < 6: drop the five notes up to that bar change
