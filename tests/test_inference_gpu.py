@@ -1,0 +1,84 @@
+"""f3 on the GPU: `inference.ScorePerformerGenerator` driving the CUDA decoder (cached `unmask_tokens`) in time windows.
+
+The loop itself is pinned to the reference on the host (tests/test_inference_host.py); what is checked here is that the loop and the
+device path fit together: windows that cut chords and slice the caches must render exactly what one uninterrupted call renders
+(greedy decoding), and that rendering agrees with the one-shot batched renderer up to near-ties."""
+import pytest
+import torch
+
+from tests import parity
+import inference_cases as cases
+
+pytestmark = pytest.mark.gpu
+
+RENDERED = [3, 5, 10, 11]
+
+
+def _piece(T, seed):
+    """A synthetic performance whose notes of one onset share (Bar, Position): 12 onsets per 4/4 bar."""
+    batch = parity.make_batch(1, T, seed=seed, full_length=True, deadpan_last=False)
+    onset = batch["onsets"][0] - 4
+    perf = batch["perf"][0].clone()
+    perf[:, 0] = 4 + onset // 12
+    perf[:, 1] = 4 + (onset % 12) * 2
+    perf[:, 6] = 4                                                        # 4/4 throughout
+    batch["perf"][0] = perf
+    batch["score"][0] = perf[:, :10]
+    return batch, perf
+
+
+def test_windowed_rendering_on_device_equals_uninterrupted_rendering():
+    from scoreperformer_b200.decode import render_batch
+    from scoreperformer_b200.inference import ScorePerformerGenerator, SPMuple2IntermediateData, SPMuple2Messenger, TokenTables
+    from scoreperformer_b200.modules.sampling import top_k
+    T = 64
+    model = parity.build_model(dropout=False, device="cuda").eval()
+    batch, perf = _piece(T, seed=77)
+    b = {k: v.cuda() for k, v in batch.items()}
+    with torch.inference_mode():
+        enc = model.forward_encoders(perf=b["perf"], perf_mask=b["perf_mask"], score=b["score"], score_mask=b["score_mask"],
+                                     bars=b["bars"], beats=b["beats"], onsets=b["onsets"], deadpan_mask=b["deadpan_mask"],
+                                     compute_loss=False)
+    notes = perf.clone()
+    notes[1:, RENDERED] = 1                                               # note 0 is given, the rest is rendered
+    notes = torch.cat([notes, torch.full_like(notes[:1], 3)])             # EOS row
+    pad = lambda e: torch.cat([e[0], e[0, -1:]]).clone()                  # one embedding row for the EOS position
+
+    tok = TokenTables(**cases.table_kwargs())
+
+    def render(time_window):
+        gen = ScorePerformerGenerator(model, cases.make_dataset(tok, [perf.numpy()]), cases.make_collator(), SPMuple2Messenger(tok),
+                                      device="cuda")
+        pd = gen.perf_data
+        pd.notes, pd.context, pd.embeddings = notes.cuda(), pad(enc.score_embeddings), pad(enc.perf_embeddings)
+        pd.intermediates = SPMuple2IntermediateData(initial_tempo=96.)
+        n_messages, n_windows, t0 = 0, 0, 0.
+        while not pd.reached_eos and n_windows < 400:
+            before = pd.gen_seq.shape[0] if pd.gen_seq is not None else 1
+            seq, messages = gen.generate_performance_notes(start_time=t0, time_window=time_window, filter_logits_fn=top_k,
+                                                           filter_kwargs={"k": 1})
+            n_messages += len(messages)
+            n_windows += 1
+            if seq is not None:
+                assert seq.is_cuda and pd.gen_seq.shape[0] == before + seq.shape[0]
+                if pd.caches is not None:                                 # caches cover exactly the kept notes but the last
+                    assert pd.caches.token_emb.shape[1] <= pd.gen_seq.shape[0] - 1
+                    assert pd.caches.transformer.attention[0].keys.shape[1] == pd.caches.token_emb.shape[1]
+            t0 += time_window
+        assert pd.reached_eos
+        return pd.gen_seq, n_messages, n_windows
+
+    whole, m_whole, w_whole = render(1e9)
+    windowed, m_win, w_win = render(0.35)
+    assert w_whole <= 2 and w_win > 4, (w_whole, w_win)
+    assert whole.shape == (T, 12) and torch.equal(whole, windowed)
+    assert m_whole == m_win == 2 * (T - 1)                                # a note-on and a note-off per rendered note
+    assert int((whole == 1).sum()) == 0
+    keep = [f for f in range(12) if f not in RENDERED]
+    assert torch.equal(whole[:, keep].cpu(), perf[:, keep])
+
+    masked = perf.clone()
+    masked[:, RENDERED] = 1
+    want = render_batch(model, notes[None, :T].cuda(), masked[None].cuda(), enc.score_embeddings, enc.perf_embeddings)
+    agree = float((whole[:, RENDERED] == want[0][:, RENDERED]).float().mean())
+    assert agree > 0.85, agree
