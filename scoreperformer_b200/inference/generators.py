@@ -331,6 +331,58 @@ class ScorePerformerGenerator:
         return caches
 
 
+def render_performances(model, messenger: SPMupleMessenger, collator, pieces, filter_kwargs: Optional[Dict[str, object]] = None,
+                        temperature: float = 1., time_messages: bool = True, sort_messages: bool = True):
+    """Whole pieces, many at once: the offline counterpart of the window loop (SURVEY §8 C5 -- the reference renders one piece at a
+    time through the same loop with an infinite window).  `pieces` are `PerformanceData` as `prepare_performance_notes` leaves them
+    (notes with the rendered fields MASKed, per-note score / style embeddings, messenger state); pieces must fit the decoder context
+    as a whole (no truncation happens here).  All pieces advance in lock-step through `decode.render_batch` -- one persistent
+    decoder-stack launch and one heads + sampling launch per note for the whole batch -- then the rendered tuples come back in ONE
+    device->host copy and each piece goes through the messenger.  Sampling is top-k (`filter_kwargs={'k': k}`, default ceil(0.1 V) as
+    in modules/sampling.py:28-59).  Returns `[(gen_seq, messages), ...]` and completes every piece's `gen_seq` / `intermediates`."""
+    from ..decode import render_batch
+    tok = messenger.tokenizer
+    sos, eos = tok[0, SOS_TOKEN], tok[0, EOS_TOKEN]
+    cols = sorted(set(range(len(tok.sizes))).difference(collator.mask_ignore_token_dims))
+    dev = pieces[0].context.device
+    rows = []
+    for pd in pieces:
+        notes = pd.notes.detach().cpu().numpy().copy()
+        n = notes.shape[0] - int(notes[-1, 0] == eos)     # the EOS row never enters the decoder
+        rows.append((notes[:n], int(notes[0, 0] == sos)))
+    S, T, F = len(rows), max(r[0].shape[0] for r in rows), rows[0][0].shape[1]
+    tokens, valid = np.zeros((S, T, F), dtype=np.int64), np.zeros((S, T), dtype=bool)
+    to_zero = np.zeros(S, dtype=np.int64)
+    context = torch.zeros((S, T, pieces[0].context.shape[-1]), dtype=pieces[0].context.dtype, device=dev)
+    style = torch.zeros((S, T, pieces[0].embeddings.shape[-1]), dtype=pieces[0].embeddings.dtype, device=dev)
+    for i, ((notes, first), pd) in enumerate(zip(rows, pieces)):
+        n = notes.shape[0]
+        to_zero[i] = notes[first, 0] - tok.zero_token     # bars counted from the piece's first note, as in the window loop
+        tokens[i, :n] = notes
+        tokens[i, first:n, 0] -= to_zero[i]
+        valid[i, :n] = True
+        context[i, :n], style[i, :n] = pd.context[:n], pd.embeddings[:n]
+    masked = tokens.copy()
+    for i, (notes, first) in enumerate(rows):
+        masked[i, first:notes.shape[0]][:, cols] = collator.mask_token_id
+    k = None if not filter_kwargs else filter_kwargs.get("k")
+    out = render_batch(model, torch.from_numpy(tokens).to(dev), torch.from_numpy(masked).to(dev), context, style,
+                       mask=torch.from_numpy(valid).to(dev), fields=cols, temperature=temperature, top_k=k)
+    host = out.cpu().numpy()
+    results = []
+    for i, ((notes, first), pd) in enumerate(zip(rows, pieces)):
+        n = notes.shape[0]
+        seq = host[i, :n].copy()
+        seq[first:, 0] += to_zero[i]
+        # note 0 is the SOS row or a given note: what was rendered starts behind it, as `gen_seq` does in the window loop
+        messages, pd.intermediates = messenger.tokens_to_messages(seq[1:], intermediates=pd.intermediates, return_intermediates=True,
+                                                                  to_times=time_messages, sort=sort_messages)
+        pd.gen_seq = torch.from_numpy(seq).to(dev)
+        pd.reached_eos = True
+        results.append((pd.gen_seq[1:], messages))
+    return results
+
+
 def _sample_meta(**fields):
     """The dataset's own sample-meta class when the reference data package is importable, else a plain namespace with the same
     fields (data/datasets/score_performance.py `ScorePerformanceSampleMeta`)."""

@@ -3,6 +3,7 @@
 The loop itself is pinned to the reference on the host (tests/test_inference_host.py); what is checked here is that the loop and the
 device path fit together: windows that cut chords and slice the caches must render exactly what one uninterrupted call renders
 (greedy decoding), and that rendering agrees with the one-shot batched renderer up to near-ties."""
+import numpy as np
 import pytest
 import torch
 
@@ -82,3 +83,54 @@ def test_windowed_rendering_on_device_equals_uninterrupted_rendering():
     want = render_batch(model, notes[None, :T].cuda(), masked[None].cuda(), enc.score_embeddings, enc.perf_embeddings)
     agree = float((whole[:, RENDERED] == want[0][:, RENDERED]).float().mean())
     assert agree > 0.85, agree
+
+
+def test_render_performances_batches_whole_pieces():
+    """Offline counterpart of the window loop: three pieces of different lengths (SOS / EOS rows, bars not starting at zero) rendered in
+    lock-step by `render_performances`; every piece agrees with its own uninterrupted window-loop rendering up to near-ties, given
+    fields come back untouched, and the messages are exactly the messenger's decoding of the returned tuples."""
+    from scoreperformer_b200.inference import (PerformanceData, ScorePerformerGenerator, SPMuple2IntermediateData, SPMuple2Messenger,
+                                               TokenTables, render_performances)
+    from scoreperformer_b200.modules.sampling import top_k
+    model = parity.build_model(dropout=False, device="cuda").eval()
+    tok = TokenTables(**cases.table_kwargs())
+    collator, messenger = cases.make_collator(), SPMuple2Messenger(tok)
+    keep = [f for f in range(12) if f not in RENDERED]
+
+    def piece_data(T, seed, first_bar):
+        batch, perf = _piece(T, seed)
+        b = {k: v.cuda() for k, v in batch.items()}
+        with torch.inference_mode():
+            enc = model.forward_encoders(perf=b["perf"], perf_mask=b["perf_mask"], score=b["score"], score_mask=b["score_mask"],
+                                         bars=b["bars"], beats=b["beats"], onsets=b["onsets"], deadpan_mask=b["deadpan_mask"],
+                                         compute_loss=False)
+        perf = perf.clone()
+        perf[:, 0] += first_bar                                           # a piece cut out of the middle of a score
+        notes = perf.clone()
+        notes[:, RENDERED] = 1
+        notes = torch.cat([torch.full_like(notes[:1], 2), notes, torch.full_like(notes[:1], 3)])      # SOS ... EOS
+        pad = lambda e: torch.cat([e[0, :1], e[0], e[0, -1:]]).clone()
+        make = lambda: PerformanceData(perf_seq=perf.numpy(), notes=notes.cuda(), context=pad(enc.score_embeddings),
+                                       embeddings=pad(enc.perf_embeddings), intermediates=SPMuple2IntermediateData(initial_tempo=96.))
+        return perf, make
+
+    specs = [piece_data(40, 5, 0), piece_data(64, 6, 7), piece_data(51, 7, 3)]
+    pieces = [make() for _, make in specs]
+    results = render_performances(model, messenger, collator, pieces, filter_kwargs={"k": 1})
+    assert len(results) == 3
+    for (perf, make), pd, (seq, messages) in zip(specs, pieces, results):
+        n = perf.shape[0]
+        assert seq.is_cuda and seq.shape == (n, 12) and pd.gen_seq.shape == (n + 1, 12) and pd.reached_eos
+        got = seq.cpu()
+        assert int((got == 1).sum()) == 0 and torch.equal(got[:, keep], perf[:, keep])
+        assert messages.shape == (2 * n, 4)
+        want_messages = messenger.tokens_to_messages(got.numpy(), intermediates=SPMuple2IntermediateData(initial_tempo=96.))
+        assert np.array_equal(messages, want_messages)
+        assert np.all(np.diff(messages[:, 0]) >= 0)                       # sorted by time
+
+        gen = ScorePerformerGenerator(model, cases.make_dataset(tok, [perf.numpy()]), collator, messenger, device="cuda")
+        gen.perf_data = make()
+        loop_seq, loop_messages = gen.generate_performance_notes(time_window=1e9, filter_logits_fn=top_k, filter_kwargs={"k": 1})
+        assert gen.perf_data.reached_eos and loop_seq.shape == (n, 12)
+        agree = float((loop_seq[:, RENDERED] == seq[:, RENDERED]).float().mean())
+        assert agree > 0.85, agree
