@@ -129,7 +129,8 @@ def render_batch(model, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
 @torch.no_grad()
 def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor, style: Tensor, mask: Optional[Tensor] = None,
                    fields: Sequence[int] = (3, 5, 10, 11), temperature: float = 1.0, top_k: Optional[int] = 1,
-                   generator: Optional[torch.Generator] = None, teacher: Optional[Tensor] = None, use_graph: bool = True) -> Tensor:
+                   generator: Optional[torch.Generator] = None, teacher: Optional[Tensor] = None, use_graph: bool = True,
+                   start: int = 0, kv_init: Optional[Sequence[Tensor]] = None, return_kv: bool = False):
     """Fill `fields` of every note >= 1 of `perf` [B, T, F], note by note, for all B scores in lockstep.
 
     perf / masked_perf: int64 [B, T, F]; score_hidden fp32 [B, T, D]; style fp32 [B, T, S]; mask bool [B, T].
@@ -139,6 +140,9 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     used by the parity tests to compare every step independently); the returned tensor still holds the model's predictions.
     `use_graph`: capture one note-step in a CUDA graph and replay it (positions are device-side); sampling with a custom
     `generator` runs eagerly.
+    Continuation (the streaming `unmask_tokens` call): with `start = s > 0` the notes 0..s are complete in `perf`, `kv_init[l]` bf16
+    [B, s, 128] holds the keys | values of decoder positions < s for every layer, and only the positions s..T-2 run (notes s+1..T-1
+    are rendered).  `return_kv` also returns the per-layer caches [B, T, 128] (rows < T-1 valid).
     """
     te_mod, head = dec.token_emb, dec.lm_head
     B, T, F = perf.shape
@@ -164,6 +168,10 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     ctx16 = K.cast_bf16(score_hidden.float().contiguous().view(B * T, -1)).view(B, T, -1)
     km = None if mask is None else mask.contiguous()
     kv_caches = [torch.zeros((B, T, 128), dtype=BF16, device=dev) for _ in range(sw.depth)]
+    assert 0 <= start <= T - 1 and (start == 0 or (kv_init is not None and len(kv_init) == sw.depth))
+    for kv, init in zip(kv_caches, kv_init or ()):
+        assert init.shape == (B, start, 128)
+        kv[:, :start] = init
     out = perf.clone()
     feed = out if teacher is None else teacher
     cat_buf = torch.empty((B, 2 * dec.dim), dtype=BF16, device=dev)
@@ -171,7 +179,7 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
 
     # The position lives on the device: every index below is a device gather / scatter, so ONE captured step replays for
     # all T-1 notes (`use_graph`), instead of ~50 host launches per note.
-    pos_t = torch.zeros(1, dtype=torch.int64, device=dev)                    # i
+    pos_t = torch.full((1,), start, dtype=torch.int64, device=dev)           # i
     field_idx = torch.tensor(list(fields), dtype=torch.int64, device=dev)
     neg_inf = -float("inf")
 
@@ -300,12 +308,12 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
             out_rows.index_copy_(1, dst, torch.stack(toks, dim=1))
         pos_t.add_(1)
 
-    n_steps = T - 1
+    n_steps = T - 1 - start
     graph_ok = use_graph and generator is None and n_steps > 4
     if not graph_ok:
         for _ in range(n_steps):
             step()
-        return out
+        return (out, kv_caches) if return_kv else out
     # two eager steps warm every lazily-initialised path, then one step is captured and replayed for the rest
     step()
     step()
@@ -319,7 +327,7 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
     for _ in range(n_steps - 2):
         graph.replay()
     K.LAUNCHES += per_step * (n_steps - 2)       # ... each replay launches every recorded kernel
-    return out
+    return (out, kv_caches) if return_kv else out
 
 
 # ----------------------------------------------------------------------------- reference-signature entry points
@@ -384,16 +392,56 @@ def unmask_mixlm(wrapper, tokens: Tensor, tokens_masked: Tensor, temperature: fl
     T = out.shape[1]
     contiguous_tail = notes.numel() > 0 and int(notes[0]) >= 1 and torch.equal(notes, torch.arange(int(notes[0]), T, device=notes.device))
     uniform = bool(hit[:, notes][..., cols].all()) if notes.numel() else False
-    fast = (ks is not None and caches is None and not return_caches and not filter_key_ids and contiguous_tail and int(notes[0]) == 1
-            and uniform and context is not None and style is not None and len(set(ks)) == 1 and set(kwargs) <= {"context", "style_embeddings"})
+    expressible = (ks is not None and not filter_key_ids and contiguous_tail and uniform and context is not None and style is not None
+                   and len(set(ks)) == 1 and set(kwargs) <= {"context", "style_embeddings"})
+    fast = expressible and caches is None and not return_caches and int(notes[0]) == 1
+    kv_init = _streamable(dec, caches, int(notes[0]) - 1, context, style, T) if expressible and not fast else None
     if fast:
         res = render_decoder(dec, out, tokens_masked, context, style, mask=mask, fields=fields, temperature=temperature, top_k=ks[0])
+    elif kv_init is not None:
+        # the streaming call of inference/generators.py: a few new notes behind a prefix whose keys / values the caller holds.  Same
+        # device-resident note-step as a whole-window rendering (persistent stack kernel, fused heads + sampling), started at the
+        # first new note; eager launches, a chord is too short to pay for a graph capture
+        res, kvs = render_decoder(dec, out, tokens_masked, context, style, mask=mask, fields=fields, temperature=temperature,
+                                  top_k=ks[0], use_graph=False, start=int(notes[0]) - 1, kv_init=kv_init, return_kv=True)
+        caches = _kv_only_caches(dec, kvs, T - 1)
     else:
         res, caches = _unmask_stepwise(wrapper, out, tokens_masked, mask, notes, hit, temperature, filter_logits_fn, filter_kwargs,
                                        filter_key_ids, caches, kwargs)
     dec.train(was_training)
     res = res[0] if squeeze else res
     return (res, caches) if return_caches else res
+
+
+def _streamable(dec, caches, start: int, context: Tensor, style: Tensor, T: int):
+    """Per-layer [B, start, 128] keys | values if the request can continue on the device-resident note-step: nothing cached and the
+    first note is the one to render, or caches whose length is exactly the known prefix (the check inference/generators.py:222-226
+    makes as well).  None sends the request to the general stepper.  SPB_STREAM=legacy switches this path off."""
+    if K._os.environ.get("SPB_STREAM", "fused") != "fused" or context.shape[1] != T or style.shape[1] != T or start < 0:
+        return None
+    if caches is None:
+        return [] if start == 0 else None
+    att = caches.transformer.attention if caches.transformer is not None else None
+    if not att or len(att) != dec.transformer.depth or caches.token_emb.shape[1] != start or start == 0:
+        return None
+    if any(a.keys is None or a.values is None or a.keys.shape[-2] != start for a in att):
+        return None
+    return [torch.cat([a.keys, a.values], dim=-1).to(BF16).contiguous() for a in att]
+
+
+def _kv_only_caches(dec, kvs: Sequence[Tensor], length: int):
+    """Caches in the reference's layout (TupleTransformerCaches / TransformerIntermediates / AttentionIntermediates, every tensor
+    [B, length, .]) after a device-resident rendering.  Keys and values are views of the working buffers.  `token_emb` and `hiddens`
+    are ZERO placeholders of the right shapes: the cached step of this implementation needs the keys and values of the prefix and
+    the last position only (the reference recomputes emb_norm / project_emb over the whole prefix from `token_emb` at every step,
+    transformer.py:171-185, and carries the per-layer hiddens without reading them)."""
+    from .models.scoreperformer.transformer import TupleTransformerCaches
+    from .modules.transformer.attend import AttentionIntermediates
+    from .modules.transformer.transformer import TransformerIntermediates
+    B = kvs[0].shape[0]
+    z = torch.zeros((B, length, dec.dim), dtype=F32, device=kvs[0].device)
+    att = [AttentionIntermediates(keys=kv[:, :length, :64], values=kv[:, :length, 64:]) for kv in kvs]
+    return TupleTransformerCaches(token_emb=z, transformer=TransformerIntermediates(hiddens=[z] * (len(kvs) + 1), attention=att))
 
 
 def _unmask_stepwise(wrapper, out, tokens_masked, mask, notes, hit, temperature, filter_logits_fn, filter_kwargs, filter_key_ids, caches, kwargs):
