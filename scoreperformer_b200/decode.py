@@ -333,9 +333,10 @@ def render_decoder(dec, perf: Tensor, masked_perf: Tensor, score_hidden: Tensor,
 # ----------------------------------------------------------------------------- reference-signature entry points
 # `unmask_tokens` / `generate` of the LM wrappers (models/scoreperformer/wrappers.py:200-307, 324-407 of the reference) keep their
 # argument lists and their cache contract, so inference/generators.py works unchanged -- but they are adapters over this file:
-# a whole window goes through `render_batch`'s device-resident loop whenever the request is expressible there (any batch size,
-# top-k / greedy sampling, no incoming caches, no per-key bans); everything else runs the general stepper below, which advances
-# one note per iteration through the cached stack step (persistent kernel) and samples on the host side of the logits.
+# a window goes through `render_decoder`'s device-resident loop whenever the request is expressible there (any batch size,
+# top-k / greedy sampling, no per-key bans) -- from note 1 for a fresh window, or from the end of caller-held caches whose length
+# is the known prefix (the streaming calls of inference/generators.py); everything else runs the general stepper below, which
+# advances one note per iteration through the cached stack step and samples on the host side of the logits.
 def _sampling_plan(filter_logits_fn, filter_kwargs, sizes: Sequence[int], fields: Sequence[int]):
     """k per field if the filter is the reference's `top_k` (sampling.py:28-33), else None (host sampling)."""
     from .modules import sampling
