@@ -184,3 +184,66 @@ def test_cut_caches_views_and_window_helpers():
     assert resume_start(bars, 9, 64) == 0
     assert resume_start(bars, 9, 6) == 6                         # 9 - (4 + 1) < 6: the context restarts behind the change at 4
     assert overflow_shift(bars, 0, 6) == 5                       # 8 - 4 < 6: drop the five notes up to that bar change
+
+
+def _reference_root():
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "scoreperformer", "inference")):
+            return cand
+    return None
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="needs the unmodified reference (baseline/_ref or /root/reference)")
+def test_loop_around_the_reference_model_matches_the_reference_loop():
+    """Live, not from goldens: the UNMODIFIED reference model (default recipe, CPU fp32, cached `unmask_tokens`) rendered once by the
+    reference's generator + messenger and once by this package's -- same windows, caches handed back and forth between the reference's
+    cache classes and this loop's `cut_caches` -- must give identical tuples and messages."""
+    os.environ["SPB200_REFERENCE_ROOT"] = _reference_root()
+    import gen_inference_golden as ref
+    import ref_shim
+    from scoreperformer.modules.sampling import top_k as ref_top_k
+    ref_model, _ = ref_shim.build_reference_model(seed=23)
+    ref_model.eval()
+    piece = cases.make_piece(26, 41)
+    tick = (piece[:, 0] - 4) * 32 + (piece[:, 1] - 4)
+    onset = np.unique(tick, return_inverse=True)[1]
+    seg = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None]
+    perf = torch.from_numpy(piece)[None]
+    mask = torch.ones(perf.shape[:2], dtype=torch.bool)
+    with torch.inference_mode():
+        enc = ref_model.forward_encoders(perf=perf, perf_mask=mask, score=perf[..., :10].contiguous(), score_mask=mask, bars=seg(piece[:, 0]),
+                                         beats=seg(4 + tick // 8), onsets=seg(4 + onset), deadpan_mask=torch.zeros(1, dtype=torch.bool),
+                                         compute_loss=False)
+    pad = lambda e: torch.cat([e[0, :1], e[0], e[0, -1:]]).clone()
+    notes = np.concatenate([np.full_like(piece[:1], 2), piece, np.full_like(piece[:1], 3)])
+    notes[1:-1, [3, 5, 10, 11]] = 1
+
+    def render(generator_cls, messenger, tokenizer, interm_cls, max_context_len):
+        gen = generator_cls(ref_model, cases.make_dataset(tokenizer, [piece]), cases.make_collator(), messenger, device="cpu")
+        pd = gen.perf_data
+        pd.perf_seq, pd.notes = piece, torch.from_numpy(notes.copy())
+        pd.context, pd.embeddings = pad(enc.score_embeddings), pad(enc.perf_embeddings)
+        pd.intermediates = interm_cls(initial_tempo=96.)
+        t, messages = 0., []
+        for _ in range(150):
+            _, m = gen.generate_performance_notes(start_time=t, time_window=0.5, max_context_len=max_context_len,
+                                                  filter_logits_fn=ref_top_k, filter_kwargs={"k": 1})
+            if len(m):
+                messages.append(np.asarray(m))
+            t += 0.5
+            if pd.reached_eos:
+                break
+        # (a context shorter than 8 x the largest chord can stall the reference's loop for good -- generators.py:199-200 -- so the
+        # end of the piece is only required of the full context)
+        assert pd.reached_eos or max_context_len < 512
+        return pd.gen_seq.numpy(), np.concatenate(messages)
+
+    ref_tok = ref._ref_tokenizer(ref.SPMuple2)
+    tables = TokenTables(**cases.table_kwargs())
+    for ctx in (512, 20):                                  # 20: the context is truncated at bar starts and the caches are dropped
+        want_tokens, want_messages = render(ref.ScorePerformerGenerator, ref.SPMuple2Messenger(ref_tok), ref_tok,
+                                            ref.SPMuple2IntermediateData, ctx)
+        got_tokens, got_messages = render(ScorePerformerGenerator, SPMuple2Messenger(tables), tables, SPMuple2IntermediateData, ctx)
+        same(got_tokens, want_tokens, f"tokens (context {ctx})")
+        same(got_messages, want_messages, f"messages (context {ctx})")
+        assert got_tokens.shape[0] >= 16 and not (got_tokens == 1).any()
