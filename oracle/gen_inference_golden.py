@@ -135,6 +135,17 @@ def messenger_goldens():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "inference_messenger.npz"), **out)
 
 
+def encode_goldens():
+    out = {}
+    for name in cases.ENCODE_CASES:
+        r = cases.run_encode_case(name, ScorePerformerGenerator, SPMuple2Messenger, _ref_tokenizer(SPMuple2))
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+        print(name, len(r["windows"]), "windows served,", len(r["calls"]), "encoder calls,", r["score"].shape[0], "embedding rows")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "inference_encode.npz"), **out)
+
+
 if __name__ == "__main__":
+    encode_goldens()
     generator_goldens()
     messenger_goldens()

@@ -205,3 +205,95 @@ def random_chunks(seed: int, n_notes: int = 160, metre_change: bool = False):
         i += int(rng.integers(1, 10))
         cuts.append(min(i, n_notes))
     return piece, cuts
+
+
+# ----------------------------------------------------------------------------- encode_embeddings: a dataset that serves bar windows
+class _Scores(list):
+    _name_to_idx = {"score0": 0}
+
+
+class BarWindowDataset:
+    """What `ScorePerformerGenerator.encode_embeddings` touches of a ScorePerformanceDataset: whole-bar windows of one score / performance
+    pair (`get(meta=...)` with `meta.start_bar` / `meta.end_bar`, SOS before bar 0, EOS behind the last bar), the bar index, the
+    window limits and the segment maps."""
+
+    def __init__(self, tokenizer, piece: np.ndarray, max_seq_len: int, max_bar: int):
+        self.tokenizer, self.max_seq_len, self.max_bar = tokenizer, max_seq_len, max_bar
+        self.processor = Processor()
+        self.performance_names, self._performance_map = ["perf0"], {"perf0": ("score0", None)}
+        self.scores, self.performances = _Scores([piece[:, :10].copy()]), [piece]
+        self.initial_tempos = {"perf0": 96.}
+        self._score_indices = [None]
+        tick = (piece[:, 0] - ZERO) * 32 + (piece[:, 1] - ZERO)
+        self._beat_maps, self._onset_maps = [ZERO + tick // 8], [ZERO + np.unique(tick, return_inverse=True)[1]]
+        self.indexer = SimpleNamespace(compute_bar_indices=self._bar_indices)
+        self.windows = []
+
+    @staticmethod
+    def _bar_indices(seq):
+        bars = seq[:, 0] - ZERO
+        first = np.searchsorted(bars, np.arange(bars[-1] + 1), side="left")       # first note of every bar (empty bars: the next note)
+        return np.concatenate([first, [len(bars)]]).astype(np.int64)
+
+    def get(self, meta):
+        idx = self._score_indices[0]
+        lo, hi = int(idx[meta.start_bar]), int(idx[meta.end_bar + 1])
+        self.windows.append((int(meta.start_bar), int(meta.end_bar), lo, hi))
+        score, perf = self.scores[0][lo:hi], self.performances[0][lo:hi]
+        if meta.start_bar == 0:
+            score, perf = self.processor.add_sos_token(score), self.processor.add_sos_token(perf)
+        if meta.end_bar + 1 >= len(idx) - 1:
+            score, perf = self.processor.add_eos_token(score), self.processor.add_eos_token(perf)
+        return SimpleNamespace(score=score, perf=perf, lo=lo)
+
+
+class EncoderStub:
+    """`model` for encode_embeddings: the embeddings are the (bar-shifted) tokens themselves, so that what comes back shows which notes
+    of which window were kept and how their bars had been moved."""
+
+    def __init__(self, dataset):
+        self.perf_decoder, self.score_encoder = object(), object()
+        self.perf_encoder = SimpleNamespace(embeddings_to_latents=self._latents)
+        self.dataset, self.calls = dataset, []
+
+    def prepare_inputs(self, x):
+        return x
+
+    def allocate_inputs(self, x, device):
+        return x
+
+    def forward_encoders(self, score, score_mask, perf, perf_mask, bars, beats, onsets, deadpan_mask, compute_loss):
+        assert compute_loss is False
+        self.calls.append([score.shape[1], digest(score[0].numpy()), digest(perf[0].numpy())])
+        return SimpleNamespace(score_embeddings=score[..., :3].float(), perf_embeddings=perf[..., [0, 1, 10]].float() + 0.5)
+
+    @staticmethod
+    def _latents(embeddings, bars, beats, onsets):
+        return torch.stack([embeddings.sum(), bars.float().sum(), beats.float().sum(), onsets.float().sum(),
+                            torch.tensor(float(bars.shape[1]))])
+
+
+def window_collator(samples):
+    (s,) = samples
+    score, perf = torch.from_numpy(s.score.copy())[None], torch.from_numpy(s.perf.copy())[None]
+    ones = torch.ones(score.shape[:2], dtype=torch.bool)
+    seg = torch.arange(score.shape[1])[None] + ZERO
+    return dict(score=score, score_mask=ones, perf=perf, perf_mask=ones.clone(), bars=seg, beats=seg.clone(), onsets=seg.clone(),
+                deadpan_mask=torch.zeros(1, dtype=torch.bool))
+
+
+ENCODE_CASES = {"abutting": dict(overlay_bars=0., max_seq_len=40, max_bar=6), "overlapping": dict(overlay_bars=0.5, max_seq_len=90, max_bar=64),
+                "one_window": dict(overlay_bars=0.5, max_seq_len=4000, max_bar=256)}
+
+
+def run_encode_case(name, generator_cls, messenger_cls, tokenizer):
+    kw = ENCODE_CASES[name]
+    piece = make_piece(180, 21)
+    ds = BarWindowDataset(tokenizer, piece, kw["max_seq_len"], kw["max_bar"])
+    model = EncoderStub(ds)
+    collator = window_collator
+    collator.mask_token_id, collator.mask_ignore_token_dims = 1, [0, 1, 2, 4, 6, 7, 8, 9]
+    gen = generator_cls(model, ds, collator, messenger_cls(tokenizer), device="cpu")
+    score_emb, perf_emb, latents = gen.encode_embeddings(0, compute_latents=True, overlay_bars=kw["overlay_bars"])
+    return dict(score=score_emb.numpy(), perf=perf_emb.numpy(), latents=latents.numpy(), calls=np.array(model.calls, dtype=np.int64),
+                windows=np.array(ds.windows, dtype=np.int64))

@@ -247,3 +247,14 @@ def test_loop_around_the_reference_model_matches_the_reference_loop():
         same(got_tokens, want_tokens, f"tokens (context {ctx})")
         same(got_messages, want_messages, f"messages (context {ctx})")
         assert got_tokens.shape[0] >= 16 and not (got_tokens == 1).any()
+
+
+@pytest.mark.parametrize("name", list(cases.ENCODE_CASES))
+def test_encode_embeddings_matches_reference(name):
+    """`encode_embeddings` (generators.py:320-426): the windows asked of the dataset, the bar-shifted inputs of every encoder call, the
+    embedding rows kept from every window (abutting windows, half-overlapping windows, one window) and the latents call."""
+    g = np.load(os.path.join(GOLDEN, "inference_encode.npz"))
+    r = cases.run_encode_case(name, ScorePerformerGenerator, SPMuple2Messenger, TokenTables(**cases.table_kwargs()))
+    for k, v in r.items():
+        same(v, g[f"{name}/{k}"], f"{name} {k}")
+    assert r["score"].shape[0] == 182 and (len(r["windows"]) > 1) == (name != "one_window")
