@@ -16,7 +16,8 @@ from typing import Optional
 
 import numpy as np
 
-from .token_tables import DEFAULT_TEMPO, NOTE_ON_MIDI_EVENT
+from . import native
+from .token_tables import DEFAULT_TEMPO, NOTE_ON_MIDI_EVENT, TokenTables
 
 
 @dataclass
@@ -169,11 +170,9 @@ class SPMuple2Messenger(SPMupleMessenger):
 
         state = intermediates if intermediates is not None else SPMuple2IntermediateData()
         tempos = state.tempos if state.tempos is not None else np.array([[state.initial_tempo, 0, 0.]])
-        bpm = tempos[-1, 0]
         pairs = state.onset_pairs
         if pairs is None:                                  # an anchor one tick before the piece unless it starts late
-            pairs = np.array([(0, 0, 1)]) if ticks[0] > 0 else np.array([(-1, -1 / bpm * scale, 1)])
-        last_tick, last_time, last_n = pairs[-1]
+            pairs = np.array([(0, 0, 1)]) if ticks[0] > 0 else np.array([(-1, -1 / tempos[-1, 0] * scale, 1)])
 
         # notes of every onset, in note order (stable), visited in increasing tick order
         order = np.argsort(ticks, kind="stable")
@@ -182,6 +181,27 @@ class SPMuple2Messenger(SPMupleMessenger):
 
         n = len(ticks)
         on, off = np.zeros(n), np.zeros(n)
+        h = native.lib() if isinstance(tok, TokenTables) else None      # other tokenizers keep their own tempo helpers
+        if h is not None:
+            tempos, pairs = self._recurrence_native(h, tok, p, state, tempos, pairs, order, starts, ticks, durations, note_bpm, rel_dev,
+                                                    rel_held, performed, scale, from_tokens, re_estimate, on, off)
+        else:
+            tempos, pairs = self._recurrence(tok, p, state, tempos, pairs, groups, ticks, durations, note_bpm, rel_dev, rel_held,
+                                             performed, scale, from_tokens, re_estimate, on, off)
+
+        messages = self._pack(tokens, on, off, note_attributes, note_on_events, note_off_events)
+        if sort:
+            messages = self.sort_messages(messages)
+        if not return_intermediates:
+            return messages
+        return messages, SPMuple2IntermediateData(tempos=tempos, initial_tempo=state.initial_tempo, onset_pairs=pairs)
+
+    @staticmethod
+    def _recurrence(tok, p, state, tempos, pairs, groups, ticks, durations, note_bpm, rel_dev, rel_held, performed, scale, from_tokens,
+                    re_estimate, on, off):
+        """The recurrence over performed onsets, in numpy: the definition csrc/onset_times.c is tested against."""
+        bpm = tempos[-1, 0]
+        last_tick, last_time, last_n = pairs[-1]
         for members in groups:
             live = performed[members]
             if not live.any():
@@ -220,10 +240,39 @@ class SPMuple2Messenger(SPMupleMessenger):
             else:
                 tempos = np.concatenate([tempos, np.array([[bpm, tick, onset_time]])])
                 last_tick, last_time, last_n = tick, onset_time, count
+        return tempos, pairs
 
-        messages = self._pack(tokens, on, off, note_attributes, note_on_events, note_off_events)
-        if sort:
-            messages = self.sort_messages(messages)
-        if not return_intermediates:
-            return messages
-        return messages, SPMuple2IntermediateData(tempos=tempos, initial_tempo=state.initial_tempo, onset_pairs=pairs)
+    @staticmethod
+    def _recurrence_native(h, tok, p, state, tempos, pairs, order, starts, ticks, durations, note_bpm, rel_dev, rel_held, performed, scale,
+                           from_tokens, re_estimate, on, off):
+        """The same recurrence in C (include/spb200_host.h).  The state arrays are copied into buffers with room for one row per onset;
+        when the first performed onset continued the incoming state's last onset, the overwritten last rows are mirrored into the
+        caller's arrays, which is what the in-place assignments of the numpy path (and of the reference) do."""
+        import ctypes
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        n_groups = len(starts)
+        bounds = np.ascontiguousarray(np.concatenate([starts, [len(order)]]), dtype=np.int64)
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        nt, npair = tempos.shape[0], pairs.shape[0]
+        tbuf, pbuf = np.zeros((nt + n_groups, 3)), np.zeros((npair + n_groups, 3))
+        tbuf[:nt], pbuf[:npair] = tempos, pairs
+        arrs = [f64(ticks), f64(durations), f64(note_bpm), f64(rel_dev), f64(rel_held), np.ascontiguousarray(performed, dtype=np.uint8)]
+        table = f64(tok.tempos)
+        out_t, out_p, resumed = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        ptr = lambda a: a.ctypes.data
+        rc = h.spb_host_onset_times(len(arrs[0]), *(ptr(a) for a in arrs), ptr(order), n_groups, ptr(bounds), ptr(tbuf), nt, ptr(pbuf),
+                                    npair, float(scale), float(state.initial_tempo), int(bool(from_tokens)), int(bool(re_estimate)),
+                                    float(p.get("tempo_min_onset_dist", 0.)), float(p.get("tempo_window", 0.)),
+                                    int(p.get("tempo_min_onsets", 0)), int(bool(tok.use_tempos and p.get("use_quantized_tempos", False))),
+                                    ptr(table), len(table), ptr(on), ptr(off), ctypes.byref(out_t), ctypes.byref(out_p),
+                                    ctypes.byref(resumed))
+        if rc == -3:
+            raise IndexError("an onset continues the previous chunk but the tempo state holds a single row")
+        if rc != 0:
+            raise RuntimeError(f"spb_host_onset_times failed ({rc})")
+        if resumed.value:
+            tempos[-1], pairs[-1] = tbuf[nt - 1], pbuf[npair - 1]
+        if out_t.value == nt and out_p.value == npair:     # nothing appended: the numpy path hands the caller's arrays back
+            return tempos, pairs
+        return tbuf[:out_t.value], pbuf[:out_p.value]
+

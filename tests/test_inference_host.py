@@ -258,3 +258,44 @@ def test_encode_embeddings_matches_reference(name):
     for k, v in r.items():
         same(v, g[f"{name}/{k}"], f"{name} {k}")
     assert r["score"].shape[0] == 182 and (len(r["windows"]) > 1) == (name != "one_window")
+
+
+def test_host_library_exports_header_and_matches_numpy_on_long_pieces(monkeypatch):
+    """include/spb200_host.h == the symbols of libspb200_host.so, and the C recurrence equals the numpy statement bit for bit on pieces
+    long enough that the local-tempo sums run over hundreds of onsets (numpy's pairwise blocks and recursion), fed whole and in chunks
+    that split chords, for every tempo mode."""
+    import re
+    from scoreperformer_b200.inference import native
+    native.build()
+    handle = native.lib()
+    assert handle is not None, "libspb200_host.so missing: run __graft_entry__.build()"
+    header = open(os.path.join(ROOT, "include", "spb200_host.h")).read()
+    declared = set(re.findall(r"\b(spb_host_\w+)\s*\(", header))
+    assert declared == {"spb_host_abi_version", "spb_host_onset_times"}
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in spb200_host.h but not exported"
+
+    def decode(piece, cuts, params):
+        msgr = SPMuple2Messenger(TokenTables(**cases.table_kwargs(**params)))
+        state, lo, out = None, 0, []
+        for hi in cuts:
+            m, state = msgr.tokens_to_messages(piece[lo:hi].copy(), intermediates=state, return_intermediates=True)
+            out.append(m)
+            lo = hi
+        return np.concatenate(out), state.tempos, state.onset_pairs
+
+    rng = np.random.default_rng(9)
+    for params in ({}, dict(tempo_window=1e9, tempo_min_onsets=300), dict(use_quantized_tempos=False, tempo_window=60.),
+                   dict(decode_recompute_tempos=False), dict(onset_tempos=True)):
+        piece = cases.make_piece(1500, int(rng.integers(1000)))
+        cuts, i = [], 0
+        while i < len(piece):
+            i += int(rng.integers(1, 400))
+            cuts.append(min(i, len(piece)))
+        for c in (cuts, [len(piece)]):
+            monkeypatch.setenv("SPB_HOST_NATIVE", "1")
+            got = decode(piece, c, params)
+            monkeypatch.setenv("SPB_HOST_NATIVE", "0")
+            want = decode(piece, c, params)
+            for a, b, what in zip(got, want, ("messages", "tempo map", "onset pairs")):
+                same(a, b, f"{what} {params}")
