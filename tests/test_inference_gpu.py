@@ -28,7 +28,11 @@ def _piece(T, seed):
     return batch, perf
 
 
-def test_windowed_rendering_on_device_equals_uninterrupted_rendering():
+@pytest.mark.parametrize("stream", ["fused", "legacy"])
+def test_windowed_rendering_on_device_equals_uninterrupted_rendering(stream, monkeypatch):
+    # fused: `unmask_tokens` continues the caller-held caches on the device-resident note-step; legacy: the general cached stepper
+    # (the path a request takes that the note-step cannot express) -- both must satisfy the same contract
+    monkeypatch.setenv("SPB_STREAM", stream)
     from scoreperformer_b200.decode import render_batch
     from scoreperformer_b200.inference import ScorePerformerGenerator, SPMuple2IntermediateData, SPMuple2Messenger, TokenTables
     from scoreperformer_b200.modules.sampling import top_k
