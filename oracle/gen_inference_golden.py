@@ -145,7 +145,24 @@ def encode_goldens():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "inference_encode.npz"), **out)
 
 
+def vocabulary_goldens():
+    """The SPMuple-specific bins from the reference's own constructors (the miditok-made tables cannot be produced here)."""
+    out = {}
+    for family, base in (("spm", SPMuple), ("spm2", SPMuple2)):
+        for n_dev, n_dur, res in ((161, 81, 16), (81, 41, 8)):
+            stub = base.__new__(base)
+            stub._max_beat_res = res
+            stub.config = SimpleNamespace(additional_params={"nb_onset_devs": n_dev, "nb_perf_durations": n_dur})
+            tag = f"{family}/{n_dev}_{n_dur}_{res}"
+            out[f"{tag}/position_shifts"] = stub._create_position_shifts()
+            out[f"{tag}/rel_onset_deviations"] = stub._create_relative_onset_deviations()
+            out[f"{tag}/rel_performed_durations"] = stub._create_relative_performed_durations()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "inference_vocab.npz"), **out)
+    print("vocabulary bins:", {k: v.shape[0] for k, v in out.items() if "161" in k})
+
+
 if __name__ == "__main__":
+    vocabulary_goldens()
     encode_goldens()
     generator_goldens()
     messenger_goldens()

@@ -196,6 +196,68 @@ class TokenTables:
                    additional_params=dict(tok.config.additional_params), use_tempos=bool(tok.config.use_tempos),
                    spmuple2=is_spmuple2(tok), zero_token=int(tok.zero_token))
 
+    @classmethod
+    def from_preset(cls, preset) -> "TokenTables":
+        """Build the tables from a tokenizer preset of the reference (`data/tokenizers/spmuple_*.json`: a path or the parsed dict)
+        without `miditok`.
+
+        The SPMuple-specific bins restate the reference (`_create_position_shifts`, `_create_relative_onset_deviations`,
+        `_create_relative_performed_durations`: spmuple/spmuple.py:653-720, spmuple/spmuple2.py:491-546; field order:
+        common/octuple_m.py:295-345 + spmuple/spmuple.py:627-651) and are checked against those methods.  Velocities, durations,
+        tempi and time signatures come from the third-party `miditok` (pinned 2.1.6 in the presets, not vendored in the
+        reference): its published construction is restated here -- velocities `linspace(0, 127, n + 1)[1:]`, one duration per
+        (beat, sample) of every `beat_res` range plus the closing one, `geomspace` / `linspace` tempi rounded to 2 decimals, time
+        signatures in the order of `time_signature_range` -- and is pinned only by the vocabulary sizes it yields."""
+        if isinstance(preset, str):
+            import json
+            with open(preset) as f:
+                preset = json.load(f)
+        cfg, family = preset["config"], preset.get("tokenization", "SPMuple2")
+        p = dict(cfg["additional_params"])
+        spm2 = family in ("SPMuple2", "SPMupleOnset", "SPMupleWindow", "SPMupleWindowRecompute")
+        # what the encodings set on top of the stored parameters (spmuple/encodings.py)
+        p.update({"use_position_shifts": True, "use_onset_indices": True})
+        if family in ("SPMupleBeat", "SPMupleBar"):
+            p.update({"rel_onset_dev": True, "rel_perf_duration": True, "bar_tempos": family == "SPMupleBar"})
+        if family == "SPMupleOnset":
+            p["onset_tempos"] = True
+        if family == "SPMupleWindow":
+            p.update({"use_quantized_tempos": True, "decode_recompute_tempos": False})
+        if family == "SPMupleWindowRecompute":
+            p.update({"use_quantized_tempos": p.get("use_quantized_tempos", True), "decode_recompute_tempos": True})
+
+        ranges = {tuple(int(v) for v in k.split("_")) if isinstance(k, str) else tuple(k): int(r) for k, r in cfg["beat_res"].items()}
+        res = max(ranges.values())
+        durations = [(beat, pos, r) for rng, r in ranges.items() for beat in range(*rng) for pos in range(r)]
+        last = max(ranges)
+        durations.append((max(last), 0, ranges[last]))
+        durations = [(0, 0, durations[1][-1])] + durations[1:]                   # miditok drops the zero duration, OctupleM adds one back
+        duration_values = np.array([(b * r + q) / r if r > 0 else 0 for b, q, r in durations])
+        velocities = np.concatenate([[0], np.linspace(0, 127, cfg["nb_velocities"] + 1, dtype=np.intc)[1:]])
+        spacing = np.geomspace if cfg.get("log_tempos", False) else np.linspace
+        tempos = spacing(*cfg["tempo_range"], cfg["nb_tempos"]).round(2)
+        metres = np.array([(int(n), int(d)) for d, beats in cfg["time_signature_range"].items() for n in beats])
+        n_positions = int(max(np.ceil(4 * metres[:, 0] / metres[:, 1]))) * res
+
+        shifts = np.concatenate([np.arange(0, 2 * res, 1), np.arange(2 * res, 4 * res, 2), np.arange(4 * res, 8 * res, 8),
+                                 np.arange(8 * res, 16 * res + 1, 16)])
+        rel_dev, rel_dur = _relative_bins(p["nb_onset_devs"], p["nb_perf_durations"], spm2)
+
+        names = ["Bar", "Position", "Pitch", "Velocity", "Duration"] + (["Tempo"] if cfg["use_tempos"] else []) \
+            + (["TimeSig"] if cfg["use_time_signatures"] else []) + (["Program"] if cfg.get("use_programs") else []) \
+            + ["PositionShift", "NotesInOnset", "PositionInOnset"] \
+            + ["RelOnsetDev" if p["rel_onset_dev"] else "OnsetDev", "RelPerfDuration" if p["rel_perf_duration"] else "PerfDuration"]
+        counts = {"Bar": p["max_bar_embedding"], "Position": n_positions, "Pitch": cfg["pitch_range"][1] - cfg["pitch_range"][0],
+                  "Velocity": len(velocities), "Duration": len(durations), "Tempo": len(tempos), "TimeSig": len(metres),
+                  "Program": len(cfg.get("programs", [])), "PositionShift": len(shifts), "NotesInOnset": p["max_notes_in_onset"],
+                  "PositionInOnset": p["max_notes_in_onset"], "RelOnsetDev": len(rel_dev), "OnsetDev": 4 * res + 1,
+                  "RelPerfDuration": len(rel_dur), "PerfDuration": len(durations)}
+        zero = len(cfg.get("special_tokens", SPECIAL_TOKENS))
+        return cls(vocab_types_idx={k: i for i, k in enumerate(names)}, sizes={k: counts[k] + zero for k in names}, beat_res=res,
+                   pitch_min=int(cfg["pitch_range"][0]), velocities=velocities, duration_values=duration_values, tempos=tempos,
+                   time_signatures=metres, position_shifts=shifts, rel_onset_deviations=rel_dev, rel_performed_durations=rel_dur,
+                   additional_params=p, use_tempos=bool(cfg["use_tempos"]), spmuple2=spm2, zero_token=zero)
+
     _ARRAYS = ("velocities", "duration_values", "tempos", "time_signatures", "position_shifts", "rel_onset_deviations",
                "rel_performed_durations")
 
@@ -213,3 +275,29 @@ class TokenTables:
         with np.load(path) as z:
             meta = json.loads(bytes(z["meta"]).decode())
             return cls(**meta, **{k: z[k] for k in cls._ARRAYS if k in z.files})
+
+
+def _relative_bins(n_dev: int, n_dur: int, spm2: bool):
+    """Bins of the RelOnsetDev / RelPerfDuration fields: piecewise linear near zero / one, geometric in the tails, rounded to four
+    decimals; onset deviations mirrored to negative values (spmuple/spmuple.py:668-720 for SPMuple, spmuple/spmuple2.py:491-546 for
+    SPMuple2 -- the two families place their breakpoints differently)."""
+    lin, steps = np.linspace, np.arange
+    if spm2:
+        q = (n_dev - 1) // 10
+        log32, log43 = np.log(3 / 2) / np.log(2), np.log(4 / 3) / np.log(2)
+        dev = [lin(0, 1 / 20, q + 1), lin(1 / 20, 1 / 10, q + 1)[1:], lin(1 / 10, 1 / 6, q + 1)[1:],
+               (2 ** (steps(q + 1) / q) * 1 / 6)[1:], (2 ** (log32 * steps(q // 2 + 1) / q * 2) * 1 / 3)[1:],
+               (2 ** (log32 * steps(q // 4 + 1) / q * 4) * 1 / 2)[1:], (2 ** (log43 * steps(q // 8 + 1) / q * 8) * 3 / 4)[1:],
+               (2 ** (steps(q // 8 + 1) / q * 8))[1:]]
+        d = (n_dur - 1) // 5
+        dur = [lin(1 / 10, 1 / 3, d + 1), lin(1 / 3, 4 / 5, 2 * d + 1)[1:], lin(4 / 5, 1., d + 1)[1:], lin(1.0, 5 / 4, d // 2 + 1)[1:],
+               lin(5 / 4, 3 / 2, d // 4 + 1)[1:], (2 ** (4 * steps(d // 4 + 1) / d) * 3 / 2)[1:]]
+    else:
+        q = (n_dev - 1) // 8
+        dev = [lin(0.0, 1 / 24, q + 1), lin(1 / 24, 1 / 8, q + 1)[1:], lin(1 / 8, 1 / 3, q + 1)[1:], lin(1 / 3, 3 / 5, q // 2 + 1)[1:],
+               lin(3 / 5, 1.0, q // 4 + 1)[1:], (2 ** (8 * steps(q // 4 + 1) / q))[1:]]
+        d = (n_dur - 1) // 4
+        dur = [lin(1 / 10, 2 / 5, d + 1), lin(2 / 5, 2 / 3, d + 1)[1:], lin(2 / 3, 1.0, d + 1)[1:], lin(1.0, 5 / 4, d // 2 + 1)[1:],
+               lin(5 / 4, 3 / 2, d // 4 + 1)[1:], (2 ** (4 * steps(d // 4 + 1) / d) * 3 / 2)[1:]]
+    dev = np.round(np.concatenate(dev), 4)
+    return np.sort(np.concatenate([-dev[1:], dev])), np.round(np.concatenate(dur), 4)

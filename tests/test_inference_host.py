@@ -299,3 +299,43 @@ def test_host_library_exports_header_and_matches_numpy_on_long_pieces(monkeypatc
             want = decode(piece, c, params)
             for a, b, what in zip(got, want, ("messages", "tempo map", "onset pairs")):
                 same(a, b, f"{what} {params}")
+
+
+PRESET = {  # the fields of the reference's data/tokenizers/spmuple_window.json that the tables depend on
+    "tokenization": "SPMupleWindow", "miditok_version": "2.1.6",
+    "config": {"pitch_range": [21, 109], "beat_res": {"0_2": 16, "2_4": 8, "4_8": 4, "8_16": 2, "16_64": 1}, "nb_velocities": 127,
+               "special_tokens": ["PAD", "MASK", "SOS", "EOS"], "use_tempos": True, "use_time_signatures": True, "use_programs": False,
+               "nb_tempos": 121, "tempo_range": [15, 480], "log_tempos": True, "programs": [0],
+               "time_signature_range": {"2": [1, 2, 3, 4], "4": [1, 2, 3, 4, 5, 6], "8": [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]},
+               "additional_params": {"nb_onset_devs": 161, "nb_perf_durations": 81, "max_bar_embedding": 256, "rel_onset_dev": True,
+                                     "rel_perf_duration": True, "real_max_bar_embedding": 256, "use_position_shifts": True,
+                                     "onset_position_shifts": True, "use_onset_indices": True, "max_notes_in_onset": 12,
+                                     "bar_tempos": False, "onset_tempos": False, "tempo_window": 8.0, "tempo_min_onset_dist": 0.5,
+                                     "tempo_min_onsets": 8, "use_quantized_tempos": True, "decode_recompute_tempos": False}}}
+
+
+def test_tables_from_a_tokenizer_preset():
+    """`TokenTables.from_preset`: vocabulary sizes of SURVEY Appendix A.1 (sum 1251), the SPMuple / SPMuple2 bins equal to the
+    reference constructors' (goldens), and a piece decodes through the messenger with the resulting tables."""
+    import copy
+    g = np.load(os.path.join(GOLDEN, "inference_vocab.npz"))
+    t = TokenTables.from_preset(copy.deepcopy(PRESET))
+    assert list(t.sizes.values()) == [260, 132, 92, 132, 133, 125, 26, 69, 16, 16, 165, 85] and list(t.vocab_types_idx) == cases.FIELDS
+    assert t.spmuple2 and t.beat_res == 16 and t.additional_params["decode_recompute_tempos"] is False
+    assert t.tempos[0] == 15. and t.tempos[-1] == 480. and t.velocities[0] == 0 and t.velocities[-1] == 127
+    assert t.duration_values[0] == 0 and t.duration_values[1] == 1 / 16 and t.duration_values[-1] == 64
+    for family, spm2 in (("spm", False), ("spm2", True)):
+        for n_dev, n_dur, res, div in ((161, 81, 16, 1), (81, 41, 8, 2)):
+            preset = copy.deepcopy(PRESET)
+            preset["tokenization"] = "SPMupleWindow" if spm2 else "SPMupleBeat"
+            preset["config"]["additional_params"].update(nb_onset_devs=n_dev, nb_perf_durations=n_dur)
+            preset["config"]["beat_res"] = {k: max(1, v // div) for k, v in PRESET["config"]["beat_res"].items()}
+            tt = TokenTables.from_preset(preset)
+            tag = f"{family}/{n_dev}_{n_dur}_{res}"
+            same(tt.position_shifts, g[f"{tag}/position_shifts"], f"{tag} position shifts")
+            same(tt.rel_onset_deviations, g[f"{tag}/rel_onset_deviations"], f"{tag} onset deviations")
+            same(tt.rel_performed_durations, g[f"{tag}/rel_performed_durations"], f"{tag} performed durations")
+    piece = cases.make_piece(120, 8)
+    piece[:, 1] = 4 + (piece[:, 1] - 4) * 2                         # the 8-per-beat grid of the synthetic piece on this 16-per-beat one
+    messages = SPMuple2Messenger(t).tokens_to_messages(piece)
+    assert messages.shape == (240, 4) and np.isfinite(messages).all() and np.all(np.diff(messages[:, 0]) >= 0)
