@@ -339,3 +339,40 @@ def test_tables_from_a_tokenizer_preset():
     piece[:, 1] = 4 + (piece[:, 1] - 4) * 2                         # the 8-per-beat grid of the synthetic piece on this 16-per-beat one
     messages = SPMuple2Messenger(t).tokens_to_messages(piece)
     assert messages.shape == (240, 4) and np.isfinite(messages).all() and np.all(np.diff(messages[:, 0]) >= 0)
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="needs the unmodified reference (baseline/_ref or /root/reference)")
+def test_random_renderings_match_the_reference_loop_live():
+    """Beyond the four goldens: random pieces, contexts, window lengths, chord grouping, style deltas, cache use, tempo modes and
+    masked field sets, rendered live by the reference's generator + messenger and by this package's around the stand-in decoder --
+    every decoder call and every window must agree exactly."""
+    os.environ["SPB200_REFERENCE_ROOT"] = _reference_root()
+    import gen_inference_golden as ref
+    rng = np.random.default_rng(2024)
+    names = []
+    for i in range(14):
+        params = [{}, dict(decode_recompute_tempos=False), dict(onset_tempos=True), dict(use_quantized_tempos=False, tempo_window=3.)][i % 4]
+        ignore = (0, 1, 2, 4, 6, 7, 8, 9) if i % 3 else (0, 1, 2, 4, 5, 6, 7, 8, 9)
+        gen_kw = dict(max_context_len=int(rng.choice([24, 40, 64, 512])), group_chord_notes=bool(rng.random() < 0.7),
+                      time_window_overflow=float(rng.choice([0., 0.1, 0.3])), disable_caches=bool(rng.random() < 0.2),
+                      delta=bool(rng.random() < 0.4), sort_messages=bool(rng.random() < 0.5))
+        name = f"fuzz{i}"
+        cases.SCENARIOS[name] = (dict(n_notes=int(rng.integers(40, 160)), seed=int(rng.integers(1000))), params, ignore, gen_kw,
+                                 float(rng.choice([0.25, 0.5, 1.0, 2.5])), "spm2")
+        names.append(name)
+    try:
+        for name in names:
+            params = cases.SCENARIOS[name][1]
+            want = cases.run_scenario(name, ref.ScorePerformerGenerator, ref.SPMuple2Messenger, ref._ref_tokenizer(ref.SPMuple2, **params),
+                                      ref.REF_CACHES, ref.SPMuple2IntermediateData)
+            got = cases.run_scenario(name, ScorePerformerGenerator, SPMuple2Messenger, TokenTables(**cases.table_kwargs(**params)),
+                                     (Caches, Inter, Attn), SPMuple2IntermediateData)
+            assert len(got[0]) == len(want[0]), (name, cases.SCENARIOS[name])
+            for i, (a, b) in enumerate(zip(got[0], want[0])):
+                for k in a:
+                    same(a[k], b[k], f"{name} {cases.SCENARIOS[name]} window {i} {k}")
+            for k in got[1]:
+                same(got[1][k], want[1][k], f"{name} final {k}")
+    finally:
+        for name in names:
+            cases.SCENARIOS.pop(name, None)
