@@ -376,3 +376,45 @@ def test_random_renderings_match_the_reference_loop_live():
     finally:
         for name in names:
             cases.SCENARIOS.pop(name, None)
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="needs the unmodified reference (baseline/_ref or /root/reference)")
+def test_random_messenger_configurations_match_the_reference_live():
+    """Random tempo / shift / deviation settings, metre changes and chunkings through the reference's messengers and this package's
+    (C recurrence and numpy statement): messages, tick messages and carried state identical."""
+    os.environ["SPB200_REFERENCE_ROOT"] = _reference_root()
+    import gen_inference_golden as ref
+    rng = np.random.default_rng(77)
+    for i in range(16):
+        spm2 = i % 2 == 0
+        params = dict(decode_recompute_tempos=bool(rng.random() < 0.6), onset_tempos=bool(rng.random() < 0.25),
+                      use_quantized_tempos=bool(rng.random() < 0.5), tempo_window=float(rng.choice([1., 4., 8., 1e6])),
+                      tempo_min_onsets=int(rng.choice([2, 8, 40])), tempo_min_onset_dist=float(rng.choice([0.1, 0.5, 2.])),
+                      bar_tempos=bool(rng.random() < 0.5), use_position_shifts=bool(rng.random() < 0.5),
+                      onset_position_shifts=bool(rng.random() < 0.5), rel_onset_dev=True, rel_perf_duration=bool(spm2 or rng.random() < 0.7))
+        if not spm2 and not params["rel_perf_duration"]:
+            continue                                       # absolute PerfDuration needs its own vocabulary column
+        ref_tok = ref._ref_tokenizer(ref.SPMuple2 if spm2 else ref.SPMuple, **params)
+        ref_m = (ref.SPMuple2Messenger if spm2 else ref.SPMupleMessenger)(ref_tok)
+        piece, cuts = cases.random_chunks(int(rng.integers(10000)), n_notes=int(rng.integers(30, 400)), metre_change=bool(rng.random() < 0.4))
+        runs = {}
+        for arm in ("reference", "native", "numpy"):
+            if arm == "reference":
+                m = ref_m
+            else:
+                os.environ["SPB_HOST_NATIVE"] = "1" if arm == "native" else "0"
+                m = (SPMuple2Messenger if spm2 else SPMupleMessenger)(TokenTables(**cases.table_kwargs(**params), spmuple2=spm2))
+            state, lo, out = None, 0, []
+            for hi in cuts:
+                if not spm2:
+                    out.append(m.tokens_to_messages(piece[lo:hi].copy(), intermediates=state, to_times=False, sort=True))
+                msgs, state = m.tokens_to_messages(piece[lo:hi].copy(), intermediates=state, return_intermediates=True,
+                                                   sort=bool(hi % 2))
+                out.append(msgs)
+                lo = hi
+            runs[arm] = (np.concatenate(out), np.asarray(state.tempos, dtype=np.float64),
+                         np.asarray(getattr(state, "onset_pairs", None) if spm2 else [[0.]], dtype=np.float64))
+        os.environ.pop("SPB_HOST_NATIVE", None)
+        for arm in ("native", "numpy"):
+            for a, b, what in zip(runs[arm], runs["reference"], ("messages", "tempo map", "onset pairs")):
+                same(a, b, f"case {i} ({'SPMuple2' if spm2 else 'SPMuple'}, {params}) {arm}: {what}")
