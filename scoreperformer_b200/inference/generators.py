@@ -102,7 +102,8 @@ class ScorePerformerGenerator:
 
     # ------------------------------------------------------------------ host mirrors of the small token tensors
     def _mirror(self, name: str, t: Tensor) -> np.ndarray:
-        """Host copy of `perf_data.<name>`, fetched once per tensor object (the caller may replace the tensor between calls)."""
+        """Host copy of `perf_data.<name>`, fetched once per tensor object: the caller may REPLACE the tensor between calls (a new
+        object is fetched again); edits made in place to the same tensor object are not seen -- assign a new tensor instead."""
         src, arr = self._mirrors.get(name, (None, None))
         if src is not t:
             arr = t.detach().cpu().numpy().copy()
@@ -342,6 +343,8 @@ def render_performances(model, messenger: SPMupleMessenger, collator, pieces, fi
     in modules/sampling.py:28-59).  Returns `[(gen_seq, messages), ...]` and completes every piece's `gen_seq` / `intermediates`."""
     from ..decode import render_batch
     tok = messenger.tokenizer
+    if not pieces or any(pd.notes is None or pd.context is None or pd.embeddings is None for pd in pieces):
+        raise ValueError("render_performances needs notes, score embeddings (context) and style embeddings for every piece")
     sos, eos = tok[0, SOS_TOKEN], tok[0, EOS_TOKEN]
     cols = sorted(set(range(len(tok.sizes))).difference(collator.mask_ignore_token_dims))
     dev = pieces[0].context.device
