@@ -6,7 +6,7 @@ Three arms render the same synthetic piece (oracle/inference_cases.make_piece: c
 windows:
   A  the UNMODIFIED reference generator + messenger (baseline/_ref) around the UNMODIFIED reference model on the host CPU (fp32, all
      cores; the first `--ref-notes` notes of the piece).  On the GPU the reference's cached decoding aborted with an illegal memory
-     access inside its eager forward on this image (first attempt of this script, gpurun_out/r02_inference_loop.log), so the CPU is
+     access inside its eager forward on this image (first attempt of this script, profiles/r02_reference_gpu_decode_abort.txt), so the CPU is
      where the reference arm runs;
   B  the reference generator + messenger around this repo's CUDA decoder (`unmask_tokens` with the reference's cache contract);
   C  scoreperformer_b200.inference.ScorePerformerGenerator + SPMuple2Messenger around the same CUDA decoder.
