@@ -418,3 +418,31 @@ def test_random_messenger_configurations_match_the_reference_live():
         for arm in ("native", "numpy"):
             for a, b, what in zip(runs[arm], runs["reference"], ("messages", "tempo map", "onset pairs")):
                 same(a, b, f"case {i} ({'SPMuple2' if spm2 else 'SPMuple'}, {params}) {arm}: {what}")
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="needs the unmodified reference (baseline/_ref or /root/reference)")
+def test_token_tables_decode_like_the_reference_tokenizer_live():
+    """Every field's `decode_token_type`, `compute_ticks` on random metre sequences and both `compute_position_shifts` modes, live
+    against the reference tokenizer's own methods (OctupleM / SPMuple) on the same tables."""
+    os.environ["SPB200_REFERENCE_ROOT"] = _reference_root()
+    import gen_inference_golden as ref
+    rng = np.random.default_rng(5)
+    tables = TokenTables(**cases.table_kwargs())
+    for base in (ref.SPMuple, ref.SPMuple2):
+        tok = ref._ref_tokenizer(base)
+        for trial in range(6):
+            piece = cases.make_piece(int(rng.integers(5, 300)), int(rng.integers(10000)), metre_change=bool(trial % 2))
+            if trial >= 3:                                  # several metre changes, compound metres included
+                bars = piece[:, 0] - 4
+                piece[:, 6] = 4 + (bars // int(rng.integers(2, 6))) % 22
+            for field in cases.FIELDS:
+                same(tables.decode_token_type(piece, field), tok.decode_token_type(piece, field), f"{base.__name__} {field}")
+            want, got = tok.compute_ticks(piece.copy(), 8, compute_beat_ticks=True), tables.compute_ticks(piece.copy(), 8, compute_beat_ticks=True)
+            for key in ("note_on", "bar", "beat"):
+                same(got[key], want[key], f"{base.__name__} ticks {key} (trial {trial})")
+            same(got["time_sig"][0], want["time_sig"][0], "metres")
+            same(got["time_sig"][1], want["time_sig"][1], "metre ticks")
+            on = np.sort(want["note_on"])
+            for mode in (True, False):
+                same(tables.compute_position_shifts(on.copy(), onset_shift=mode), tok.compute_position_shifts(on.copy(), onset_shift=mode),
+                     f"position shifts onset_shift={mode}")
