@@ -446,3 +446,55 @@ def test_token_tables_decode_like_the_reference_tokenizer_live():
             for mode in (True, False):
                 same(tables.compute_position_shifts(on.copy(), onset_shift=mode), tok.compute_position_shifts(on.copy(), onset_shift=mode),
                      f"position shifts onset_shift={mode}")
+
+
+def test_host_abi_from_a_c_program(tmp_path):
+    """The host C ABI without Python in the callee's process: tests/host_abi_client.c is compiled against include/spb200_host.h, linked
+    to libspb200_host.so, fed the arrays of a piece, and must return what the numpy recurrence computes."""
+    import shutil
+    import subprocess
+    from scoreperformer_b200.inference import native
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    lib_path = native.build()
+    exe = str(tmp_path / "client")
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["gcc", "-O1", "-std=c11", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host_abi_client.c"), "-o", exe,
+                    "-L", libdir, "-lspb200_host", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+
+    tok = TokenTables(**cases.table_kwargs())
+    p = tok.additional_params
+    piece = cases.make_piece(400, 12)
+    ticks = tok.compute_ticks(piece, 8)["note_on"].astype(float)
+    arrays = [ticks, tok.decode_token_type(piece, "Duration").astype(float), tok.decode_token_type(piece, "Tempo").astype(float),
+              tok.decode_token_type(piece, "RelOnsetDev").astype(float), tok.decode_token_type(piece, "RelPerfDuration").astype(float)]
+    performed = (piece[:, 3] != 4).astype(np.uint8)
+    order = np.argsort(ticks, kind="stable").astype(np.int64)
+    starts = np.flatnonzero(np.concatenate([[True], ticks[order][1:] != ticks[order][:-1]])).astype(np.int64)
+    bounds = np.concatenate([starts, [len(order)]]).astype(np.int64)
+    scale = 60 / 8
+    tempos0, pairs0 = np.array([[96., 0, 0.]]), np.array([[-1., -1 / 96. * scale, 1.]])
+    header = np.array([len(ticks), len(starts), 1, 1, 0, 1, p["tempo_min_onsets"], 1, len(tok.tempos), 0, 0, 0], dtype=np.int32)
+    scalars = np.array([scale, 96., p["tempo_min_onset_dist"], p["tempo_window"], 0.])
+    with open(tmp_path / "in.bin", "wb") as f:
+        for a in [header, scalars] + arrays + [performed, order, bounds, tempos0, pairs0, tok.tempos.astype(float)]:
+            f.write(np.ascontiguousarray(a).tobytes())
+    subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
+    raw = open(tmp_path / "out.bin", "rb").read()
+    n_t, n_p, resumed, _ = np.frombuffer(raw[:16], dtype=np.int32)
+    body = np.frombuffer(raw[16:], dtype=np.float64)
+    n = len(ticks)
+    on, off = body[:n], body[n:2 * n]
+    tempos, pairs = body[2 * n:2 * n + 3 * n_t].reshape(-1, 3), body[2 * n + 3 * n_t:].reshape(-1, 3)
+
+    want_on, want_off = np.zeros(n), np.zeros(n)
+    tok._current_midi_metadata = {"tempo_scale": scale}
+    groups = np.split(order, starts[1:])
+    state = SPMuple2IntermediateData(initial_tempo=96.)
+    want_t, want_p = SPMuple2Messenger._recurrence(tok, p, state, tempos0.copy(), pairs0.copy(), groups, *arrays, performed.astype(bool), scale,
+                                                   False, True, want_on, want_off)
+    assert resumed == 0 and n_t == len(want_t) and n_p == len(want_p)
+    same(on, want_on, "onset times")
+    same(off, want_off, "offset times")
+    same(tempos, want_t, "tempo map")
+    same(pairs, want_p, "onset pairs")
