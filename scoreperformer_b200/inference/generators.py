@@ -142,7 +142,18 @@ class ScorePerformerGenerator:
                                    delta_embedding: Optional[Tensor] = None, max_context_len: int = 512,
                                    group_chord_notes: bool = True, time_messages: bool = True, sort_messages: bool = False,
                                    filter_logits_fn: Callable = top_k, filter_kwargs: Optional[Dict[str, object]] = None,
-                                   disable_tqdm: bool = True, disable_caches: bool = False):
+                                   disable_tqdm: bool = True, disable_caches: bool = False, lookahead_notes: int = 0):
+        """One time window of the rendering (generators.py:106-295); arguments and results as in the reference.
+
+        `lookahead_notes` (an addition; 0 = the reference's call pattern, one decoder call per chord): render up to that many notes of
+        the following chords in the SAME decoder call, then walk the chords on the host exactly as if they had been rendered one by
+        one -- messenger, time-window test, cut -- and slice the returned caches back to the chord the reference would have stopped
+        at.  A decoder call has a fixed cost (weight staging, prepared terms) that dwarfs a note-step, so a window of several chords
+        costs one call instead of one per chord.  The kept tuples, messages, tempo state and caches are the same as without
+        lookahead whenever a note's rendering depends on earlier notes only (greedy decoding; with sampling the random draws of
+        notes beyond the window are simply discarded instead of never made).  Switched off where the call pattern matters:
+        when the Tempo field is an input refreshed from the messenger between chords, and wherever the window would reach
+        `max_context_len` (truncation decisions are the reference's, chord by chord)."""
         pd, tok = self.perf_data, self.tokenizer
         notes = self._mirror("notes", pd.notes)
         style_all = pd.embeddings.clone().detach() if pd.embeddings is not None else None
@@ -175,13 +186,25 @@ class ScorePerformerGenerator:
                 pd.reached_eos = True
                 break
 
+            # further whole chords for the same decoder call, as long as the window stays below the context limit without them
+            bounds = [cur, end]
+            room = max_context_len - 1 - (window.shape[0] + k)
+            while lookahead_notes > 0 and not refresh_tempo and bounds[-1] - cur < lookahead_notes:
+                nxt = chord_end(notes, bounds[-1]) if group_chord_notes else bounds[-1] + 1
+                if notes[nxt - 1, 0] == self.eos_token_id or nxt - end > room:
+                    break
+                bounds.append(nxt)
+            run_end = bounds[-1]
+
             window = np.concatenate([window, notes[cur:end]], axis=0)
             if window.shape[0] >= max_context_len:
                 shift = overflow_shift(window[:, 0], first, max_context_len)
                 window, known, start, first, caches = window[shift:], known - shift, start + shift, 0, None
                 if known < max_context_len / 8:
                     break                                  # more notes inside the time window than the context can hold
-            n = window.shape[0]
+            if run_end > end:
+                window = np.concatenate([window, notes[end:run_end]], axis=0)
+            n, k = window.shape[0], run_end - cur
 
             # what the model sees: bars counted from the window's first note, every rendered field of every note MASKed in the
             # second stream
@@ -192,9 +215,9 @@ class ScorePerformerGenerator:
             masked[first:, self._mask_cols] = self.collator.mask_token_id
 
             if style_all is not None and delta is not None:
-                style_all[cur:end] += delta
-            context = score_all[start:end].unsqueeze(0) if score_all is not None else None
-            style = style_all[start:end].unsqueeze(0) if style_all is not None else None
+                style_all[cur:run_end] += delta
+            context = score_all[start:run_end].unsqueeze(0) if score_all is not None else None
+            style = style_all[start:run_end].unsqueeze(0) if style_all is not None else None
             if caches is not None and (n - 1 - k != caches.token_emb.shape[1] or caches.token_emb.shape[1] == 0
                                        or len(caches.transformer.attention) == 0):
                 caches = None
@@ -204,17 +227,25 @@ class ScorePerformerGenerator:
                     torch.from_numpy(tokens).to(self.device), torch.from_numpy(masked).to(self.device),
                     context=context, style_embeddings=style, caches=None if disable_caches else caches, return_caches=True,
                     filter_logits_fn=filter_logits_fn, filter_kwargs=filter_kwargs, disable_tqdm=disable_tqdm)
-                fresh = out[n - k:n].cpu().numpy().copy()  # the one device->host read of the chord
+                fresh = out[n - k:n].cpu().numpy().copy()  # the one device->host read of the call
             ran = True
             fresh[:, 0] += to_zero
-            chord_times, state = self.messenger.tokens_to_messages(fresh, note_attributes=False, note_off_events=False,
-                                                                   intermediates=state, return_intermediates=True, sort=False)
-            times.extend(chord_times.tolist())
-            rendered.append(fresh)
-            if chord_times.max() >= start_time + time_window + time_window_overflow:
+            full = False
+            for a, b in zip(bounds[:-1], bounds[1:]):      # the chords of the call, one by one as the reference meets them
+                chord = fresh[a - cur:b - cur]
+                chord_times, state = self.messenger.tokens_to_messages(chord, note_attributes=False, note_off_events=False,
+                                                                       intermediates=state, return_intermediates=True, sort=False)
+                times.extend(chord_times.tolist())
+                rendered.append(chord)
+                if chord_times.max() >= start_time + time_window + time_window_overflow:
+                    full = True
+                    if b < run_end and caches is not None:  # chords rendered ahead of the one that filled the window never happened
+                        caches = self.cut_caches(caches, right_idx=n - 1 - (run_end - b))
+                    break
+                window[n - k + (a - cur):n - k + (b - cur)] = chord
+            if full:
                 break
-            window[n - k:] = fresh
-            cur = end
+            cur = run_end
 
         if not ran:
             return None, []

@@ -138,3 +138,58 @@ def test_render_performances_batches_whole_pieces():
         assert gen.perf_data.reached_eos and loop_seq.shape == (n, 12)
         agree = float((loop_seq[:, RENDERED] == seq[:, RENDERED]).float().mean())
         assert agree > 0.85, agree
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: never run on a GPU by its author (the host logic is "
+                                        "pinned on CPU in tests/test_inference_host.py; the device path is the one the tests above use, "
+                                        "with more notes per call) -- expected to pass, reported as XPASS when it does")
+def test_lookahead_rendering_on_device_equals_chord_by_chord_rendering():
+    """`lookahead_notes`: several chords per decoder call on the CUDA decoder must render what chord-by-chord calls render (greedy),
+    with fewer calls."""
+    from scoreperformer_b200.inference import ScorePerformerGenerator, SPMuple2IntermediateData, SPMuple2Messenger, TokenTables
+    from scoreperformer_b200.modules.sampling import top_k
+    T = 64
+    model = parity.build_model(dropout=False, device="cuda").eval()
+    batch, perf = _piece(T, seed=78)
+    b = {k: v.cuda() for k, v in batch.items()}
+    with torch.inference_mode():
+        enc = model.forward_encoders(perf=b["perf"], perf_mask=b["perf_mask"], score=b["score"], score_mask=b["score_mask"],
+                                     bars=b["bars"], beats=b["beats"], onsets=b["onsets"], deadpan_mask=b["deadpan_mask"],
+                                     compute_loss=False)
+    notes = perf.clone()
+    notes[1:, RENDERED] = 1
+    notes = torch.cat([notes, torch.full_like(notes[:1], 3)])
+    pad = lambda e: torch.cat([e[0], e[0, -1:]]).clone()
+    tok = TokenTables(**cases.table_kwargs())
+
+    def render(ahead):
+        gen = ScorePerformerGenerator(model, cases.make_dataset(tok, [perf.numpy()]), cases.make_collator(), SPMuple2Messenger(tok),
+                                      device="cuda")
+        pd = gen.perf_data
+        pd.notes, pd.context, pd.embeddings = notes.cuda(), pad(enc.score_embeddings), pad(enc.perf_embeddings)
+        pd.intermediates = SPMuple2IntermediateData(initial_tempo=96.)
+        calls, original = [0], model.perf_decoder.unmask_tokens
+
+        def counted(*a, **k):
+            calls[0] += 1
+            return original(*a, **k)
+
+        model.perf_decoder.unmask_tokens = counted
+        try:
+            t0, messages = 0., []
+            for _ in range(400):
+                _, m = gen.generate_performance_notes(start_time=t0, time_window=0.7, filter_logits_fn=top_k, filter_kwargs={"k": 1},
+                                                      lookahead_notes=ahead)
+                messages.extend(np.asarray(m).tolist())
+                t0 += 0.7
+                if pd.reached_eos:
+                    break
+        finally:
+            del model.perf_decoder.unmask_tokens
+        assert pd.reached_eos
+        return pd.gen_seq, np.array(messages), calls[0]
+
+    plain, plain_messages, plain_calls = render(0)
+    ahead, ahead_messages, ahead_calls = render(12)
+    assert torch.equal(plain, ahead) and np.array_equal(plain_messages, ahead_messages)
+    assert ahead_calls < plain_calls, (ahead_calls, plain_calls)

@@ -218,7 +218,7 @@ def test_loop_around_the_reference_model_matches_the_reference_loop():
     notes = np.concatenate([np.full_like(piece[:1], 2), piece, np.full_like(piece[:1], 3)])
     notes[1:-1, [3, 5, 10, 11]] = 1
 
-    def render(generator_cls, messenger, tokenizer, interm_cls, max_context_len):
+    def render(generator_cls, messenger, tokenizer, interm_cls, max_context_len, **extra):
         gen = generator_cls(ref_model, cases.make_dataset(tokenizer, [piece]), cases.make_collator(), messenger, device="cpu")
         pd = gen.perf_data
         pd.perf_seq, pd.notes = piece, torch.from_numpy(notes.copy())
@@ -227,7 +227,7 @@ def test_loop_around_the_reference_model_matches_the_reference_loop():
         t, messages = 0., []
         for _ in range(150):
             _, m = gen.generate_performance_notes(start_time=t, time_window=0.5, max_context_len=max_context_len,
-                                                  filter_logits_fn=ref_top_k, filter_kwargs={"k": 1})
+                                                  filter_logits_fn=ref_top_k, filter_kwargs={"k": 1}, **extra)
             if len(m):
                 messages.append(np.asarray(m))
             t += 0.5
@@ -246,6 +246,12 @@ def test_loop_around_the_reference_model_matches_the_reference_loop():
         got_tokens, got_messages = render(ScorePerformerGenerator, SPMuple2Messenger(tables), tables, SPMuple2IntermediateData, ctx)
         same(got_tokens, want_tokens, f"tokens (context {ctx})")
         same(got_messages, want_messages, f"messages (context {ctx})")
+        # several chords per decoder call (the reference model's own cached unmask_tokens renders them): same rendering, greedy
+        if ctx == 512:
+            ahead_tokens, ahead_messages = render(ScorePerformerGenerator, SPMuple2Messenger(tables), tables, SPMuple2IntermediateData, ctx,
+                                                  lookahead_notes=10)
+            same(ahead_tokens, want_tokens, "tokens with lookahead")
+            same(ahead_messages, want_messages, "messages with lookahead")
         assert got_tokens.shape[0] >= 16 and not (got_tokens == 1).any()
 
 
@@ -498,3 +504,33 @@ def test_host_abi_from_a_c_program(tmp_path):
     same(off, want_off, "offset times")
     same(tempos, want_t, "tempo map")
     same(pairs, want_p, "onset pairs")
+
+
+@pytest.mark.parametrize("name", list(cases.SCENARIOS))
+@pytest.mark.parametrize("ahead", [6, 40])
+def test_lookahead_rendering_keeps_the_reference_results(gen_golden, name, ahead):
+    """`lookahead_notes`: several chords per decoder call.  Everything a caller sees -- kept tuples, messages, tempo map, onset pairs,
+    cache length after every window, the written-back style embeddings, the final sequence -- must equal the reference's goldens;
+    only the number of decoder calls drops."""
+    g = gen_golden
+    piece_kw, params, ignore, gen_kw, window, kind = cases.SCENARIOS[name]
+    variant = f"{name}_ahead{ahead}"
+    cases.SCENARIOS[variant] = (piece_kw, params, ignore, dict(gen_kw, lookahead_notes=ahead), window, kind)
+    try:
+        windows, final = cases.run_scenario(variant, ScorePerformerGenerator, SPMuple2Messenger, TokenTables(**cases.table_kwargs(**params)),
+                                            (Caches, Inter, Attn), SPMuple2IntermediateData)
+    finally:
+        cases.SCENARIOS.pop(variant)
+    assert len(windows) == int(g[f"{name}/n_windows"])
+    calls = ref_calls = 0
+    for i, w in enumerate(windows):
+        for k, v in w.items():
+            if k != "calls":
+                same(v, g[f"{name}/w{i}/{k}"], f"{variant} window {i} {k}")
+        calls, ref_calls = calls + len(w["calls"]), ref_calls + len(g[f"{name}/w{i}/calls"])
+    for k in ("gen_seq", "notes"):
+        same(final[k], g[f"{name}/final/{k}"], f"{variant} final {k}")
+    if name == "tempo_is_input":
+        assert calls == ref_calls                           # lookahead is off when Tempo is refreshed between chords
+    else:
+        assert calls < ref_calls, (calls, ref_calls)
