@@ -9,7 +9,8 @@ windows:
      access inside its eager forward on this image (first attempt of this script, profiles/r02_reference_gpu_decode_abort.txt), so the CPU is
      where the reference arm runs;
   B  the reference generator + messenger around this repo's CUDA decoder (`unmask_tokens` with the reference's cache contract);
-  C  scoreperformer_b200.inference.ScorePerformerGenerator + SPMuple2Messenger around the same CUDA decoder.
+  C  scoreperformer_b200.inference.ScorePerformerGenerator + SPMuple2Messenger around the same CUDA decoder;
+  D  (--lookahead N) C with several chords per decoder call; must render what C renders.
 B and C hand the decoder the same windows, so their tokens and messages must be IDENTICAL (asserted); A is the timing of the
 reference end to end (its encoders see the shorter piece, so its tokens are not compared here -- tests/test_decode_gpu.py does that).  Wall clock per rendered note with a synchronize on both sides, after a warm-up rendering.
 `--fake` replaces the model by oracle/inference_cases.FakeDecoder (CPU; for checking the script itself).
@@ -57,7 +58,7 @@ def encode(model, piece, device):
     return pad(enc.score_embeddings), pad(enc.perf_embeddings)
 
 
-def render(generator_cls, messenger, tokenizer, model, piece, emb, interm_cls, top_k, window, device):
+def render(generator_cls, messenger, tokenizer, model, piece, emb, interm_cls, top_k, window, device, **extra):
     gen = generator_cls(model, cases.make_dataset(tokenizer, [piece]), cases.make_collator(), messenger, device=device)
     notes = np.concatenate([np.full_like(piece[:1], 2), piece, np.full_like(piece[:1], 3)])
     notes[1:-1, RENDERED] = 1
@@ -71,7 +72,7 @@ def render(generator_cls, messenger, tokenizer, model, piece, emb, interm_cls, t
         torch.cuda.synchronize()
     t0, t, windows, messages = time.perf_counter(), 0., 0, []
     while not pd.reached_eos and windows < 5000:
-        _, m = gen.generate_performance_notes(start_time=t, time_window=window, filter_logits_fn=top_k, filter_kwargs={"k": 1})
+        _, m = gen.generate_performance_notes(start_time=t, time_window=window, filter_logits_fn=top_k, filter_kwargs={"k": 1}, **extra)
         if len(m):
             messages.append(np.asarray(m))
         t += window
@@ -89,6 +90,7 @@ def main():
     ap.add_argument("--notes", type=int, default=300)
     ap.add_argument("--window", type=float, default=0.5)
     ap.add_argument("--ref-notes", type=int, default=60)
+    ap.add_argument("--lookahead", type=int, default=0, help="arm D: this package's loop with lookahead_notes=N (0 = skip)")
     ap.add_argument("--fake", action="store_true")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -124,6 +126,12 @@ def main():
             mdl.perf_decoder.log.clear()
         arms[name] = render(gcls, msgr, tok, mdl, piece, embs[name][1], icls, tk, args.window, device)
 
+    if args.lookahead > 0:                             # arm D: several chords per decoder call
+        name, gcls, msgr, tok, mdl, icls, tk = plan[-1]
+        render(gcls, msgr, tok, mdl, warm, embs[name][0], icls, tk, args.window, device, lookahead_notes=args.lookahead)
+        arms["D"] = render(gcls, msgr, tok, mdl, piece, embs[name][1], icls, tk, args.window, device, lookahead_notes=args.lookahead)
+        assert np.array_equal(arms["D"]["tokens"], arms["C"]["tokens"]), "lookahead changed the rendering"
+
     if not args.fake and args.ref_notes > 0:          # arm A on the host cores
         torch.set_num_threads(os.cpu_count() or 1)
         ref_model, _ = ref_shim.build_reference_model(seed=23)
@@ -141,7 +149,8 @@ def main():
     lines = [f"rendering loop on {torch.cuda.get_device_name(0) if device != 'cpu' else 'cpu (fake decoder)'}: {n} notes, "
              f"{args.window} s windows, greedy; B and C: tokens and {len(c['messages'])} messages identical"]
     label = {"A": f"reference generator + reference model, CPU fp32, {os.cpu_count()} threads", "B": "reference generator + CUDA decoder of this repo",
-             "C": "scoreperformer_b200.inference + CUDA decoder of this repo"}
+             "C": "scoreperformer_b200.inference + CUDA decoder of this repo",
+             "D": f"the same with lookahead_notes={args.lookahead}"}
     for name in sorted(arms):
         r = arms[name]
         k = r.get("notes", n)
