@@ -29,7 +29,7 @@ ref_shim.install_stubs()
 import inference_cases as cases  # noqa: E402
 from scoreperformer.data.tokenizers import SPMuple, SPMuple2  # noqa: E402
 from scoreperformer.inference.generators import ScorePerformerGenerator  # noqa: E402
-from scoreperformer.inference.messengers import SPMupleMessenger, SPMuple2Messenger, IntermediateData, SPMuple2IntermediateData  # noqa: E402
+from scoreperformer.inference.messengers import SPMupleMessenger, SPMuple2Messenger, SPMuple2IntermediateData  # noqa: E402
 from scoreperformer.models.scoreperformer import TupleTransformerCaches  # noqa: E402
 from scoreperformer.modules.transformer import AttentionIntermediates, TransformerIntermediates  # noqa: E402
 from scoreperformer.utils import find_closest  # noqa: E402

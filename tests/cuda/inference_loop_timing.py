@@ -105,7 +105,6 @@ def main():
         from scoreperformer_b200.modules.sampling import top_k
         model_b = cases.make_model(cases.FakeDecoder(ref.REF_CACHES))
         model_c = cases.make_model(cases.FakeDecoder((Caches, Inter, Attn)))
-        emb_w = emb = None
         plan = [("B", ref.ScorePerformerGenerator, ref.SPMuple2Messenger(ref_tok), ref_tok, model_b, ref.SPMuple2IntermediateData, top_k),
                 ("C", ScorePerformerGenerator, SPMuple2Messenger(tables), tables, model_c, SPMuple2IntermediateData, top_k)]
         embs = {"B": (None, None), "C": (None, None)}
