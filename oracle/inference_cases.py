@@ -182,7 +182,8 @@ def run_scenario(name, generator_cls, messenger_cls, tokenizer, cache_classes, i
             calls=np.array(decoder.log[before:], dtype=np.float64).reshape(-1, 11),
             seq=np.zeros((0, 12), np.int64) if seq is None else seq.cpu().numpy(),
             messages=np.zeros((0, 4)) if len(messages) == 0 else np.asarray(messages, dtype=np.float64),
-            tempos=np.zeros((0, 3)) if pd.intermediates.tempos is None else np.array(pd.intermediates.tempos, dtype=np.float64),
+            tempos=np.zeros((0, 3)) if pd.intermediates is None or pd.intermediates.tempos is None
+            else np.array(pd.intermediates.tempos, dtype=np.float64),
             pairs=np.zeros((0, 3)) if getattr(pd.intermediates, "onset_pairs", None) is None
             else np.array(pd.intermediates.onset_pairs, dtype=np.float64),
             state=np.array([-1 if pd.caches is None else pd.caches.token_emb.shape[1], int(pd.reached_eos),

@@ -367,12 +367,15 @@ def test_random_renderings_match_the_reference_loop_live():
                                  float(rng.choice([0.25, 0.5, 1.0, 2.5])), "spm2")
         names.append(name)
     try:
-        for name in names:
+        for j, name in enumerate(names):
             params = cases.SCENARIOS[name][1]
-            want = cases.run_scenario(name, ref.ScorePerformerGenerator, ref.SPMuple2Messenger, ref._ref_tokenizer(ref.SPMuple2, **params),
-                                      ref.REF_CACHES, ref.SPMuple2IntermediateData)
-            got = cases.run_scenario(name, ScorePerformerGenerator, SPMuple2Messenger, TokenTables(**cases.table_kwargs(**params)),
-                                     (Caches, Inter, Attn), SPMuple2IntermediateData)
+            spm2 = j % 5 != 4                               # every fifth case: the SPMuple family (tick-based messenger, no tempo state)
+            want = cases.run_scenario(name, ref.ScorePerformerGenerator, ref.SPMuple2Messenger if spm2 else ref.SPMupleMessenger,
+                                      ref._ref_tokenizer(ref.SPMuple2 if spm2 else ref.SPMuple, **params), ref.REF_CACHES,
+                                      ref.SPMuple2IntermediateData)
+            got = cases.run_scenario(name, ScorePerformerGenerator, SPMuple2Messenger if spm2 else SPMupleMessenger,
+                                     TokenTables(**cases.table_kwargs(**params), spmuple2=spm2), (Caches, Inter, Attn),
+                                     SPMuple2IntermediateData)
             assert len(got[0]) == len(want[0]), (name, cases.SCENARIOS[name])
             for i, (a, b) in enumerate(zip(got[0], want[0])):
                 for k in a:
