@@ -210,3 +210,85 @@ def test_trainer_sampler_shards_an_epoch():
     batch = collate_rows([data[i] for i in shards[0][:3]])
     assert batch["perf"].shape[0] == 3 and set(batch) == set(data[0])
 
+
+
+def test_streaming_unmask_dispatch(monkeypatch):
+    """decode.unmask_mixlm decides on the host which path a request takes; the decisions (and the caches handed in and out) are checked
+    here with the device paths replaced by recorders: a fresh window and a window continuing caller-held caches go to the
+    device-resident note-step with the right start / keys|values, everything it cannot express goes to the general stepper."""
+    import types
+    import torch
+    from scoreperformer_b200 import decode
+    from scoreperformer_b200.modules.sampling import top_k, top_p
+    from scoreperformer_b200.models.scoreperformer.transformer import TupleTransformerCaches
+    from scoreperformer_b200.modules.transformer.attend import AttentionIntermediates
+    from scoreperformer_b200.modules.transformer.transformer import TransformerIntermediates
+
+    sizes = [260, 132, 92, 132, 133, 125, 26, 69, 16, 16, 165, 85]
+    dec = types.SimpleNamespace(training=False, dim=256, token_emb=types.SimpleNamespace(field_sizes=sizes),
+                                transformer=types.SimpleNamespace(depth=4), eval=lambda: None, train=lambda mode=True: None)
+    wrapper = types.SimpleNamespace(model=dec, mask_token_id=1, pad_token_id=0)
+    calls = []
+
+    def fake_render(d, out, masked, context, style, **kw):
+        calls.append(("device", kw))
+        res = out.clone()
+        res[res == 1] = 7
+        if kw.get("return_kv"):
+            T = out.shape[1]
+            return res, [torch.arange(T, dtype=torch.float32)[None, :, None].expand(out.shape[0], T, 128).to(torch.bfloat16).clone()
+                         for _ in range(4)]
+        return res
+
+    def fake_stepper(w, out, masked, mask, notes, hit, *rest):
+        calls.append(("stepper", rest[-2]))
+        res = out.clone()
+        res[res == 1] = 9
+        return res, "stepper-caches"
+
+    monkeypatch.setattr(decode, "render_decoder", fake_render)
+    monkeypatch.setattr(decode, "_unmask_stepwise", fake_stepper)
+
+    def window(n, k):
+        t = torch.randint(4, 16, (1, n, 12))
+        t[:, n - k:, [3, 5, 10, 11]] = 1
+        m = t.clone()
+        m[:, :, [3, 5, 10, 11]] = 1
+        return t, m, torch.zeros(1, n, 256), torch.zeros(1, n, 64)
+
+    def run(n, k, caches=None, return_caches=True, fn=top_k, kw={"k": 1}, **extra):
+        t, m, ctx, sty = window(n, k)
+        calls.clear()
+        return decode.unmask_mixlm(wrapper, t, m, 1.0, fn, kw, None, caches, return_caches, context=ctx, style_embeddings=sty, **extra)
+
+    # fresh window, caches requested: device path from position 0, caches in the reference's layout come back
+    out, caches = run(4, 3)
+    assert calls[0][0] == "device" and calls[0][1]["start"] == 0 and calls[0][1]["kv_init"] == [] and calls[0][1]["use_graph"] is False
+    assert int((out == 1).sum()) == 0 and isinstance(caches, TupleTransformerCaches)
+    assert caches.token_emb.shape == (1, 3, 256) and len(caches.transformer.hiddens) == 5 and len(caches.transformer.attention) == 4
+    assert caches.transformer.attention[0].keys.shape == (1, 3, 64) and caches.transformer.attention[0].values.shape == (1, 3, 64)
+    # continuing those caches with two new notes: starts at the cache length, keys | values are handed over as [B, start, 128] bf16
+    out, caches2 = run(6, 2, caches=caches)
+    kind, kw = calls[0]
+    assert kind == "device" and kw["start"] == 3 and len(kw["kv_init"]) == 4
+    assert kw["kv_init"][0].shape == (1, 3, 128) and kw["kv_init"][0].dtype == torch.bfloat16
+    assert torch.equal(kw["kv_init"][0][0, :, 0].float(), torch.arange(3.)) and caches2.token_emb.shape[1] == 5
+    # caches in the stepper's own format (real hiddens) are accepted as well: only keys and values are read
+    full = TupleTransformerCaches(token_emb=torch.ones(1, 3, 256), transformer=TransformerIntermediates(
+        hiddens=[torch.ones(1, 3, 256)] * 5, attention=[AttentionIntermediates(torch.ones(1, 3, 64), torch.zeros(1, 3, 64)) for _ in range(4)]))
+    run(6, 2, caches=full)
+    assert calls[0][0] == "device" and calls[0][1]["start"] == 3 and float(calls[0][1]["kv_init"][2][0, 1, 0]) == 1.0
+    # what the note-step cannot express goes to the general stepper: cache length != known prefix, unknown filter, no caches behind
+    # a known prefix, the legacy switch; the one-shot request without caches keeps the captured-graph path
+    run(7, 2, caches=caches)
+    assert calls[0][0] == "stepper"
+    run(6, 2, caches=caches, fn=top_p, kw={"thres": 0.5})
+    assert calls[0][0] == "stepper"
+    run(6, 2, caches=None)
+    assert calls[0][0] == "stepper"
+    monkeypatch.setenv("SPB_STREAM", "legacy")
+    run(6, 2, caches=caches)
+    assert calls[0][0] == "stepper"
+    monkeypatch.delenv("SPB_STREAM")
+    out = run(4, 3, return_caches=False)
+    assert calls[0][0] == "device" and "start" not in calls[0][1] and int((out == 1).sum()) == 0
